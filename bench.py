@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- `taxor search` hot-path throughput on B200 (BASELINE.json metric: Mbases/s, syncmer hash + HIXF query).
+
+A "step" is one pass of the hot path over this rank's read set (configs[1]: 1 M synthetic 10 kb reads per GPU
+against a synthetic 1,000-genome HIXF, k=22 s=12).  Reads are sharded across ranks, the index is replicated,
+there is no data-path collective (scaling = weak: per-GPU work is fixed).
+
+  value  : reads resident in HBM when the timed region starts (kernels only), CUDA events on the launch stream
+  e2e    : the same through txr_search() from pinned HOST buffers, H2D + kernels + D2H + host ordering per step
+  roofline    : kernel #2 (IXF probe/count), algorithmic bytes / CUDA-event duration vs the measured HBM peak
+  cpu_baseline: the CPU oracle port (OpenMP, all host cores) on a bounded sample of the same reads (rank 0, N=1)
+
+`--impl reference` times the reference's CPU algorithm (oracle port; see DESIGN.md for why not oracle/_ref)
+on the host cores for the same workload, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "taxor search Mbases/s (syncmer hash+HIXF query)"
+UNIT = "Mbases/s"
+K, S, T = 22, 12, 5
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("TAXOR_BENCH_READS", 1_000_000)), help="reads per GPU per step")
+    ap.add_argument("--read-len", type=int, default=10_000)
+    ap.add_argument("--genomes", type=int, default=int(os.environ.get("TAXOR_BENCH_GENOMES", 1000)))
+    ap.add_argument("--genome-len", type=int, default=int(os.environ.get("TAXOR_BENCH_GENOME_LEN", 1_000_000)), help="mean genome length")
+    ap.add_argument("--t-max", type=int, default=64)
+    ap.add_argument("--read-error", type=float, default=0.05)
+    ap.add_argument("--error-rate", type=float, default=0.10, help="taxor search --error-rate (see DESIGN.md workload)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cache", default=os.environ.get("TAXOR_BENCH_CACHE", "/dev/shm/taxor_b200_bench"))
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------
+def genome_lengths(n, mean, seed=7):
+    """RefSeq-ABFV-like size mix: log-uniform over a 16x range around the mean (small 'viral' to large genomes)."""
+    rng = np.random.default_rng(seed)
+    x = np.exp(rng.uniform(np.log(0.25), np.log(4.0), n))
+    x = x / x.mean() * mean
+    return np.maximum(x.astype(np.int64), 20_000)
+
+
+def make_genomes(args):
+    from taxor_b200 import tools
+    lens = genome_lengths(args.genomes, args.genome_len)
+    return [tools.genome(1000 + g, int(lens[g])) for g in range(args.genomes)], lens
+
+
+def index_cache_paths(args):
+    tag = f"g{args.genomes}_l{args.genome_len}_t{args.t_max}_k{K}s{S}"
+    d = os.path.join(args.cache, tag)
+    return d, os.path.join(d, "DONE")
+
+
+def build_index_arrays(args, genomes, lens, ctx):
+    """Hashes every genome with kernel #1 on the GPU, then lays out + peels the HIXF on the CPU (tooling)."""
+    from taxor_b200 import capi, tools
+    t0 = time.time()
+    ub = []
+    ctx.set_params(k=K, s=S, t=T, use_syncmer=True, window_size=20, error_rate=args.error_rate)
+    chunk = 64
+    for a in range(0, len(genomes), chunk):
+        part = genomes[a:a + chunk]
+        nw = np.array([len(w) for w in part], dtype=np.uint64)
+        off = np.zeros(len(part), dtype=np.uint64)
+        off[1:] = np.cumsum(nw)[:-1]
+        reads = capi.PackedReads(np.concatenate(part), off, np.asarray(lens[a:a + chunk], dtype=np.uint32))
+        o, h = ctx.hash_batch(reads, dedup=False)
+        for i in range(len(part)):
+            ub.append(h[int(o[i]):int(o[i + 1])])
+    t1 = time.time()
+    hx = tools.BuiltHixf(ub, t_max=args.t_max, seed=1)
+    t2 = time.time()
+    info = dict(hash_s=round(t1 - t0, 2), build_s=round(t2 - t1, 2), n_ixf=hx.n_ixf, fp_bytes=hx.fp_bytes,
+                n_hashes=int(sum(len(x) for x in ub)), reseeds=hx.reseeds)
+    return hx, info
+
+
+def save_index(hx, d, info):
+    os.makedirs(d, exist_ok=True)
+    np.save(os.path.join(d, "meta.npy"), np.stack([hx.seed, hx.bins, hx.tbins, hx.seg_len]))
+    np.save(os.path.join(d, "bin_off.npy"), hx.bin_off)
+    np.save(os.path.join(d, "next.npy"), hx.next_ixf_id)
+    np.save(os.path.join(d, "ub.npy"), hx.bin_to_ub)
+    sizes = np.array([x.size for x in hx.data], dtype=np.uint64)
+    np.save(os.path.join(d, "sizes.npy"), sizes)
+    with open(os.path.join(d, "fp.bin"), "wb") as f:
+        for x in hx.data:
+            f.write(memoryview(x))
+    with open(os.path.join(d, "info.json"), "w") as f:
+        json.dump(dict(info, n_user_bins=hx.n_user_bins), f)
+    open(os.path.join(d, "DONE"), "w").close()
+
+
+class LoadedIndex:
+    def __init__(self, d):
+        m = np.load(os.path.join(d, "meta.npy"))
+        self.seed, self.bins, self.tbins, self.seg_len = m[0], m[1], m[2], m[3]
+        self.bin_off = np.load(os.path.join(d, "bin_off.npy"))
+        self.next_ixf_id = np.load(os.path.join(d, "next.npy"))
+        self.bin_to_ub = np.load(os.path.join(d, "ub.npy"))
+        sizes = np.load(os.path.join(d, "sizes.npy"))
+        fp = np.memmap(os.path.join(d, "fp.bin"), dtype=np.uint8, mode="r")
+        self.data, at = [], 0
+        for s in sizes:
+            self.data.append(fp[at:at + int(s)])
+            at += int(s)
+        with open(os.path.join(d, "info.json")) as f:
+            self.info = json.load(f)
+        self.n_user_bins = self.info["n_user_bins"]
+        self.n_ixf = len(self.seed)
+        self.fp_bytes = int(sizes.sum())
+
+
+def upload_index(ctx, ix):
+    data = [np.ascontiguousarray(x) for x in ix.data]
+    ctx.upload_index(ix.seed, ix.bins, ix.tbins, ix.seg_len, data, ix.bin_off, ix.next_ixf_id, ix.bin_to_ub, ix.n_user_bins)
+
+
+def make_reads(args, genomes, lens, rank):
+    """This rank's shard of the read set, simulated straight into pinned host memory."""
+    from taxor_b200 import capi, tools
+    n = args.reads
+    nw_per = tools.packed_words(args.read_len)
+    pin = capi.PinnedArray(n * nw_per, np.uint64)
+    pin.array[:] = 0
+    words, off, ln, src = tools.simulate_reads(genomes, lens, np.full(n, args.read_len, np.uint32), args.read_error,
+                                               seed=42 + 7919 * rank, out_words=pin.array)
+    off_pin = capi.PinnedArray(n, np.uint64)
+    off_pin.array[:] = off
+    len_pin = capi.PinnedArray(n, np.uint32)
+    len_pin.array[:] = ln
+    return pin, off_pin, len_pin
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port)
+# ----------------------------------------------------------------------------------------------------------
+def cpu_run(args, ix, pin_words, off, ln, n_sample, threads):
+    """Times oracle.search_batch (restated CPU path, OpenMP over reads) on the first n_sample reads."""
+    from oracle.oracle import HixfArrays, Oracle
+    from taxor_b200 import capi
+    o = Oracle()
+    arrays = HixfArrays(np.ascontiguousarray(ix.seed), np.ascontiguousarray(ix.bins), np.ascontiguousarray(ix.tbins),
+                        np.ascontiguousarray(ix.seg_len), [np.ascontiguousarray(x) for x in ix.data],
+                        np.ascontiguousarray(ix.bin_off), np.ascontiguousarray(ix.next_ixf_id), np.ascontiguousarray(ix.bin_to_ub))
+    h = o.make_hixf(arrays)
+    reads = capi.PackedReads(pin_words, off, ln)
+    codes = np.empty(int(ln[:n_sample].astype(np.uint64).sum()), dtype=np.uint8)
+    coff = np.zeros(n_sample + 1, dtype=np.uint64)
+    at = 0
+    for i in range(n_sample):
+        c = capi.unpack_codes(reads, i)
+        codes[at:at + len(c)] = c
+        at += len(c)
+        coff[i + 1] = at
+    t0 = time.perf_counter()
+    res = o.search_batch(h, codes, coff, k=K, s=S, t=T, use_syncmer=True, window_size=20, error_rate=args.error_rate,
+                         threads=threads, want_raw=False)
+    dt = time.perf_counter() - t0
+    return at / dt / 1e6, dt, res
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference" and rank != 0:
+        return 0
+
+    import __graft_entry__ as ge
+    from taxor_b200 import capi
+    import taxor_b200
+    if not (os.path.exists(taxor_b200.LIB_PATH) and os.path.exists(taxor_b200.TOOLS_PATH)):
+        ge.build()
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1 and args.impl == "ours":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = capi.Context(local_rank)
+    genomes, lens = make_genomes(args)
+
+    # ---- index: rank 0 builds (GPU hashing + CPU peeling), everybody loads it from /dev/shm ----
+    d, done = index_cache_paths(args)
+    if rank == 0 and not os.path.exists(done):
+        hx, info = build_index_arrays(args, genomes, lens, ctx)
+        save_index(hx, d, info)
+        hx.close()
+    if dist is not None:
+        dist.barrier()
+    ix = LoadedIndex(d)
+    upload_index(ctx, ix)
+    ctx.set_params(k=K, s=S, t=T, use_syncmer=True, window_size=20, error_rate=args.error_rate)
+
+    pin, off_pin, len_pin = make_reads(args, genomes, lens, rank)
+    n_reads = args.reads
+    bases_per_step = int(len_pin.array.astype(np.uint64).sum())
+    reads = capi.PackedReads(pin.array, off_pin.array, len_pin.array)
+
+    workload = {"workload": f"configs[1]: {args.genomes} synthetic genomes (mean {args.genome_len} bp, 16x log-uniform size mix), "
+                            f"k={K} s={S} t={T} syncmers, HIXF t_max={args.t_max} ({ix.n_ixf} IXFs, {ix.fp_bytes / 1e9:.2f} GB fingerprints); "
+                            f"{n_reads} reads x {args.read_len} bp per GPU, {args.read_error:.0%} error, --error-rate {args.error_rate}",
+                "reads_per_gpu": n_reads, "read_len": args.read_len, "index_bytes": ix.fp_bytes,
+                "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective",
+                "l2": "inputs larger than L2 (packed reads and index each exceed 126 MB); no flush needed"}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        n_s = min(n_reads, 2000)
+        v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
+        n_s = int(min(n_reads, max(200, n_s * args.cpu_seconds / max(dt, 1e-3))))
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        value = float(np.mean([x[0] for x in vals]))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": float(np.mean([x[1] for x in vals]) * 1e3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{n_s} of the {n_reads} reads per step (restated CPU path, OpenMP over reads; not the reference binary)"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # (1) device-resident: kernels only.  One pipeline slot so that the per-stage CUDA events are not overlapped
+    ctx.configure(n_slots=1)
+    h = ctx.upload_reads(reads)
+    for _ in range(args.warmup):
+        ctx.search_resident(h, fetch=False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {"hash_ms": 0.0, "dedup_ms": 0.0, "query_ms": 0.0, "query_bytes": 0, "hash_bytes": 0, "launches": 0, "query_launches": 0,
+             "query_items": 0, "n_hashes": 0}
+    with torch.cuda.stream(stream):
+        ev0.record()
+        for _ in range(args.steps):
+            ctx.search_resident(h, fetch=False)
+            tm = ctx.timing()
+            for kname in ("hash_ms", "dedup_ms", "query_ms", "query_bytes", "query_items"):
+                stage[kname] += tm[kname]
+            stage["launches"] += tm["hash_launches"] + tm["dedup_launches"] + tm["query_launches"]
+            stage["query_launches"] += tm["query_launches"]
+        ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    resident_ms = float(ms.item())
+    ctx.free_reads(h)
+
+    # (2) end to end from pinned host buffers through txr_search (3 pipeline slots)
+    ctx.configure(n_slots=3)
+    for _ in range(max(1, min(args.warmup, 2))):
+        ctx.search_raw(pin.ptr, off_pin.ptr, len_pin.ptr, n_reads)
+    barrier()
+    n_hits = 0
+    with torch.cuda.stream(stream):
+        ev0.record()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = ctx.search_raw(pin.ptr, off_pin.ptr, len_pin.ptr, n_reads)
+            n_hits = int(r.hit_begin[n_reads])
+        ev1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = torch.tensor([max(ev0.elapsed_time(ev1), 0.0)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms.item())
+    tm_e2e = ctx.timing()
+
+    total_bases = bases_per_step * world
+    value = total_bases * args.steps / (resident_ms / 1e3) / 1e6
+    e2e_value = total_bases * args.steps / (e2e_ms / 1e3) / 1e6
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        q_gbs = stage["query_bytes"] / (stage["query_ms"] / 1e3) / 1e9 if stage["query_ms"] > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": "ixf_query_small_kernel (kernel #2, all HIXF levels of a batch)",
+                "achieved": q_gbs, "peak": peak, "unit": "GB/s", "frac": q_gbs / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic": None,
+                "avg_launch_ms": stage["query_ms"] / max(stage["query_launches"], 1),
+                "algorithmic_bytes_per_step": stage["query_bytes"] / args.steps,
+                "stage_ms_per_step": {"hash": stage["hash_ms"] / args.steps, "dedup": stage["dedup_ms"] / args.steps,
+                                      "query": stage["query_ms"] / args.steps}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            n_s = min(n_reads, 1000)
+            v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
+            n_s = int(min(n_reads, max(200, n_s * args.cpu_seconds / max(dt, 1e-3))))
+            v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"first {n_s} of the {n_reads} reads, {dt:.1f} s (restated CPU path with OpenMP over reads; not the reference binary)"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic", "config": workload,
+                "reads_per_s": n_reads * world * args.steps / (resident_ms / 1e3),
+                "e2e": {"value": e2e_value, "unit": UNIT,
+                        "h2d_bytes_per_step": int(pin.nbytes + off_pin.nbytes + len_pin.nbytes + 8 * (n_reads + 1)),
+                        "d2h_bytes_per_step": int(4 * n_reads + 12 * n_hits + 576 * ((n_reads + 131071) // 131072)),
+                        "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "hits_per_step": n_hits,
+                        "stage_ms_per_step_overlapped": {kk: tm_e2e[kk] for kk in ("h2d_ms", "hash_ms", "dedup_ms", "query_ms", "d2h_ms")}},
+                "gpu_launches": int(stage["launches"]),
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                "index_build": ix.info, "host_cores": cores}
+        print(json.dumps(line))
+    pin.free()
+    off_pin.free()
+    len_pin.free()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

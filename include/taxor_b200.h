@@ -1,0 +1,151 @@
+/*
+ * taxor_b200.h -- C ABI of the B200-native `taxor search` hot path (libtaxor_b200.so).
+ *
+ * The reference (JensUweUlrich/Taxor) has no FFI layer; its natural seam is the body of the `worker`
+ * lambda in src/main/taxor_search.cpp:196-313, i.e. exactly two calls per read
+ *     hashing::seq_to_syncmers(k, seq, s, t)                       src/main/taxor_search.cpp:222
+ *     membership_agent::bulk_contains(hashes, threshold)           src/main/taxor_search.cpp:265
+ * plus thresholder.get() (:263) and the 0.8*max filter (:275-286).  A GPU needs batches, so every entry
+ * point below is the batch-granular replacement of one of those calls; INTEGRATION.md shows the binding a
+ * maintainer would add to search_single().  All `file:line` citations are relative to /root/reference/.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 (TXR_OK) or a negative error code
+ * and never throws; handles are opaque; the caller owns every host buffer it passes in; result views stay
+ * valid until the next call on the same context or txr_result_free(); one context per GPU; calls on one
+ * context must be serialised by the caller; distinct contexts may be used from distinct host threads.
+ * There is NO CPU fallback: without a CUDA device txr_ctx_create fails with TXR_ERR_CUDA.
+ */
+#ifndef TAXOR_B200_H
+#define TAXOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TXR_OK 0
+#define TXR_ERR_CUDA (-1)        /* CUDA runtime error; see txr_last_error() */
+#define TXR_ERR_ARG (-2)         /* invalid argument */
+#define TXR_ERR_STATE (-3)       /* call order (no index / params yet) */
+#define TXR_ERR_UNSUPPORTED (-4) /* parameter combination outside the GPU path (e.g. window_size > k) */
+#define TXR_ERR_FORMAT (-5)      /* malformed input (illegal base, bad .hixf) */
+#define TXR_ERR_OVERFLOW (-6)    /* internal capacity exceeded after retries */
+#define TXR_ERR_IO (-7)
+
+typedef struct txr_ctx txr_ctx;
+typedef struct txr_reads txr_reads;   /* a read set resident in HBM */
+
+const char *txr_last_error(void);      /* thread-local, human-readable */
+const char *txr_version(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Index: replaces the in-memory hixf::hierarchical_interleaved_xor_filter<uint8_t>
+ * (src/hixf/build/hierarchical_interleaved_xor_filter.hpp:78-160: ixf_vector, next_ixf_id, user_bins).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct
+{
+    uint64_t seed;       /* per-IXF hash seed (re-seeded on build failure, construct_ixf.cpp:101-108)      */
+    uint64_t bins;       /* counting-vector size == ixf_bin_to_filename_position[i].size() (hixf.hpp:313)  */
+    uint64_t tbins;      /* stored fingerprints per slot row (bins padded to a multiple of 64)             */
+    uint64_t seg_len;    /* slots per segment; the filter has 3*seg_len rows                               */
+    const uint8_t *fp;   /* host pointer, fp[slot * tbins + bin]                                           */
+} txr_ixf_view;
+
+typedef struct
+{
+    uint64_t n_ixf;
+    const txr_ixf_view *ixf;
+    const uint64_t *bin_off;           /* n_ixf+1 offsets into the two per-bin arrays                      */
+    const int64_t *next_ixf_id;        /* hixf.hpp:122                                                     */
+    const int64_t *bin_to_user_bin;    /* user_bins.ixf_bin_to_filename_position (hixf.hpp:178), -1=merged */
+    uint64_t n_user_bins;
+} txr_hixf_view;
+
+/* Parameters that the reference takes from the .hixf (taxor_search.cpp:165-169) and from the CLI. */
+typedef struct
+{
+    uint8_t kmer_size, syncmer_size, t_syncmer;
+    uint8_t use_syncmer;               /* index.use_syncmer()                                              */
+    uint32_t window_size;              /* index.window_size(); k-mer mode requires window_size == kmer_size */
+    uint16_t scaling;                  /* FracMin scaling (taxor_search.cpp:223-233); 1 = off              */
+    double percentage;                 /* --percentage; <= 0 selects the model (threshold.hpp:27-48)       */
+    double error_rate;                 /* --error-rate (default 0.04, taxor_search_configuration.hpp:16)   */
+} txr_params;
+
+/* bulk_contains result for a batch (hixf.hpp:371-406), one segment per read, each segment in the
+ * reference's DFS pre-order; `keep` marks the pairs that survive the 0.8*max filter (taxor_search.cpp:275-286). */
+typedef struct
+{
+    uint64_t n_reads;
+    const uint32_t *hash_count;        /* [n_reads]   hashes.size()  (taxor_search.cpp:261)                */
+    const uint64_t *threshold;         /* [n_reads]   thresholder.get() (taxor_search.cpp:263)             */
+    const uint64_t *hit_begin;         /* [n_reads+1]                                                      */
+    const int64_t *user_bin;           /* [n_hits]    result[i].first                                      */
+    const uint32_t *count;             /* [n_hits]    result[i].second                                     */
+    const uint8_t *keep;               /* [n_hits]                                                         */
+} txr_result;
+
+/* Per-stage device time of the most recent search call, measured with CUDA events on the launch stream. */
+typedef struct
+{
+    float h2d_ms, hash_ms, dedup_ms, query_ms, d2h_ms, total_ms;
+    uint64_t query_launches, hash_launches, dedup_launches;
+    uint64_t query_items;              /* (read, IXF) work items processed                                  */
+    uint64_t query_bytes;              /* sum over items of H*3*tbins + 8*H   (SURVEY 8(d) algorithmic bytes) */
+    uint64_t hash_bytes;               /* sum over reads of ceil(L/4) + 8*H_raw                              */
+    uint64_t n_hashes;                 /* sum of hash_count                                                  */
+} txr_timing;
+
+/* ---- context ---- */
+int txr_ctx_create(int device, txr_ctx **out);
+void txr_ctx_destroy(txr_ctx *ctx);
+/* The caller's CUDA stream (a cudaStream_t; NULL = legacy default stream).  Every search call forks its internal
+ * streams from it and joins them back, so CUDA events recorded on it bracket the whole call. */
+int txr_ctx_set_stream(txr_ctx *ctx, void *stream);
+/* max reads / bases per internal batch and number of pipeline slots (defaults 131072 / 1.5e9 / 3). */
+int txr_ctx_configure(txr_ctx *ctx, uint64_t max_batch_reads, uint64_t max_batch_bases, int n_slots);
+
+/* one-time re-layout of the index into HBM; replaces load_index() + index.ixf() (load_index.hpp:27-38) */
+int txr_index_upload(txr_ctx *ctx, const txr_hixf_view *index);
+int txr_params_set(txr_ctx *ctx, const txr_params *params);
+/* hixf::threshold::threshold::get (src/hixf/search/threshold.hpp:51-81) with the context's parameters */
+int txr_threshold_get(txr_ctx *ctx, uint64_t hash_count, double scaling_factor, uint64_t *out);
+
+/* ---- reads: 2-bit packing (A0 C1 G2 T3, seqan3::dna4 collapse of IUPAC, src/hixf/build/dna4_traits.hpp:15-18) ----
+ * Layout: read r occupies 64-bit words [word_off[r], word_off[r] + ceil(len/32)] (one zero pad word),
+ * base i of a read sits in word i/32 at bits [62-2*(i%32), 63-2*(i%32)] (first base most significant). */
+uint64_t txr_packed_words(uint64_t n_bases);                                 /* ceil(n/32) + 1 */
+int txr_pack_2bit(const char *ascii, uint64_t len, uint64_t *dst_words);     /* TXR_ERR_FORMAT on a non-IUPAC char */
+int txr_pack_codes(const uint8_t *codes, uint64_t len, uint64_t *dst_words); /* codes 0..3 */
+int txr_unpack_codes(const uint64_t *words, uint64_t len, uint8_t *codes);
+void *txr_host_alloc(size_t bytes);                                          /* pinned host memory */
+void txr_host_free(void *p);
+
+/* ---- search: replaces the per-read body of `worker` (taxor_search.cpp:196-313) for n_reads reads ---- */
+/* end to end from HOST buffers (pinned or pageable): H2D, hash, dedup, query levels, D2H, host ordering. */
+int txr_search(txr_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len,
+               uint64_t n_reads, txr_result *out);
+/* reads resident in HBM (measurement of the device path without host<->device copies) */
+int txr_reads_upload(txr_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len,
+                     uint64_t n_reads, txr_reads **out);
+void txr_reads_free(txr_ctx *ctx, txr_reads *reads);
+/* fetch != 0: also copy the hits back and fill *out (out may be NULL when fetch == 0) */
+int txr_search_resident(txr_ctx *ctx, txr_reads *reads, int fetch, txr_result *out);
+int txr_get_timing(txr_ctx *ctx, txr_timing *out);
+
+/* ---- kernel-level entry points for parity tests ---- */
+/* kernel #1 alone: seq_to_syncmers / minimiser_hash for a batch.  hash_off[n_reads+1]; hashes of read r are
+ * hashes[hash_off[r] .. hash_off[r+1]) (distinct, unordered, in syncmer mode; position order in k-mer mode).
+ * dedup == 0 returns the raw emission list (syncmer mode).  Buffers are owned by the context. */
+int txr_hash_batch(txr_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len,
+                   uint64_t n_reads, int dedup, const uint64_t **hash_off, const uint64_t **hashes);
+/* kernel #2 alone: interleaved_xor_filter::counting_agent().bulk_count(values) (call site hixf.hpp:307-309)
+ * for one IXF of the uploaded index; counts[bins]. */
+int txr_ixf_bulk_count(txr_ctx *ctx, uint64_t ixf_idx, const uint64_t *values, uint64_t n, uint32_t *counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,90 @@
+// device_types.cuh -- plain structs shared by the kernels and the host engine.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace txr
+{
+constexpr int kTileWindows = 1024;         // windows per warp tile in the hash kernels (32 per lane)
+constexpr uint64_t kEmptyKey = ~0ULL;      // sentinel of the dedup tables
+constexpr uint32_t kSmallRowBytes = 512;   // IXFs with tbins <= this are probed by one warp per (read, IXF)
+
+// ---- kernel #1 (hashing) ----
+struct HashArgs
+{
+    const uint64_t *words;     // 2-bit packed reads, MSB-first, one zero pad word per read
+    const uint64_t *word_off;  // [n_reads] first word of each read
+    const uint32_t *len;       // [n_reads] bases
+    const uint64_t *out_off;   // [n_reads+1] capacity offsets into `out`
+    uint64_t *out;             // hashes
+    uint32_t *n_out;           // [n_reads] number of hashes written (raw emissions / k-mers)
+    uint32_t n_reads;
+    uint32_t *work_counter;    // dynamic read assignment
+    uint32_t *overflow;        // set to 1 when a read needed more than its capacity
+    uint64_t kmer_seed;        // k-mer mode: adjust_seed(k)
+    int k, s, t;               // generic kernel only
+};
+
+struct DedupArgs
+{
+    const uint32_t *read_ids;  // reads of this size class (nullptr: identity)
+    uint32_t n_ids;
+    const uint64_t *out_off;
+    uint64_t *hashes;          // in place: raw -> distinct
+    const uint32_t *n_raw;
+    uint32_t *hash_count;      // [n_reads] distinct (after the FracMin scaling filter)
+    uint64_t *gtable;          // global-memory tables (class C), pre-filled with kEmptyKey
+    const uint64_t *gtable_off;
+    uint32_t scaling;          // 1 = off
+    double scaling_limit;      // double(UINT64_MAX) / double(scaling)
+};
+
+// ---- kernel #2 (IXF probe / count / threshold / compaction) ----
+struct IxfDev
+{
+    const uint8_t *fp;         // fp[slot * tbins + bin], 256-byte aligned, tbins % 64 == 0
+    uint64_t seed;
+    uint32_t seg_len;
+    uint32_t tbins;            // row stride in bytes
+    uint32_t bins;             // counting-vector size
+    uint32_t meta_off;         // first entry of this IXF in the per-bin metadata arrays
+};
+
+enum : uint8_t { kBinMid = 0, kBinRunEnd = 1, kBinMerged = 2 };
+
+struct QueryArgs
+{
+    const IxfDev *ixf;
+    const int32_t *bin_ub;         // user bin id of a run end
+    const int32_t *bin_child;      // child IXF of a merged bin
+    const uint32_t *bin_run_begin; // first bin of the split run that ends here
+    const uint8_t *bin_kind;
+
+    const uint64_t *hashes;
+    const uint64_t *hash_off;      // [n_reads+1] (capacity offsets)
+    const uint32_t *hash_count;
+    const uint64_t *thr_lut;       // threshold by hash_count
+    uint32_t lut_len;
+
+    const uint2 *items;            // (read, ixf) work items of this level; nullptr: item i = (i, 0)
+    const uint32_t *n_items_ptr;   // device counter written by the previous level
+    uint32_t n_items_direct;
+    uint32_t items_cap;            // capacity of `items` (a level that overflowed is re-run by the host)
+    uint32_t *cursor;              // work-stealing cursor of this launch
+
+    uint2 *next_small;             // next level, children with tbins <= kSmallRowBytes
+    uint32_t *next_small_n;
+    uint2 *next_large;
+    uint32_t *next_large_n;
+    uint32_t next_cap;
+
+    uint32_t *hit_read;
+    int32_t *hit_ub;
+    uint32_t *hit_cnt;
+    uint32_t *n_hits;
+    uint32_t hit_cap;
+
+    unsigned long long *stat_bytes; // algorithmic bytes: sum H*3*tbins + 8*H
+    unsigned long long *stat_items;
+};
+} // namespace txr

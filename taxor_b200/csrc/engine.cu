@@ -1,0 +1,1331 @@
+// engine.cu -- host engine + C ABI (include/taxor_b200.h) of the B200-native `taxor search` hot path.
+//
+// Replaces the chunk loop + worker of search_single (src/main/taxor_search.cpp:196-326) for batches of reads:
+//   H2D packed reads -> kernel #1 (hash) -> dedup -> kernel #2 once per HIXF level -> D2H hits -> host: order the
+//   hits of every read in the reference's DFS pre-order (hixf.hpp:313-338), thresholds, 0.8*max filter flags.
+// The index is re-laid-out once into HBM (txr_index_upload); reads stream through `n_slots` pipeline slots,
+// each with its own stream, so the copy of batch i+1 overlaps the kernels of batch i.
+#include "../../include/taxor_b200.h"
+#include "device_types.cuh"
+#include "ixf_arith.cuh"
+#include "threshold.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace txr
+{
+cudaError_t launch_syncmer(const HashArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_kmer(const HashArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_dedup_small(const DedupArgs &a, cudaStream_t st);
+cudaError_t launch_dedup_medium(const DedupArgs &a, cudaStream_t st);
+cudaError_t launch_dedup_global(const DedupArgs &a, cudaStream_t st);
+cudaError_t launch_filter(const DedupArgs &a, cudaStream_t st);
+cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_query_large(const QueryArgs &a, int sm_count, uint32_t max_tbins, cudaStream_t st);
+cudaError_t launch_bulk_count(const IxfDev &d, const uint64_t *values, uint32_t n, uint32_t *counts, cudaStream_t st);
+} // namespace txr
+
+using namespace txr;
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int set_error(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define CU(call)                                                                                          \
+    do                                                                                                    \
+    {                                                                                                     \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return set_error(TXR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(call)           \
+    do                      \
+    {                       \
+        int rc_ = (call);   \
+        if (rc_ != TXR_OK)  \
+            return rc_;     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// small RAII buffers that only ever grow
+// ---------------------------------------------------------------------------------------------------------
+struct DevBuf
+{
+    void *p{nullptr};
+    size_t cap{0};
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return TXR_OK;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        CU(cudaMalloc(&p, want));
+        cap = want;
+        return TXR_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+struct PinBuf
+{
+    void *p{nullptr};
+    size_t cap{0};
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return TXR_OK;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        CU(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+        return TXR_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// index in HBM
+// ---------------------------------------------------------------------------------------------------------
+struct DeviceIndex
+{
+    bool loaded{false};
+    std::vector<IxfDev> ixf;            // host copy of the descriptors
+    DevBuf arena;                       // all fingerprint rows
+    DevBuf d_ixf, d_bin_ub, d_bin_child, d_bin_run_begin, d_bin_kind;
+    std::vector<uint32_t> dfs_rank;     // user bin -> position in the reference's DFS pre-order
+    uint32_t depth{0};                  // number of tree levels
+    uint32_t max_tbins{0};
+    bool any_large{false};
+    uint64_t n_user_bins{0};
+    uint64_t fp_bytes{0};
+    void release()
+    {
+        arena.release();
+        d_ixf.release();
+        d_bin_ub.release();
+        d_bin_child.release();
+        d_bin_run_begin.release();
+        d_bin_kind.release();
+        loaded = false;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// a batch of reads as the kernels see it
+// ---------------------------------------------------------------------------------------------------------
+struct BatchMeta // host side description, built once per batch
+{
+    uint64_t first_read{0};
+    uint32_t n_reads{0};
+    uint64_t n_bases{0};
+    uint64_t first_word{0}, n_words{0};
+    uint64_t total_cap{0};
+    uint64_t max_cap{0};
+    std::vector<uint64_t> word_off; // relative to first_word
+    std::vector<uint32_t> len;
+    std::vector<uint64_t> out_off;  // n_reads + 1
+    std::vector<uint32_t> ids_small, ids_medium, ids_global;
+    std::vector<uint64_t> gtable_off; // ids_global.size() + 1
+};
+
+struct BatchDev // device copies of the metadata
+{
+    DevBuf word_off, len, out_off, ids_small, ids_medium, ids_global, gtable_off;
+};
+
+enum CounterSlot : int
+{
+    C_NHITS = 0,
+    C_HASH_OVERFLOW = 1,
+    C_HASH_WORK = 2,
+    C_LEVEL0 = 8, // per level: n_small, n_large, cursor_small, cursor_large
+    C_PER_LEVEL = 4,
+    C_MAX_LEVELS = 32,
+    C_STATS = C_LEVEL0 + C_PER_LEVEL * C_MAX_LEVELS, // two u64: bytes, items (8-byte aligned: index is even)
+    C_TOTAL = C_STATS + 4
+};
+
+struct Slot
+{
+    cudaStream_t stream{nullptr};
+    cudaEvent_t ev[6]{}; // start, h2d done, hash done, dedup done, query done, d2h done
+    DevBuf words;
+    BatchDev meta;
+    DevBuf hashes, n_raw, hash_count, gtable;
+    DevBuf queues; // per level >= 1: small[cap], large[cap]
+    DevBuf hit_read, hit_ub, hit_cnt;
+    DevBuf counters;
+    PinBuf h_meta, h_counters, h_hash_count, h_hits;
+    uint32_t queue_cap{0}, hit_cap{0};
+    // state of the batch in flight
+    const BatchMeta *bm{nullptr};
+    const BatchDev *bd{nullptr};
+    const uint64_t *d_words{nullptr};
+    bool busy{false};
+};
+
+struct ResultStore
+{
+    std::vector<uint32_t> hash_count;
+    std::vector<uint64_t> threshold, hit_begin;
+    std::vector<int64_t> user_bin;
+    std::vector<uint32_t> count;
+    std::vector<uint8_t> keep;
+    void clear()
+    {
+        hash_count.clear();
+        threshold.clear();
+        hit_begin.clear();
+        user_bin.clear();
+        count.clear();
+        keep.clear();
+    }
+};
+
+struct txr_reads
+{
+    DevBuf words;
+    uint64_t n_reads{0};
+    std::vector<BatchMeta> batches;
+    std::vector<std::unique_ptr<BatchDev>> dev;
+};
+
+struct txr_ctx
+{
+    int device{0};
+    int sm_count{148};
+    uint64_t max_batch_reads{131072};
+    uint64_t max_batch_bases{1500000000ull};
+    int n_slots{3};
+    std::vector<std::unique_ptr<Slot>> slots;
+    DeviceIndex index;
+    bool have_params{false};
+    txr_params params{};
+    Thresholder thresholder;
+    uint64_t kmer_seed{0};
+    std::vector<uint64_t> lut; // threshold by hash_count (host)
+    DevBuf d_lut;
+    uint64_t d_lut_len{0};
+    ResultStore result;
+    txr_timing timing{};
+    // scratch for the parity entry points
+    std::vector<uint64_t> hb_off, hb_hashes;
+    DevBuf scratch_a, scratch_b;
+    cudaStream_t primary{nullptr};     // caller's stream: every search forks from it and joins back into it
+    cudaEvent_t fork_ev{nullptr}, join_ev{nullptr};
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------
+static inline uint64_t windows_of(uint64_t len, int k) { return len >= (uint64_t)k ? len - k + 1 : 0; }
+
+// upper bound on the hashes kernel #1 can emit for a read (see DESIGN.md "hash capacity"): two selected windows
+// are at least min(t-1, k-s+1-t)+1 apart
+static uint64_t hash_capacity(const txr_params &p, uint64_t len)
+{
+    const uint64_t w = windows_of(len, p.kmer_size);
+    if (!p.use_syncmer)
+        return w;
+    const int wn = p.kmer_size - p.syncmer_size + 1;
+    const int spacing = std::min<int>(p.t_syncmer - 1, wn - p.t_syncmer) + 1;
+    return (w + spacing - 1) / std::max(spacing, 1) + 1;
+}
+
+static uint64_t next_pow2(uint64_t x)
+{
+    uint64_t p = 1;
+    while (p < x)
+        p <<= 1;
+    return p;
+}
+
+static int ensure_slots(txr_ctx *c)
+{
+    while ((int)c->slots.size() < c->n_slots)
+    {
+        auto s = std::make_unique<Slot>();
+        CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        for (auto &e : s->ev)
+            CU(cudaEventCreate(&e));
+        c->slots.push_back(std::move(s));
+    }
+    return TXR_OK;
+}
+
+// threshold LUT covering hash counts [0, need)
+static int ensure_lut(txr_ctx *c, uint64_t need)
+{
+    if (need <= c->lut.size() && c->d_lut_len >= need)
+        return TXR_OK;
+    const uint64_t old = c->lut.size();
+    if (need > old)
+    {
+        uint64_t grow = std::max<uint64_t>(need, old + old / 2 + 1024);
+        c->lut.resize(grow);
+        for (uint64_t i = old; i < grow; ++i)
+            c->lut[i] = c->thresholder.get(i, 1.0);
+    }
+    // all streams must be idle before the table is replaced
+    CU(cudaDeviceSynchronize());
+    TRY(c->d_lut.ensure(c->lut.size() * 8));
+    CU(cudaMemcpy(c->d_lut.p, c->lut.data(), c->lut.size() * 8, cudaMemcpyHostToDevice));
+    c->d_lut_len = c->lut.size();
+    return TXR_OK;
+}
+
+// Builds the host metadata for reads [first, first+n): word offsets relative to the first word of the batch,
+// hash capacities and dedup size classes.
+static void build_batch_meta(const txr_ctx *c, const uint64_t *word_off, const uint32_t *len, uint64_t first,
+                             uint32_t n, BatchMeta &m)
+{
+    m.first_read = first;
+    m.n_reads = n;
+    m.first_word = word_off[first];
+    m.word_off.resize(n);
+    m.len.assign(len + first, len + first + n);
+    m.out_off.resize((size_t)n + 1);
+    m.ids_small.clear();
+    m.ids_medium.clear();
+    m.ids_global.clear();
+    m.gtable_off.assign(1, 0);
+    uint64_t bases = 0, cap_sum = 0, max_cap = 0;
+    const bool dedup = c->params.use_syncmer;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        m.word_off[i] = word_off[first + i] - m.first_word;
+        const uint64_t cap = hash_capacity(c->params, len[first + i]);
+        m.out_off[i] = cap_sum;
+        cap_sum += cap;
+        max_cap = std::max(max_cap, cap);
+        bases += len[first + i];
+        if (dedup)
+        {
+            if (cap <= 2048)
+                m.ids_small.push_back(i);
+            else if (cap <= 8192)
+                m.ids_medium.push_back(i);
+            else
+            {
+                m.ids_global.push_back(i);
+                m.gtable_off.push_back(m.gtable_off.back() + next_pow2(2 * cap));
+            }
+        }
+    }
+    m.out_off[n] = cap_sum;
+    m.total_cap = cap_sum;
+    m.max_cap = max_cap;
+    m.n_bases = bases;
+    const uint64_t last = first + n - 1;
+    m.n_words = word_off[last] + txr_packed_words(len[last]) - m.first_word;
+}
+
+static size_t meta_bytes(const BatchMeta &m)
+{
+    return m.word_off.size() * 8 + m.len.size() * 4 + m.out_off.size() * 8 + m.ids_small.size() * 4 + m.ids_medium.size() * 4 +
+           m.ids_global.size() * 4 + m.gtable_off.size() * 8 + 64;
+}
+
+// copies the metadata arrays to the device (through `stage` when given, which must be pinned and large enough)
+static int upload_batch_meta(const BatchMeta &m, BatchDev &d, cudaStream_t st, uint8_t *stage)
+{
+    struct Item
+    {
+        DevBuf *dst;
+        const void *src;
+        size_t bytes;
+    };
+    Item items[] = {{&d.word_off, m.word_off.data(), m.word_off.size() * 8},
+                    {&d.len, m.len.data(), m.len.size() * 4},
+                    {&d.out_off, m.out_off.data(), m.out_off.size() * 8},
+                    {&d.ids_small, m.ids_small.data(), m.ids_small.size() * 4},
+                    {&d.ids_medium, m.ids_medium.data(), m.ids_medium.size() * 4},
+                    {&d.ids_global, m.ids_global.data(), m.ids_global.size() * 4},
+                    {&d.gtable_off, m.gtable_off.data(), m.gtable_off.size() * 8}};
+    size_t off = 0;
+    for (auto &it : items)
+    {
+        if (it.bytes == 0)
+            continue;
+        TRY(it.dst->ensure(it.bytes));
+        const void *src = it.src;
+        if (stage)
+        {
+            memcpy(stage + off, it.src, it.bytes);
+            src = stage + off;
+            off += (it.bytes + 15) & ~size_t(15);
+        }
+        CU(cudaMemcpyAsync(it.dst->p, src, it.bytes, cudaMemcpyHostToDevice, st));
+    }
+    return TXR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launching one batch on a slot
+// ---------------------------------------------------------------------------------------------------------
+static int slot_reserve(txr_ctx *c, Slot &s, const BatchMeta &m)
+{
+    const uint32_t n = m.n_reads;
+    TRY(s.hashes.ensure(std::max<uint64_t>(m.total_cap, 1) * 8));
+    TRY(s.n_raw.ensure((size_t)n * 4));
+    TRY(s.hash_count.ensure((size_t)n * 4));
+    TRY(s.counters.ensure(C_TOTAL * 4));
+    TRY(s.h_counters.ensure(C_TOTAL * 4));
+    TRY(s.h_hash_count.ensure((size_t)n * 4));
+    if (!m.ids_global.empty())
+        TRY(s.gtable.ensure(m.gtable_off.back() * 8));
+    if (s.queue_cap < 2 * n + 1024)
+        s.queue_cap = 2 * n + 1024;
+    if (s.hit_cap < 4 * n + 1024)
+        s.hit_cap = 4 * n + 1024;
+    const uint32_t levels = std::max<uint32_t>(c->index.depth, 1);
+    TRY(s.queues.ensure((size_t)levels * 2 * s.queue_cap * sizeof(uint2)));
+    TRY(s.hit_read.ensure((size_t)s.hit_cap * 4));
+    TRY(s.hit_ub.ensure((size_t)s.hit_cap * 4));
+    TRY(s.hit_cnt.ensure((size_t)s.hit_cap * 4));
+    TRY(s.h_hits.ensure((size_t)s.hit_cap * 12));
+    return TXR_OK;
+}
+
+static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev &d, const uint64_t *d_words,
+                             bool dedup)
+{
+    uint32_t *cnt = s.counters.as<uint32_t>();
+    HashArgs h{};
+    h.words = d_words;
+    h.word_off = d.word_off.as<uint64_t>();
+    h.len = d.len.as<uint32_t>();
+    h.out_off = d.out_off.as<uint64_t>();
+    h.out = s.hashes.as<uint64_t>();
+    h.n_out = c->params.use_syncmer || c->params.scaling > 1 ? s.n_raw.as<uint32_t>() : s.hash_count.as<uint32_t>();
+    h.n_reads = m.n_reads;
+    h.work_counter = cnt + C_HASH_WORK;
+    h.overflow = cnt + C_HASH_OVERFLOW;
+    h.kmer_seed = c->kmer_seed;
+    h.k = c->params.kmer_size;
+    h.s = c->params.syncmer_size;
+    h.t = c->params.t_syncmer;
+    if (c->params.use_syncmer)
+        CU(launch_syncmer(h, c->sm_count, s.stream));
+    else
+        CU(launch_kmer(h, c->sm_count, s.stream));
+    c->timing.hash_launches += 1;
+    CU(cudaEventRecord(s.ev[2], s.stream));
+
+    if (!dedup)
+    {
+        CU(cudaEventRecord(s.ev[3], s.stream));
+        return TXR_OK;
+    }
+    DedupArgs dd{};
+    dd.out_off = d.out_off.as<uint64_t>();
+    dd.hashes = s.hashes.as<uint64_t>();
+    dd.n_raw = s.n_raw.as<uint32_t>();
+    dd.hash_count = s.hash_count.as<uint32_t>();
+    dd.scaling = c->params.scaling;
+    dd.scaling_limit = double(UINT64_MAX) / double(c->params.scaling ? c->params.scaling : 1);
+    if (c->params.use_syncmer)
+    {
+        if (!m.ids_small.empty())
+        {
+            dd.read_ids = m.ids_small.size() == m.n_reads ? nullptr : d.ids_small.as<uint32_t>();
+            dd.n_ids = (uint32_t)m.ids_small.size();
+            CU(launch_dedup_small(dd, s.stream));
+            c->timing.dedup_launches += 1;
+        }
+        if (!m.ids_medium.empty())
+        {
+            dd.read_ids = d.ids_medium.as<uint32_t>();
+            dd.n_ids = (uint32_t)m.ids_medium.size();
+            CU(launch_dedup_medium(dd, s.stream));
+            c->timing.dedup_launches += 1;
+        }
+        if (!m.ids_global.empty())
+        {
+            CU(cudaMemsetAsync(s.gtable.p, 0xff, m.gtable_off.back() * 8, s.stream));
+            dd.read_ids = d.ids_global.as<uint32_t>();
+            dd.n_ids = (uint32_t)m.ids_global.size();
+            dd.gtable = s.gtable.as<uint64_t>();
+            dd.gtable_off = d.gtable_off.as<uint64_t>();
+            CU(launch_dedup_global(dd, s.stream));
+            c->timing.dedup_launches += 1;
+        }
+    }
+    else if (c->params.scaling > 1)
+    {
+        dd.read_ids = nullptr;
+        dd.n_ids = m.n_reads;
+        CU(launch_filter(dd, s.stream));
+        c->timing.dedup_launches += 1;
+    }
+    CU(cudaEventRecord(s.ev[3], s.stream));
+    return TXR_OK;
+}
+
+static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev &d)
+{
+    const DeviceIndex &ix = c->index;
+    uint32_t *cnt = s.counters.as<uint32_t>();
+    QueryArgs q{};
+    q.ixf = ix.d_ixf.as<IxfDev>();
+    q.bin_ub = ix.d_bin_ub.as<int32_t>();
+    q.bin_child = ix.d_bin_child.as<int32_t>();
+    q.bin_run_begin = ix.d_bin_run_begin.as<uint32_t>();
+    q.bin_kind = ix.d_bin_kind.as<uint8_t>();
+    q.hashes = s.hashes.as<uint64_t>();
+    q.hash_off = d.out_off.as<uint64_t>();
+    q.hash_count = s.hash_count.as<uint32_t>();
+    q.thr_lut = c->d_lut.as<uint64_t>();
+    q.lut_len = (uint32_t)std::min<uint64_t>(c->d_lut_len, 0xffffffffu);
+    q.hit_read = s.hit_read.as<uint32_t>();
+    q.hit_ub = s.hit_ub.as<int32_t>();
+    q.hit_cnt = s.hit_cnt.as<uint32_t>();
+    q.n_hits = cnt + C_NHITS;
+    q.hit_cap = s.hit_cap;
+    q.next_cap = s.queue_cap;
+    q.stat_bytes = reinterpret_cast<unsigned long long *>(cnt + C_STATS);
+    q.stat_items = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 2);
+    uint2 *queues = s.queues.as<uint2>();
+    const uint32_t levels = std::min<uint32_t>(ix.depth, C_MAX_LEVELS);
+    for (uint32_t lv = 0; lv < levels; ++lv)
+    {
+        uint32_t *lc = cnt + C_LEVEL0 + C_PER_LEVEL * lv;
+        uint32_t *nc = cnt + C_LEVEL0 + C_PER_LEVEL * (lv + 1); // next level's counters
+        const bool last = lv + 1 == levels;
+        // outputs of this level (a leaf level never descends; give it valid but unused targets)
+        const uint32_t nl = last ? lv : lv + 1;
+        q.next_small = queues + (size_t)(2 * nl) * s.queue_cap;
+        q.next_large = queues + (size_t)(2 * nl + 1) * s.queue_cap;
+        q.next_small_n = last ? lc + 0 : nc + 0;
+        q.next_large_n = last ? lc + 1 : nc + 1;
+        if (lv == 0)
+        {
+            q.items = nullptr;
+            q.n_items_ptr = nullptr;
+            q.n_items_direct = m.n_reads;
+            q.items_cap = m.n_reads;
+            q.cursor = lc + 2;
+            if (ix.ixf[0].tbins <= kSmallRowBytes)
+                CU(launch_query_small(q, c->sm_count, s.stream));
+            else
+                CU(launch_query_large(q, c->sm_count, ix.max_tbins, s.stream));
+            c->timing.query_launches += 1;
+        }
+        else
+        {
+            q.items_cap = s.queue_cap;
+            q.n_items_direct = 0;
+            q.items = queues + (size_t)(2 * lv) * s.queue_cap;
+            q.n_items_ptr = lc + 0;
+            q.cursor = lc + 2;
+            CU(launch_query_small(q, c->sm_count, s.stream));
+            c->timing.query_launches += 1;
+            if (ix.any_large)
+            {
+                q.items = queues + (size_t)(2 * lv + 1) * s.queue_cap;
+                q.n_items_ptr = lc + 1;
+                q.cursor = lc + 3;
+                CU(launch_query_large(q, c->sm_count, ix.max_tbins, s.stream));
+                c->timing.query_launches += 1;
+            }
+        }
+    }
+    CU(cudaEventRecord(s.ev[4], s.stream));
+    return TXR_OK;
+}
+
+// enqueue everything for one batch; `h_words` != nullptr: copy the packed reads from the host first
+static int submit_batch(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev *resident_meta,
+                        const uint64_t *d_words_resident, const uint64_t *h_words, bool run_query)
+{
+    TRY(slot_reserve(c, s, m));
+    TRY(ensure_lut(c, m.max_cap + 1));
+    CU(cudaEventRecord(s.ev[0], s.stream));
+    const BatchDev *bd = resident_meta;
+    const uint64_t *d_words = d_words_resident;
+    if (h_words)
+    {
+        TRY(s.words.ensure(m.n_words * 8));
+        TRY(s.h_meta.ensure(meta_bytes(m) + 7 * 16));
+        CU(cudaMemcpyAsync(s.words.p, h_words + m.first_word, m.n_words * 8, cudaMemcpyHostToDevice, s.stream));
+        TRY(upload_batch_meta(m, s.meta, s.stream, s.h_meta.as<uint8_t>()));
+        bd = &s.meta;
+        d_words = s.words.as<uint64_t>();
+    }
+    CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, s.stream));
+    CU(cudaEventRecord(s.ev[1], s.stream));
+    TRY(launch_hash_stage(c, s, m, *bd, d_words, true));
+    if (run_query)
+        TRY(launch_query_stage(c, s, m, *bd));
+    else
+        CU(cudaEventRecord(s.ev[4], s.stream));
+    CU(cudaMemcpyAsync(s.h_counters.p, s.counters.p, C_TOTAL * 4, cudaMemcpyDeviceToHost, s.stream));
+    s.bm = &m;
+    s.bd = bd;
+    s.d_words = d_words;
+    s.busy = true;
+    return TXR_OK;
+}
+
+// waits for a batch, re-runs the query stage with larger queues if one overflowed, optionally fetches the hits
+// and appends the batch to the result store
+static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
+{
+    const BatchMeta &m = *s.bm;
+    for (int attempt = 0;; ++attempt)
+    {
+        CU(cudaStreamSynchronize(s.stream));
+        const uint32_t *hc = s.h_counters.as<uint32_t>();
+        if (hc[C_HASH_OVERFLOW])
+            return set_error(TXR_ERR_OVERFLOW, "hash capacity bound violated (k=%d s=%d t=%d)", c->params.kmer_size,
+                             c->params.syncmer_size, c->params.t_syncmer);
+        bool overflow = hc[C_NHITS] > s.hit_cap;
+        uint32_t need_q = 0;
+        for (uint32_t lv = 0; lv < std::min<uint32_t>(c->index.depth, C_MAX_LEVELS); ++lv)
+            need_q = std::max(need_q, std::max(hc[C_LEVEL0 + C_PER_LEVEL * lv], hc[C_LEVEL0 + C_PER_LEVEL * lv + 1]));
+        overflow = overflow || need_q > s.queue_cap;
+        if (!overflow)
+            break;
+        if (attempt >= 8)
+            return set_error(TXR_ERR_OVERFLOW, "hit/queue buffers still too small after %d retries", attempt);
+        // grow (the overflowing counters are lower bounds only: deeper levels were truncated), then re-run
+        s.hit_cap = std::max<uint32_t>(s.hit_cap, hc[C_NHITS]) * 2;
+        s.queue_cap = std::max(s.queue_cap, need_q) * 2;
+        TRY(slot_reserve(c, s, m));
+        CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, s.stream));
+        TRY(launch_query_stage(c, s, m, *s.bd));
+        CU(cudaMemcpyAsync(s.h_counters.p, s.counters.p, C_TOTAL * 4, cudaMemcpyDeviceToHost, s.stream));
+    }
+    const uint32_t *hc = s.h_counters.as<uint32_t>();
+    const uint32_t n_hits = hc[C_NHITS];
+    uint64_t stats[2];
+    memcpy(stats, hc + C_STATS, 16);
+    c->timing.query_bytes += stats[0];
+    c->timing.query_items += stats[1];
+
+    float ms = 0;
+    cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]);
+    c->timing.h2d_ms += ms;
+    cudaEventElapsedTime(&ms, s.ev[1], s.ev[2]);
+    c->timing.hash_ms += ms;
+    cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]);
+    c->timing.dedup_ms += ms;
+    cudaEventElapsedTime(&ms, s.ev[3], s.ev[4]);
+    c->timing.query_ms += ms;
+
+    if (fetch)
+    {
+        const uint32_t n = m.n_reads;
+        CU(cudaEventRecord(s.ev[4], s.stream));
+        CU(cudaMemcpyAsync(s.h_hash_count.p, s.hash_count.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
+        uint32_t *hh = s.h_hits.as<uint32_t>();
+        if (n_hits)
+        {
+            CU(cudaMemcpyAsync(hh, s.hit_read.p, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(hh + s.hit_cap, s.hit_ub.p, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(hh + 2 * (size_t)s.hit_cap, s.hit_cnt.p, (size_t)n_hits * 4, cudaMemcpyDeviceToHost, s.stream));
+        }
+        CU(cudaEventRecord(s.ev[5], s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]);
+        c->timing.d2h_ms += ms;
+
+        // ---- host post-pass: group by read, DFS pre-order, threshold, 0.8*max flags ----
+        ResultStore &R = c->result;
+        const uint32_t *h_count = s.h_hash_count.as<uint32_t>();
+        const uint32_t *h_read = hh;
+        const int32_t *h_ub = reinterpret_cast<const int32_t *>(hh + s.hit_cap);
+        const uint32_t *h_cnt = hh + 2 * (size_t)s.hit_cap;
+        std::vector<uint32_t> begin((size_t)n + 1, 0);
+        for (uint32_t i = 0; i < n_hits; ++i)
+            ++begin[h_read[i] + 1];
+        for (uint32_t r = 0; r < n; ++r)
+            begin[r + 1] += begin[r];
+        std::vector<uint32_t> order(n_hits), fill(begin.begin(), begin.end() - 1);
+        for (uint32_t i = 0; i < n_hits; ++i)
+            order[fill[h_read[i]]++] = i;
+        const std::vector<uint32_t> &rank = c->index.dfs_rank;
+        const size_t base_hits = R.user_bin.size();
+        R.user_bin.resize(base_hits + n_hits);
+        R.count.resize(base_hits + n_hits);
+        R.keep.resize(base_hits + n_hits);
+        uint64_t n_hashes = 0, hash_bytes = 0;
+        for (uint32_t r = 0; r < n; ++r)
+        {
+            uint32_t *o = order.data() + begin[r];
+            const uint32_t cnt = begin[r + 1] - begin[r];
+            if (cnt > 1)
+                std::sort(o, o + cnt, [&](uint32_t x, uint32_t y) { return rank[h_ub[x]] < rank[h_ub[y]]; });
+            uint64_t max_count = 0;                                       // taxor_search.cpp:275-280
+            for (uint32_t i = 0; i < cnt; ++i)
+                max_count = std::max<uint64_t>(max_count, h_cnt[o[i]]);
+            for (uint32_t i = 0; i < cnt; ++i)
+            {
+                const size_t at = base_hits + begin[r] + i;
+                R.user_bin[at] = h_ub[o[i]];
+                R.count[at] = h_cnt[o[i]];
+                // taxor_search.cpp:285: dropped iff double(count) < double(max_count) * 0.8
+                R.keep[at] = !(static_cast<double>(h_cnt[o[i]]) < static_cast<double>(max_count) * 0.8);
+            }
+            R.hash_count.push_back(h_count[r]);
+            R.threshold.push_back(h_count[r] < c->lut.size() ? c->lut[h_count[r]] : c->thresholder.get(h_count[r], 1.0));
+            R.hit_begin.push_back(base_hits + begin[r]);
+            n_hashes += h_count[r];
+            hash_bytes += (m.len[r] + 3) / 4;
+        }
+        c->timing.n_hashes += n_hashes;
+        c->timing.hash_bytes += hash_bytes + 8 * n_hashes;
+    }
+    s.busy = false;
+    return TXR_OK;
+}
+
+static void finish_result(txr_ctx *c, txr_result *out)
+{
+    ResultStore &R = c->result;
+    R.hit_begin.push_back(R.user_bin.size());
+    if (!out)
+        return;
+    out->n_reads = R.hash_count.size();
+    out->hash_count = R.hash_count.data();
+    out->threshold = R.threshold.data();
+    out->hit_begin = R.hit_begin.data();
+    out->user_bin = R.user_bin.data();
+    out->count = R.count.data();
+    out->keep = R.keep.data();
+}
+
+// split reads [0, n) into batches bounded by reads and bases
+static void plan_batches(const txr_ctx *c, const uint32_t *len, uint64_t n, std::vector<std::pair<uint64_t, uint32_t>> &out)
+{
+    out.clear();
+    uint64_t i = 0;
+    while (i < n)
+    {
+        uint64_t bases = 0, j = i;
+        while (j < n && j - i < c->max_batch_reads && (j == i || bases + len[j] <= c->max_batch_bases))
+            bases += len[j++];
+        out.emplace_back(i, (uint32_t)(j - i));
+        i = j;
+    }
+}
+
+// make the slot streams wait for work already queued on the caller's stream ...
+static int fork_streams(txr_ctx *c)
+{
+    if (!c->fork_ev)
+    {
+        CU(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(c->fork_ev, c->primary));
+    for (auto &s : c->slots)
+        CU(cudaStreamWaitEvent(s->stream, c->fork_ev, 0));
+    return TXR_OK;
+}
+// ... and the caller's stream wait for everything the slots did (so events on it bracket the search)
+static int join_streams(txr_ctx *c)
+{
+    for (auto &s : c->slots)
+    {
+        CU(cudaEventRecord(c->join_ev, s->stream));
+        CU(cudaStreamWaitEvent(c->primary, c->join_ev, 0));
+    }
+    return TXR_OK;
+}
+
+static int check_ready(txr_ctx *c)
+{
+    if (!c)
+        return set_error(TXR_ERR_ARG, "null context");
+    if (!c->index.loaded)
+        return set_error(TXR_ERR_STATE, "no index uploaded");
+    if (!c->have_params)
+        return set_error(TXR_ERR_STATE, "txr_params_set not called");
+    CU(cudaSetDevice(c->device));
+    return ensure_slots(c);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *txr_last_error(void) { return g_last_error.c_str(); }
+const char *txr_version(void) { return "taxor_b200 0.1 (sm_100a)"; }
+
+int txr_ctx_create(int device, txr_ctx **out)
+{
+    if (!out)
+        return set_error(TXR_ERR_ARG, "out is null");
+    *out = nullptr;
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n)
+        return set_error(TXR_ERR_CUDA, "CUDA device %d not available (%d devices); this library has no CPU fallback", device, n);
+    CU(cudaSetDevice(device));
+    auto c = std::make_unique<txr_ctx>();
+    c->device = device;
+    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    *out = c.release();
+    return TXR_OK;
+}
+
+void txr_ctx_destroy(txr_ctx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &s : c->slots)
+    {
+        for (DevBuf *b : {&s->words, &s->meta.word_off, &s->meta.len, &s->meta.out_off, &s->meta.ids_small, &s->meta.ids_medium,
+                          &s->meta.ids_global, &s->meta.gtable_off, &s->hashes, &s->n_raw, &s->hash_count, &s->gtable, &s->queues,
+                          &s->hit_read, &s->hit_ub, &s->hit_cnt, &s->counters})
+            b->release();
+        for (PinBuf *b : {&s->h_meta, &s->h_counters, &s->h_hash_count, &s->h_hits})
+            b->release();
+        for (auto &e : s->ev)
+            cudaEventDestroy(e);
+        cudaStreamDestroy(s->stream);
+    }
+    if (c->fork_ev)
+    {
+        cudaEventDestroy(c->fork_ev);
+        cudaEventDestroy(c->join_ev);
+    }
+    c->index.release();
+    c->d_lut.release();
+    c->scratch_a.release();
+    c->scratch_b.release();
+    delete c;
+}
+
+int txr_ctx_set_stream(txr_ctx *c, void *stream)
+{
+    if (!c)
+        return set_error(TXR_ERR_ARG, "null context");
+    c->primary = static_cast<cudaStream_t>(stream);
+    return TXR_OK;
+}
+
+int txr_ctx_configure(txr_ctx *c, uint64_t max_batch_reads, uint64_t max_batch_bases, int n_slots)
+{
+    if (!c || max_batch_reads == 0 || max_batch_bases == 0 || n_slots < 1 || n_slots > 8)
+        return set_error(TXR_ERR_ARG, "bad configuration");
+    if (max_batch_reads > (1u << 30))
+        return set_error(TXR_ERR_ARG, "max_batch_reads too large");
+    c->max_batch_reads = max_batch_reads;
+    c->max_batch_bases = max_batch_bases;
+    c->n_slots = n_slots;
+    return TXR_OK;
+}
+
+int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
+{
+    if (!c || !v || v->n_ixf == 0)
+        return set_error(TXR_ERR_ARG, "null or empty index");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    DeviceIndex &ix = c->index;
+    ix.release();
+    const uint64_t n = v->n_ixf;
+    // validate + size the arena (rows padded to a multiple of 64 bytes, each IXF 256-byte aligned)
+    std::vector<uint64_t> arena_off(n);
+    uint64_t arena_bytes = 0, total_bins = v->bin_off[n];
+    ix.ixf.resize(n);
+    ix.max_tbins = 0;
+    ix.any_large = false;
+    ix.fp_bytes = 0;
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const txr_ixf_view &x = v->ixf[i];
+        if (x.bins == 0 || x.tbins < x.bins || x.seg_len == 0 || x.seg_len >= (1ull << 31) || !x.fp)
+            return set_error(TXR_ERR_ARG, "IXF %llu: inconsistent geometry", (unsigned long long)i);
+        if (v->bin_off[i + 1] - v->bin_off[i] != x.bins)
+            return set_error(TXR_ERR_ARG, "IXF %llu: bin metadata size != bins", (unsigned long long)i);
+        const uint64_t dev_tbins = (x.tbins + 63) / 64 * 64;
+        if (dev_tbins > 65536)
+            return set_error(TXR_ERR_UNSUPPORTED, "IXF %llu: %llu technical bins not supported", (unsigned long long)i,
+                             (unsigned long long)x.tbins);
+        arena_off[i] = arena_bytes;
+        arena_bytes += (3 * x.seg_len * dev_tbins + 255) / 256 * 256;
+        ix.ixf[i] = IxfDev{nullptr, x.seed, (uint32_t)x.seg_len, (uint32_t)dev_tbins, (uint32_t)x.bins, (uint32_t)v->bin_off[i]};
+        ix.max_tbins = std::max<uint32_t>(ix.max_tbins, (uint32_t)dev_tbins);
+        ix.any_large = ix.any_large || dev_tbins > kSmallRowBytes;
+        ix.fp_bytes += 3 * x.seg_len * dev_tbins;
+    }
+    TRY(ix.arena.ensure(arena_bytes));
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const txr_ixf_view &x = v->ixf[i];
+        uint8_t *dst = ix.arena.as<uint8_t>() + arena_off[i];
+        ix.ixf[i].fp = dst;
+        const uint64_t rows = 3 * x.seg_len, dev_tbins = ix.ixf[i].tbins;
+        if (dev_tbins == x.tbins)
+            CU(cudaMemcpy(dst, x.fp, rows * x.tbins, cudaMemcpyHostToDevice));
+        else
+        {
+            CU(cudaMemset(dst, 0, rows * dev_tbins));
+            CU(cudaMemcpy2D(dst, dev_tbins, x.fp, x.tbins, x.tbins, rows, cudaMemcpyHostToDevice));
+        }
+    }
+    // per-bin metadata: kind, user bin, child, first bin of the split run (hixf.hpp:313-338)
+    std::vector<int32_t> ub(total_bins), child(total_bins);
+    std::vector<uint32_t> run_begin(total_bins);
+    std::vector<uint8_t> kind(total_bins);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const uint64_t o = v->bin_off[i], nb = v->ixf[i].bins;
+        uint32_t run_start = 0;
+        for (uint64_t b = 0; b < nb; ++b)
+        {
+            const int64_t cur = v->bin_to_user_bin[o + b];
+            if (cur < 0)
+            {
+                const int64_t nx = v->next_ixf_id[o + b];
+                if (nx < 0 || (uint64_t)nx >= n || (uint64_t)nx == i)
+                    return set_error(TXR_ERR_ARG, "IXF %llu bin %llu: merged bin without a child IXF", (unsigned long long)i,
+                                     (unsigned long long)b);
+                kind[o + b] = kBinMerged;
+                child[o + b] = (int32_t)nx;
+                ub[o + b] = -1;
+                run_start = (uint32_t)b + 1;
+            }
+            else
+            {
+                if ((uint64_t)cur >= v->n_user_bins)
+                    return set_error(TXR_ERR_ARG, "user bin id %lld out of range", (long long)cur);
+                const bool end = b + 1 == nb || cur != v->bin_to_user_bin[o + b + 1];
+                kind[o + b] = end ? kBinRunEnd : kBinMid;
+                ub[o + b] = (int32_t)cur;
+                child[o + b] = -1;
+                run_begin[o + b] = run_start;
+                if (end)
+                    run_start = (uint32_t)b + 1;
+            }
+        }
+    }
+    // DFS pre-order rank of every user bin + tree depth (iterative DFS from IXF 0, bins ascending)
+    ix.dfs_rank.assign(v->n_user_bins, 0xffffffffu);
+    ix.n_user_bins = v->n_user_bins;
+    {
+        struct Frame
+        {
+            uint64_t ixf, bin;
+            uint32_t level;
+        };
+        std::vector<Frame> stack{{0, 0, 1}};
+        std::vector<uint8_t> seen(n, 0);
+        seen[0] = 1;
+        uint32_t rank = 0, depth = 1;
+        while (!stack.empty())
+        {
+            Frame &f = stack.back();
+            if (f.bin == v->ixf[f.ixf].bins)
+            {
+                stack.pop_back();
+                continue;
+            }
+            const uint64_t at = v->bin_off[f.ixf] + f.bin++;
+            if (kind[at] == kBinMerged)
+            {
+                const uint64_t ch = (uint64_t)child[at];
+                if (seen[ch])
+                    return set_error(TXR_ERR_ARG, "IXF %llu is reachable twice: not a tree", (unsigned long long)ch);
+                seen[ch] = 1;
+                const uint32_t lvl = f.level + 1;
+                depth = std::max(depth, lvl);
+                stack.push_back(Frame{ch, 0, lvl});
+            }
+            else if (kind[at] == kBinRunEnd)
+            {
+                if (ix.dfs_rank[ub[at]] == 0xffffffffu)
+                    ix.dfs_rank[ub[at]] = rank++;
+            }
+        }
+        ix.depth = depth;
+        if (depth > C_MAX_LEVELS)
+            return set_error(TXR_ERR_UNSUPPORTED, "HIXF deeper than %d levels", (int)C_MAX_LEVELS);
+    }
+    TRY(ix.d_ixf.ensure(n * sizeof(IxfDev)));
+    TRY(ix.d_bin_ub.ensure(total_bins * 4));
+    TRY(ix.d_bin_child.ensure(total_bins * 4));
+    TRY(ix.d_bin_run_begin.ensure(total_bins * 4));
+    TRY(ix.d_bin_kind.ensure(total_bins));
+    CU(cudaMemcpy(ix.d_ixf.p, ix.ixf.data(), n * sizeof(IxfDev), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ix.d_bin_ub.p, ub.data(), total_bins * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ix.d_bin_child.p, child.data(), total_bins * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ix.d_bin_run_begin.p, run_begin.data(), total_bins * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ix.d_bin_kind.p, kind.data(), total_bins, cudaMemcpyHostToDevice));
+    ix.loaded = true;
+    return TXR_OK;
+}
+
+int txr_params_set(txr_ctx *c, const txr_params *p)
+{
+    if (!c || !p)
+        return set_error(TXR_ERR_ARG, "null argument");
+    if (p->kmer_size < 1 || p->kmer_size > 32)
+        return set_error(TXR_ERR_ARG, "kmer_size %d out of range", p->kmer_size);
+    if (p->use_syncmer)
+    {
+        const int wn = p->kmer_size - p->syncmer_size + 1;
+        if (p->syncmer_size < 1 || p->syncmer_size >= p->kmer_size || p->t_syncmer < 1 || p->t_syncmer > wn)
+            return set_error(TXR_ERR_ARG, "syncmer parameters k=%d s=%d t=%d out of range", p->kmer_size, p->syncmer_size, p->t_syncmer);
+    }
+    else if (p->window_size != p->kmer_size)
+        return set_error(TXR_ERR_UNSUPPORTED, "k-mer mode requires window_size == kmer_size (minimiser windows are not on the GPU path)");
+    CU(cudaSetDevice(c->device));
+    c->params = *p;
+    if (c->params.scaling == 0)
+        c->params.scaling = 1;
+    c->thresholder = Thresholder(p->window_size, p->kmer_size, p->percentage, p->error_rate, p->use_syncmer != 0);
+    c->kmer_seed = 0x8F3F73B5CF1C9ADEULL >> (64u - 2u * p->kmer_size); // src/hixf/build/adjust_seed.hpp:40-44
+    c->lut.clear();
+    c->d_lut_len = 0;
+    c->have_params = true;
+    return ensure_lut(c, 4096);
+}
+
+int txr_threshold_get(txr_ctx *c, uint64_t hash_count, double scaling_factor, uint64_t *out)
+{
+    if (!c || !out || !c->have_params)
+        return set_error(TXR_ERR_STATE, "no parameters");
+    *out = c->thresholder.get(hash_count, scaling_factor);
+    return TXR_OK;
+}
+
+// ---- packing ----
+uint64_t txr_packed_words(uint64_t n_bases) { return (n_bases + 31) / 32 + 1; }
+
+static const int8_t *dna4_table()
+{
+    static int8_t tab[256];
+    static bool init = false;
+    if (!init)
+    {
+        memset(tab, -1, sizeof tab);
+        const char *groups[4] = {"ANRWMDHV", "CYSB", "GK", "TU"}; // seqan3::dna4 char_to_rank
+        for (int r = 0; r < 4; ++r)
+            for (const char *q = groups[r]; *q; ++q)
+            {
+                tab[(unsigned char)*q] = (int8_t)r;
+                tab[(unsigned char)(*q + 32)] = (int8_t)r;
+            }
+        init = true;
+    }
+    return tab;
+}
+
+int txr_pack_2bit(const char *ascii, uint64_t len, uint64_t *dst)
+{
+    const int8_t *tab = dna4_table();
+    const uint64_t nw = txr_packed_words(len);
+    uint64_t i = 0;
+    for (uint64_t w = 0; w + 1 < nw; ++w)
+    {
+        uint64_t x = 0;
+        const uint64_t end = std::min<uint64_t>(len, i + 32);
+        int sh = 62;
+        for (; i < end; ++i, sh -= 2)
+        {
+            const int8_t r = tab[(unsigned char)ascii[i]];
+            if (r < 0)
+                return set_error(TXR_ERR_FORMAT, "illegal nucleotide character 0x%02x at position %llu", (unsigned char)ascii[i],
+                                 (unsigned long long)i);
+            x |= (uint64_t)r << sh;
+        }
+        dst[w] = x;
+    }
+    dst[nw - 1] = 0;
+    return TXR_OK;
+}
+
+int txr_pack_codes(const uint8_t *codes, uint64_t len, uint64_t *dst)
+{
+    const uint64_t nw = txr_packed_words(len);
+    uint64_t i = 0;
+    for (uint64_t w = 0; w + 1 < nw; ++w)
+    {
+        uint64_t x = 0;
+        const uint64_t end = std::min<uint64_t>(len, i + 32);
+        int sh = 62;
+        for (; i < end; ++i, sh -= 2)
+        {
+            if (codes[i] > 3)
+                return set_error(TXR_ERR_FORMAT, "base code %d at position %llu", codes[i], (unsigned long long)i);
+            x |= (uint64_t)codes[i] << sh;
+        }
+        dst[w] = x;
+    }
+    dst[nw - 1] = 0;
+    return TXR_OK;
+}
+
+int txr_unpack_codes(const uint64_t *words, uint64_t len, uint8_t *codes)
+{
+    for (uint64_t i = 0; i < len; ++i)
+        codes[i] = (uint8_t)((words[i >> 5] >> (62 - 2 * (i & 31))) & 3);
+    return TXR_OK;
+}
+
+void *txr_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+    {
+        set_error(TXR_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void txr_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
+// ---- search ----
+static int validate_reads(const uint64_t *word_off, const uint32_t *len, uint64_t n)
+{
+    for (uint64_t i = 0; i + 1 < n; ++i)
+        if (word_off[i + 1] < word_off[i] + txr_packed_words(len[i]))
+            return set_error(TXR_ERR_ARG, "reads must be packed in ascending, non-overlapping order (read %llu)", (unsigned long long)i);
+    return TXR_OK;
+}
+
+int txr_search(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
+               txr_result *out)
+{
+    TRY(check_ready(c));
+    if (!words || !word_off || !len || !out)
+        return set_error(TXR_ERR_ARG, "null argument");
+    TRY(validate_reads(word_off, len, n_reads));
+    c->result.clear();
+    c->timing = txr_timing{};
+    const auto t0 = std::chrono::steady_clock::now();
+    TRY(fork_streams(c));
+    std::vector<std::pair<uint64_t, uint32_t>> plan;
+    plan_batches(c, len, n_reads, plan);
+    std::vector<BatchMeta> metas(c->n_slots);
+    const size_t S = (size_t)c->n_slots;
+    for (size_t b = 0; b < plan.size() + S - 1; ++b)
+    {
+        if (b >= S - 1 && b - (S - 1) < plan.size())
+        {
+            Slot &done = *c->slots[(b - (S - 1)) % S];
+            if (done.busy)
+                TRY(collect_batch(c, done, true));
+        }
+        if (b < plan.size())
+        {
+            Slot &s = *c->slots[b % S];
+            if (s.busy)
+                TRY(collect_batch(c, s, true));
+            BatchMeta &m = metas[b % S];
+            build_batch_meta(c, word_off, len, plan[b].first, plan[b].second, m);
+            TRY(submit_batch(c, s, m, nullptr, nullptr, words, true));
+        }
+    }
+    for (auto &s : c->slots)
+        if (s->busy)
+            TRY(collect_batch(c, *s, true));
+    TRY(join_streams(c));
+    finish_result(c, out);
+    c->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return TXR_OK;
+}
+
+int txr_reads_upload(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
+                     txr_reads **out)
+{
+    TRY(check_ready(c));
+    if (!words || !word_off || !len || !out || n_reads == 0)
+        return set_error(TXR_ERR_ARG, "null or empty argument");
+    TRY(validate_reads(word_off, len, n_reads));
+    auto r = std::make_unique<txr_reads>();
+    r->n_reads = n_reads;
+    const uint64_t first_word = word_off[0];
+    const uint64_t total_words = word_off[n_reads - 1] + txr_packed_words(len[n_reads - 1]) - first_word;
+    TRY(r->words.ensure(total_words * 8));
+    CU(cudaMemcpy(r->words.p, words + first_word, total_words * 8, cudaMemcpyHostToDevice));
+    std::vector<std::pair<uint64_t, uint32_t>> plan;
+    plan_batches(c, len, n_reads, plan);
+    r->batches.resize(plan.size());
+    for (size_t b = 0; b < plan.size(); ++b)
+    {
+        BatchMeta &m = r->batches[b];
+        build_batch_meta(c, word_off, len, plan[b].first, plan[b].second, m);
+        m.first_word -= first_word; // now relative to the resident word array
+        r->dev.push_back(std::make_unique<BatchDev>());
+        TRY(upload_batch_meta(m, *r->dev.back(), nullptr, nullptr));
+    }
+    CU(cudaDeviceSynchronize());
+    *out = r.release();
+    return TXR_OK;
+}
+
+void txr_reads_free(txr_ctx *c, txr_reads *r)
+{
+    if (!r)
+        return;
+    if (c)
+        cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    r->words.release();
+    for (auto &d : r->dev)
+        for (DevBuf *b : {&d->word_off, &d->len, &d->out_off, &d->ids_small, &d->ids_medium, &d->ids_global, &d->gtable_off})
+            b->release();
+    delete r;
+}
+
+int txr_search_resident(txr_ctx *c, txr_reads *r, int fetch, txr_result *out)
+{
+    TRY(check_ready(c));
+    if (!r || (fetch && !out))
+        return set_error(TXR_ERR_ARG, "null argument");
+    c->result.clear();
+    c->timing = txr_timing{};
+    const auto t0 = std::chrono::steady_clock::now();
+    TRY(fork_streams(c));
+    const size_t S = (size_t)c->n_slots;
+    for (size_t b = 0; b < r->batches.size(); ++b)
+    {
+        Slot &s = *c->slots[b % S];
+        if (s.busy)
+            TRY(collect_batch(c, s, fetch != 0));
+        const BatchMeta &m = r->batches[b];
+        TRY(submit_batch(c, s, m, r->dev[b].get(), r->words.as<uint64_t>() + m.first_word, nullptr, true));
+    }
+    // collect in submission order
+    for (size_t b = (r->batches.size() > S ? r->batches.size() - S : 0); b < r->batches.size(); ++b)
+    {
+        Slot &s = *c->slots[b % S];
+        if (s.busy)
+            TRY(collect_batch(c, s, fetch != 0));
+    }
+    TRY(join_streams(c));
+    if (fetch)
+        finish_result(c, out);
+    c->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return TXR_OK;
+}
+
+int txr_get_timing(txr_ctx *c, txr_timing *out)
+{
+    if (!c || !out)
+        return set_error(TXR_ERR_ARG, "null argument");
+    *out = c->timing;
+    return TXR_OK;
+}
+
+// ---- parity entry points ----
+int txr_hash_batch(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
+                   int dedup, const uint64_t **hash_off, const uint64_t **hashes)
+{
+    if (!c || !c->have_params)
+        return set_error(TXR_ERR_STATE, "txr_params_set not called");
+    CU(cudaSetDevice(c->device));
+    TRY(ensure_slots(c));
+    if (!words || !word_off || !len || !hash_off || !hashes)
+        return set_error(TXR_ERR_ARG, "null argument");
+    TRY(validate_reads(word_off, len, n_reads));
+    c->hb_off.assign(1, 0);
+    c->hb_hashes.clear();
+    std::vector<std::pair<uint64_t, uint32_t>> plan;
+    plan_batches(c, len, n_reads, plan);
+    Slot &s = *c->slots[0];
+    BatchMeta m;
+    std::vector<uint64_t> h_hashes;
+    std::vector<uint32_t> h_cnt;
+    for (auto &pb : plan)
+    {
+        build_batch_meta(c, word_off, len, pb.first, pb.second, m);
+        TRY(slot_reserve(c, s, m));
+        TRY(s.words.ensure(m.n_words * 8));
+        CU(cudaMemcpyAsync(s.words.p, words + m.first_word, m.n_words * 8, cudaMemcpyHostToDevice, s.stream));
+        TRY(upload_batch_meta(m, s.meta, s.stream, nullptr));
+        CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, s.stream));
+        TRY(launch_hash_stage(c, s, m, s.meta, s.words.as<uint64_t>(), dedup != 0));
+        CU(cudaStreamSynchronize(s.stream));
+        uint32_t ovf = 0;
+        CU(cudaMemcpy(&ovf, s.counters.as<uint32_t>() + C_HASH_OVERFLOW, 4, cudaMemcpyDeviceToHost));
+        if (ovf)
+            return set_error(TXR_ERR_OVERFLOW, "hash capacity bound violated");
+        h_hashes.resize(std::max<uint64_t>(m.total_cap, 1));
+        h_cnt.resize(m.n_reads);
+        CU(cudaMemcpy(h_hashes.data(), s.hashes.p, m.total_cap * 8, cudaMemcpyDeviceToHost));
+        const bool counted = dedup && (c->params.use_syncmer || c->params.scaling > 1);
+        const bool raw_in_nraw = c->params.use_syncmer || c->params.scaling > 1;
+        const void *src = counted || !raw_in_nraw ? s.hash_count.p : s.n_raw.p;
+        CU(cudaMemcpy(h_cnt.data(), src, (size_t)m.n_reads * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < m.n_reads; ++i)
+        {
+            c->hb_hashes.insert(c->hb_hashes.end(), h_hashes.begin() + m.out_off[i], h_hashes.begin() + m.out_off[i] + h_cnt[i]);
+            c->hb_off.push_back(c->hb_hashes.size());
+        }
+    }
+    *hash_off = c->hb_off.data();
+    *hashes = c->hb_hashes.data();
+    return TXR_OK;
+}
+
+int txr_ixf_bulk_count(txr_ctx *c, uint64_t ixf_idx, const uint64_t *values, uint64_t n, uint32_t *counts)
+{
+    if (!c || !c->index.loaded)
+        return set_error(TXR_ERR_STATE, "no index uploaded");
+    if (ixf_idx >= c->index.ixf.size() || (!values && n) || !counts || n > 0xffffffffu)
+        return set_error(TXR_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    TRY(ensure_slots(c));
+    const IxfDev &d = c->index.ixf[ixf_idx];
+    TRY(c->scratch_a.ensure(std::max<uint64_t>(n, 1) * 8));
+    TRY(c->scratch_b.ensure((size_t)d.tbins * 4));
+    cudaStream_t st = c->slots[0]->stream;
+    if (n)
+        CU(cudaMemcpyAsync(c->scratch_a.p, values, n * 8, cudaMemcpyHostToDevice, st));
+    CU(launch_bulk_count(d, c->scratch_a.as<uint64_t>(), (uint32_t)n, c->scratch_b.as<uint32_t>(), st));
+    CU(cudaMemcpyAsync(counts, c->scratch_b.p, (size_t)d.bins * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return TXR_OK;
+}
+
+} // extern "C"

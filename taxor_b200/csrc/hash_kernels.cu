@@ -1,0 +1,697 @@
+// hash_kernels.cu -- kernel #1 of the `taxor search` hot path for sm_100a.
+//
+//   syncmer_kernel<K,S,T>   open canonical syncmers -> wyhash (replaces hashing::seq_to_syncmers,
+//                           src/hashing/syncmer.cpp:80-165, before the set insert)
+//   syncmer_generic_kernel  same for any (k,s,t): one thread per read, sequential restatement
+//   kmer_kernel             canonical k-mers XOR seed (replaces seq | minimiser_hash with window == k,
+//                           src/main/taxor_search.cpp:210-212,240-256)
+//   dedup_smem_kernel /     per-read distinct set (the ankerl::unordered_dense::set of syncmer.cpp:145) and the
+//   dedup_global_kernel /   FracMin scaling filter (taxor_search.cpp:223-233, 244-251)
+//   filter_kernel
+//
+// Design (not a translation): reads are 2-bit packed MSB-first, so the forward code of any s-mer / k-mer is a
+// bit field of the packed stream and its reverse complement is a bit field of the bit-reversed, complemented
+// stream.  One warp owns one read and walks it in tiles of 1024 windows; each lane owns 32 consecutive windows
+// whose 42 canonical s-mers live in registers.  A k-mer is an open syncmer iff the s-mer at offset t-1 is the
+// minimum of its k-s+1 s-mers, i.e. iff it is a STRICT minimum of the t-1 s-mers to its left and the k-s+1-t to
+// its right: two fixed-width sliding minima computed by doubling.  Whenever that s-mer only TIES the
+// neighbourhood minimum, the reference's history-dependent tie rule decides (leftmost minimum in the first
+// window, rightmost on a rescan, no replacement on equal arrival; syncmer.cpp:116-140); such tiles are replayed
+// sequentially by lane 0 with the exact rule, anchored at the nearest window whose minimum is unique.
+#include "device_types.cuh"
+#include "ixf_arith.cuh"
+
+namespace txr
+{
+constexpr int kHashWarps = 4; // warps per CTA of the syncmer kernel
+
+namespace
+{
+__device__ __forceinline__ uint64_t pair_swap(uint64_t y)
+{
+    return ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);
+}
+// reverse complement of a 64-base block (2-bit groups reversed, each complemented)
+__device__ __forceinline__ uint64_t revcomp_block(uint64_t x) { return pair_swap(__brevll(~x)); }
+
+// forward code of the n-mer starting at base `pos` of a packed read (n <= 32)
+__device__ __forceinline__ uint64_t mer_at(const uint64_t *__restrict__ w, uint64_t pos, int n)
+{
+    const uint64_t wi = pos >> 5;
+    const int off = (int)(pos & 31) * 2;
+    uint64_t x = w[wi];
+    if (off)
+        x = (x << off) | (w[wi + 1] >> (64 - off));
+    return x >> (64 - 2 * n);
+}
+__device__ __forceinline__ uint64_t revcomp_mer(uint64_t fwd, int n)
+{
+    return pair_swap(__brevll(~fwd)) >> (64 - 2 * n);
+}
+__device__ __forceinline__ uint64_t canon_mer_at(const uint64_t *__restrict__ w, uint64_t pos, int n)
+{
+    const uint64_t f = mer_at(w, pos, n);
+    const uint64_t r = revcomp_mer(f, n);
+    return f < r ? f : r;
+}
+
+// static bit-field extraction from a 128-bit value held as four 32-bit registers (x[3] most significant)
+template <int START, int LEN>
+__device__ __forceinline__ uint32_t field128(const uint32_t (&x)[4])
+{
+    constexpr int sh = 128 - 2 * (START + LEN);
+    static_assert(sh >= 0 && 2 * LEN <= 32, "field out of range");
+    constexpr int wi = sh >> 5, b = sh & 31;
+    constexpr uint32_t mask = (2 * LEN == 32) ? 0xffffffffu : ((1u << (2 * LEN)) - 1u);
+    const uint32_t lo = x[wi];
+    const uint32_t hi = (wi + 1 < 4) ? x[wi + 1 < 4 ? wi + 1 : 3] : 0u;
+    return __funnelshift_r(lo, hi, b) & mask;
+}
+
+template <int Q, int QN, int S>
+struct SmerFill
+{
+    __device__ __forceinline__ static void run(const uint32_t (&f)[4], const uint32_t (&r)[4], uint32_t (&v)[QN])
+    {
+        const uint32_t a = field128<Q, S>(f);
+        const uint32_t b = field128<64 - Q - S, S>(r);
+        v[Q] = min(a, b);
+        SmerFill<Q + 1, QN, S>::run(f, r, v);
+    }
+};
+template <int QN, int S>
+struct SmerFill<QN, QN, S>
+{
+    __device__ __forceinline__ static void run(const uint32_t (&)[4], const uint32_t (&)[4], uint32_t (&)[QN]) {}
+};
+
+
+// min(v[start .. start+N-1]) from the doubling tables (all indices are compile-time after unrolling)
+template <int N, int QN>
+__device__ __forceinline__ uint32_t range_min(const uint32_t (&v)[QN], const uint32_t (&m2)[QN], const uint32_t (&m4)[QN],
+                                              const uint32_t (&m8)[QN], const uint32_t (&m16)[QN], int start)
+{
+    if constexpr (N == 0)
+        return 0xffffffffu;
+    else if constexpr (N == 1)
+        return v[start];
+    else if constexpr (N < 4)
+        return min(m2[start], m2[start + N - 2]);
+    else if constexpr (N < 8)
+        return min(m4[start], m4[start + N - 4]);
+    else if constexpr (N < 16)
+        return min(m8[start], m8[start + N - 8]);
+    else
+        return min(m16[start], m16[start + N - 16]);
+}
+
+// exact sequential state of the reference scan --------------------------------------------------------------
+struct ScanState
+{
+    uint64_t min_val;
+    uint64_t min_pos; // position (s-mer start) of the current window minimum
+};
+
+// minimum of window j (s-mers j .. j+wn-1): value, leftmost and rightmost position
+__device__ void window_min(const uint64_t *w, uint64_t j, int wn, int s, uint64_t &mv, uint64_t &lm, uint64_t &rm)
+{
+    mv = ~0ULL;
+    lm = rm = j;
+    for (int q = 0; q < wn; ++q)
+    {
+        const uint64_t v = canon_mer_at(w, j + q, s);
+        if (v < mv)
+        {
+            mv = v;
+            lm = rm = j + q;
+        }
+        else if (v == mv)
+            rm = j + q;
+    }
+}
+
+// state after window j, given the state after window j-1 (syncmer.cpp:125-140); v_new = s-mer j+wn-1
+__device__ __forceinline__ void scan_step(const uint64_t *w, uint64_t j, int wn, int s, uint64_t v_new, ScanState &st)
+{
+    if (st.min_pos == j - 1) // the minimum left the window: rescan, rightmost minimum wins
+    {
+        uint64_t mv, lm, rm;
+        window_min(w, j, wn, s, mv, lm, rm);
+        st.min_val = mv;
+        st.min_pos = rm;
+    }
+    else if (v_new < st.min_val) // strictly smaller arrival
+    {
+        st.min_val = v_new;
+        st.min_pos = j + wn - 1;
+    }
+}
+
+// exact state after window j0 of a read, derived from the nearest anchor (a window with a unique minimum,
+// or window 0 where the leftmost minimum is taken; syncmer.cpp:116-123)
+__device__ ScanState scan_state_at(const uint64_t *w, uint64_t j0, int wn, int s)
+{
+    uint64_t a = j0;
+    uint64_t mv, lm, rm;
+    while (true)
+    {
+        window_min(w, a, wn, s, mv, lm, rm);
+        if (lm == rm || a == 0)
+            break;
+        --a;
+    }
+    ScanState st{mv, lm};
+    for (uint64_t j = a + 1; j <= j0; ++j)
+        scan_step(w, j, wn, s, canon_mer_at(w, j + wn - 1, s), st);
+    return st;
+}
+} // namespace
+
+// -----------------------------------------------------------------------------------------------------------
+// fast syncmer kernel: one warp per read, 2S <= 32
+// -----------------------------------------------------------------------------------------------------------
+template <int K, int S, int T>
+__global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
+{
+    constexpr int WN = K - S + 1;    // s-mers per k-mer window
+    constexpr int QN = 32 + WN - 1;  // s-mers a lane needs for its 32 windows
+    constexpr int NL = T - 1;        // neighbourhood left of the candidate s-mer
+    constexpr int NR = WN - T;       // ... and right of it
+    static_assert(32 + K - 1 <= 64, "two packed words per lane");
+    static_assert(T >= 1 && T <= WN, "t out of range");
+
+    // per warp: canonical s-mers of the tile (slow path only), later reused for the compacted selected windows
+    __shared__ uint32_t s_v[kHashWarps][kTileWindows + 32];
+    __shared__ uint32_t s_sel[kHashWarps][32];      // per-lane selection masks written by the slow path
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    while (true)
+    {
+        uint32_t r = 0;
+        if (lane == 0)
+            r = atomicAdd(a.work_counter, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= a.n_reads)
+            break;
+        const uint32_t L = a.len[r];
+        const uint64_t W = L >= (uint32_t)K ? (uint64_t)L - K + 1 : 0;
+        const uint64_t *__restrict__ w = a.words + a.word_off[r];
+        const uint64_t nw = ((uint64_t)L + 31) / 32 + 1;
+        uint64_t *__restrict__ out = a.out + a.out_off[r];
+        const uint64_t cap = a.out_off[r + 1] - a.out_off[r];
+        uint64_t cursor = 0;
+        bool carry_valid = false;
+        ScanState carry{0, 0};
+
+        for (uint64_t tile = 0; tile < W; tile += kTileWindows)
+        {
+            const uint64_t g = (tile >> 5) + lane;
+            const uint64_t hi = g < nw ? w[g] : 0;
+            uint64_t lo = __shfl_down_sync(0xffffffffu, hi, 1);
+            if (lane == 31)
+                lo = g + 1 < nw ? w[g + 1] : 0;
+            const uint64_t rhi = revcomp_block(lo), rlo = revcomp_block(hi);
+            const uint32_t f[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
+            const uint32_t rc[4] = {(uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32)};
+
+            uint32_t v[QN];
+            SmerFill<0, QN, S>::run(f, rc, v);
+
+            // sliding minima by doubling: mN[q] = min(v[q .. q+N-1]) (clamped at the end of the lane's range)
+            uint32_t m2[QN], m4[QN], m8[QN], m16[QN];
+#pragma unroll
+            for (int q = 0; q < QN; ++q)
+                m2[q] = q + 1 < QN ? min(v[q], v[q + 1]) : v[q];
+#pragma unroll
+            for (int q = 0; q < QN; ++q)
+                m4[q] = q + 2 < QN ? min(m2[q], m2[q + 2]) : m2[q];
+#pragma unroll
+            for (int q = 0; q < QN; ++q)
+                m8[q] = q + 4 < QN ? min(m4[q], m4[q + 4]) : m4[q];
+#pragma unroll
+            for (int q = 0; q < QN; ++q)
+                m16[q] = q + 8 < QN ? min(m8[q], m8[q + 8]) : m8[q];
+
+            // candidate s-mer of window i is v[i+T-1]; strict minimum of NL left and NR right neighbours
+            uint32_t sel = 0, tie = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+            {
+                const uint32_t other = min(range_min<NL>(v, m2, m4, m8, m16, i), range_min<NR>(v, m2, m4, m8, m16, i + T));
+                const uint32_t c = v[i + T - 1];
+                sel |= (c < other ? 1u : 0u) << i;
+                tie |= (c == other ? 1u : 0u) << i;
+            }
+            const uint64_t j0 = tile + 32ull * lane;
+            const uint32_t valid = j0 >= W ? 0u : (W - j0 >= 32 ? 0xffffffffu : ((1u << (uint32_t)(W - j0)) - 1u));
+            sel &= valid;
+            tie &= valid;
+
+            if (__any_sync(0xffffffffu, tie != 0))
+            {
+                // exact replay of the tile by lane 0 (reference tie rules)
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    s_v[wib][32 * lane + i] = v[i];
+                if (lane == 31)
+                {
+#pragma unroll
+                    for (int i = 32; i < QN; ++i)
+                        s_v[wib][32 * lane + i] = v[i];
+                }
+                s_sel[wib][lane] = 0;
+                __syncwarp();
+                if (lane == 0)
+                {
+                    const uint64_t jend = min(W, tile + (uint64_t)kTileWindows);
+                    ScanState st;
+                    uint64_t j = tile;
+                    if (tile == 0)
+                    {
+                        uint64_t mv, lm, rm;
+                        window_min(w, 0, WN, S, mv, lm, rm);
+                        st = ScanState{mv, lm};
+                        if (st.min_pos == (uint64_t)(T - 1))
+                            s_sel[wib][0] |= 1u;
+                        j = 1;
+                    }
+                    else
+                        st = carry_valid ? carry : scan_state_at(w, tile - 1, WN, S);
+                    for (; j < jend; ++j)
+                    {
+                        const uint32_t lj = (uint32_t)(j - tile);
+                        if (st.min_pos == j - 1)
+                        {
+                            uint32_t mv = 0xffffffffu, mp = 0;
+                            for (int q = WN - 1; q >= 0; --q) // rightmost minimum
+                            {
+                                const uint32_t x = s_v[wib][lj + q];
+                                if (x < mv)
+                                {
+                                    mv = x;
+                                    mp = q;
+                                }
+                            }
+                            st.min_val = mv;
+                            st.min_pos = j + mp;
+                        }
+                        else
+                        {
+                            const uint32_t x = s_v[wib][lj + WN - 1];
+                            if (x < st.min_val)
+                            {
+                                st.min_val = x;
+                                st.min_pos = j + WN - 1;
+                            }
+                        }
+                        if (st.min_pos == j + T - 1)
+                            s_sel[wib][lj >> 5] |= 1u << (lj & 31);
+                    }
+                    carry = st;
+                }
+                __syncwarp();
+                sel = s_sel[wib][lane];
+                carry.min_val = __shfl_sync(0xffffffffu, carry.min_val, 0);
+                carry.min_pos = __shfl_sync(0xffffffffu, carry.min_pos, 0);
+                carry_valid = true;
+            }
+            else
+                carry_valid = false;
+
+            // compact the selected windows of the tile, then hash them with all lanes busy
+            const uint32_t n = __popc(sel);
+            uint32_t incl = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t t2 = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d)
+                    incl += t2;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_v[wib]);
+            uint32_t at = incl - n;
+            uint32_t m = sel;
+            while (m)
+            {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                s_pos[at++] = (uint16_t)(32 * lane + b);
+            }
+            __syncwarp();
+            for (uint32_t it = lane; it < total; it += 32)
+            {
+                const uint64_t pos = tile + s_pos[it];
+                const uint64_t h = wyhash_u64(canon_mer_at(w, pos, K));
+                if (cursor + it < cap)
+                    out[cursor + it] = h;
+            }
+            cursor += total;
+            __syncwarp();
+        }
+        if (lane == 0)
+        {
+            a.n_out[r] = (uint32_t)min(cursor, cap);
+            if (cursor > cap)
+                *a.overflow = 1u;
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// generic syncmer kernel: any (k <= 32, s < k, t); one thread per read, sequential scan with the reference's
+// state machine (syncmer.cpp:97-146).  Fallback only -- correctness first.
+// -----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) syncmer_generic_kernel(HashArgs a)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_reads)
+        return;
+    const int K = a.k, S = a.s, T = a.t, WN = K - S + 1;
+    const uint32_t L = a.len[r];
+    const uint64_t W = L >= (uint32_t)K ? (uint64_t)L - K + 1 : 0;
+    const uint64_t *w = a.words + a.word_off[r];
+    uint64_t *out = a.out + a.out_off[r];
+    const uint64_t cap = a.out_off[r + 1] - a.out_off[r];
+    uint64_t cursor = 0;
+    ScanState st{0, 0};
+    for (uint64_t j = 0; j < W; ++j)
+    {
+        if (j == 0)
+        {
+            uint64_t mv, lm, rm;
+            window_min(w, 0, WN, S, mv, lm, rm);
+            st = ScanState{mv, lm};
+        }
+        else
+            scan_step(w, j, WN, S, canon_mer_at(w, j + WN - 1, S), st);
+        if (st.min_pos == j + T - 1)
+        {
+            if (cursor < cap)
+                out[cursor] = wyhash_u64(canon_mer_at(w, j, K));
+            ++cursor;
+        }
+    }
+    a.n_out[r] = (uint32_t)min(cursor, cap);
+    if (cursor > cap)
+        *a.overflow = 1u;
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// canonical k-mer kernel (window == k): one warp per read; window j of a tile is handled by lane j % 32 so
+// that the 8-byte stores of a warp are contiguous.
+// -----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kmer_kernel(HashArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int K = a.k;
+    while (true)
+    {
+        uint32_t r = 0;
+        if (lane == 0)
+            r = atomicAdd(a.work_counter, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= a.n_reads)
+            break;
+        const uint32_t L = a.len[r];
+        const uint64_t W = L >= (uint32_t)K ? (uint64_t)L - K + 1 : 0;
+        const uint64_t *__restrict__ w = a.words + a.word_off[r];
+        const uint64_t nw = ((uint64_t)L + 31) / 32 + 1;
+        uint64_t *__restrict__ out = a.out + a.out_off[r];
+        const uint64_t cap = a.out_off[r + 1] - a.out_off[r];
+        for (uint64_t tile = 0; tile < W; tile += kTileWindows)
+        {
+            const uint64_t g = (tile >> 5) + lane;
+            const uint64_t mine = g < nw ? w[g] : 0;
+            const uint64_t extra = (lane == 0 && g + 32 < nw) ? w[g + 32] : 0; // word 32 of the tile
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i)
+            {
+                const uint64_t hi = __shfl_sync(0xffffffffu, mine, i);
+                uint64_t lo = __shfl_sync(0xffffffffu, mine, (i + 1) & 31);
+                const uint64_t ex = __shfl_sync(0xffffffffu, extra, 0);
+                if (i == 31)
+                    lo = ex;
+                const uint64_t j = tile + 32ull * i + lane;
+                const int off = 2 * lane;
+                const uint64_t x = off ? (hi << off) | (lo >> (64 - off)) : hi;
+                const uint64_t fw = x >> (64 - 2 * K);
+                const uint64_t rv = revcomp_mer(fw, K);
+                const uint64_t fs = fw ^ a.kmer_seed, rs = rv ^ a.kmer_seed;
+                if (j < W && j < cap)
+                    out[j] = fs < rs ? fs : rs;
+            }
+        }
+        if (lane == 0)
+        {
+            a.n_out[r] = (uint32_t)min(W, cap);
+            if (W > cap)
+                *a.overflow = 1u;
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// per-read distinct set + FracMin scaling filter
+// -----------------------------------------------------------------------------------------------------------
+namespace
+{
+__device__ __forceinline__ bool scaling_keep(uint64_t h, uint32_t scaling, double limit)
+{
+    // taxor_search.cpp:227-228: double(wyhash(h)) <= double(UINT64_MAX) / double(scaling)
+    return scaling <= 1 || __ull2double_rn(wyhash_u64(h)) <= limit;
+}
+
+template <typename table_ptr_t>
+__device__ __forceinline__ void table_insert(table_ptr_t tab, uint32_t mask, uint64_t h)
+{
+    uint32_t slot = (uint32_t)(h ^ (h >> 32)) & mask;
+    while (true)
+    {
+        const unsigned long long old = atomicCAS((unsigned long long *)&tab[slot], (unsigned long long)kEmptyKey, (unsigned long long)h);
+        if (old == kEmptyKey || old == h)
+            return;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// compacts the non-empty slots of tab[0..slots) that pass the scaling filter into dst; returns the count.
+// Block-wide; every thread must call it.
+__device__ uint32_t table_compact(const uint64_t *tab, uint32_t slots, uint64_t *dst, bool extra_empty_key,
+                                  uint32_t scaling, double limit, uint32_t *s_scan)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t base = 0;
+    for (uint32_t c0 = 0; c0 < slots; c0 += nt)
+    {
+        const uint32_t i = c0 + tid;
+        uint64_t key = kEmptyKey;
+        if (i < slots)
+            key = tab[i];
+        const bool keep = key != kEmptyKey && scaling_keep(key, scaling, limit);
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0)
+            s_scan[wid] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, all = 0;
+        for (int q = 0; q < (nt >> 5); ++q)
+        {
+            const uint32_t c = s_scan[q];
+            if (q < wid)
+                before += c;
+            all += c;
+        }
+        if (keep)
+            dst[base + before + __popc(bal & ((1u << lane) - 1u))] = key;
+        base += all;
+        __syncthreads();
+    }
+    if (extra_empty_key && scaling_keep(kEmptyKey, scaling, limit))
+    {
+        if (tid == 0)
+            dst[base] = kEmptyKey;
+        ++base;
+    }
+    return base;
+}
+} // namespace
+
+// one CTA per read, table in shared memory (SLOTS a power of two >= 2 * capacity of the class)
+template <int SLOTS>
+__global__ void dedup_smem_kernel(DedupArgs a)
+{
+    extern __shared__ uint64_t s_tab[];
+    __shared__ uint32_t s_scan[32];
+    __shared__ int s_saw_empty;
+    const uint32_t id = blockIdx.x;
+    if (id >= a.n_ids)
+        return;
+    const uint32_t r = a.read_ids ? a.read_ids[id] : id;
+    for (int i = threadIdx.x; i < SLOTS; i += blockDim.x)
+        s_tab[i] = kEmptyKey;
+    if (threadIdx.x == 0)
+        s_saw_empty = 0;
+    __syncthreads();
+    uint64_t *p = a.hashes + a.out_off[r];
+    const uint32_t n = a.n_raw[r];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const uint64_t h = p[i];
+        if (h == kEmptyKey)
+            s_saw_empty = 1;
+        else
+            table_insert(s_tab, SLOTS - 1, h);
+    }
+    __syncthreads();
+    const uint32_t cnt = table_compact(s_tab, SLOTS, p, s_saw_empty != 0, a.scaling, a.scaling_limit, s_scan);
+    if (threadIdx.x == 0)
+        a.hash_count[r] = cnt;
+}
+
+// one CTA per read, table in global memory (pre-filled with kEmptyKey by the host)
+__global__ void dedup_global_kernel(DedupArgs a)
+{
+    __shared__ uint32_t s_scan[32];
+    __shared__ int s_saw_empty;
+    const uint32_t id = blockIdx.x;
+    if (id >= a.n_ids)
+        return;
+    const uint32_t r = a.read_ids ? a.read_ids[id] : id;
+    uint64_t *tab = a.gtable + a.gtable_off[id];
+    const uint32_t slots = (uint32_t)(a.gtable_off[id + 1] - a.gtable_off[id]);
+    if (threadIdx.x == 0)
+        s_saw_empty = 0;
+    __syncthreads();
+    uint64_t *p = a.hashes + a.out_off[r];
+    const uint32_t n = a.n_raw[r];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const uint64_t h = p[i];
+        if (h == kEmptyKey)
+            s_saw_empty = 1;
+        else
+            table_insert(tab, slots - 1, h);
+    }
+    __threadfence();
+    __syncthreads();
+    const uint32_t cnt = table_compact(tab, slots, p, s_saw_empty != 0, a.scaling, a.scaling_limit, s_scan);
+    if (threadIdx.x == 0)
+        a.hash_count[r] = cnt;
+}
+
+// k-mer mode with scaling > 1: order-preserving filter, one CTA per read (no dedup: duplicates are kept,
+// taxor_search.cpp:242-255)
+__global__ void filter_kernel(DedupArgs a)
+{
+    __shared__ uint32_t s_scan[32];
+    const uint32_t r = blockIdx.x;
+    if (r >= a.n_ids)
+        return;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    uint64_t *p = a.hashes + a.out_off[r];
+    const uint32_t n = a.n_raw[r];
+    uint32_t base = 0;
+    for (uint32_t c0 = 0; c0 < n; c0 += nt)
+    {
+        const uint32_t i = c0 + tid;
+        uint64_t key = 0;
+        bool keep = false;
+        if (i < n)
+        {
+            key = p[i];
+            keep = scaling_keep(key, a.scaling, a.scaling_limit);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0)
+            s_scan[wid] = __popc(bal);
+        __syncthreads(); // all reads of this chunk are done before anyone writes below it
+        uint32_t before = 0, all = 0;
+        for (int q = 0; q < (nt >> 5); ++q)
+        {
+            const uint32_t c = s_scan[q];
+            if (q < wid)
+                before += c;
+            all += c;
+        }
+        if (keep)
+            p[base + before + __popc(bal & ((1u << lane) - 1u))] = key;
+        base += all;
+        __syncthreads();
+    }
+    if (tid == 0)
+        a.hash_count[r] = base;
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// host-side launchers
+// -----------------------------------------------------------------------------------------------------------
+template <int K, int S, int T>
+static bool try_launch_syncmer(const HashArgs &a, int k, int s, int t, int grid, cudaStream_t st)
+{
+    if (k != K || s != S || t != T)
+        return false;
+    syncmer_kernel<K, S, T><<<grid, 32 * kHashWarps, 0, st>>>(a);
+    return true;
+}
+
+cudaError_t launch_syncmer(const HashArgs &a, int sm_count, cudaStream_t st)
+{
+    const int grid = sm_count * 8;
+    bool ok = try_launch_syncmer<22, 12, 5>(a, a.k, a.s, a.t, grid, st)      // Taxor's published indexes
+              || try_launch_syncmer<20, 10, 5>(a, a.k, a.s, a.t, grid, st)   // taxor build defaults
+              || try_launch_syncmer<24, 12, 6>(a, a.k, a.s, a.t, grid, st)
+              || try_launch_syncmer<26, 14, 6>(a, a.k, a.s, a.t, grid, st)
+              || try_launch_syncmer<28, 14, 7>(a, a.k, a.s, a.t, grid, st)
+              || try_launch_syncmer<30, 16, 7>(a, a.k, a.s, a.t, grid, st)
+              || try_launch_syncmer<18, 10, 4>(a, a.k, a.s, a.t, grid, st)
+              || try_launch_syncmer<16, 8, 4>(a, a.k, a.s, a.t, grid, st);
+    if (!ok)
+        syncmer_generic_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_syncmer_generic(const HashArgs &a, cudaStream_t st)
+{
+    syncmer_generic_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kmer(const HashArgs &a, int sm_count, cudaStream_t st)
+{
+    kmer_kernel<<<sm_count * 4, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dedup_small(const DedupArgs &a, cudaStream_t st) // capacity <= 2048
+{
+    if (a.n_ids == 0)
+        return cudaSuccess;
+    dedup_smem_kernel<4096><<<a.n_ids, 128, 4096 * 8, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dedup_medium(const DedupArgs &a, cudaStream_t st) // capacity <= 8192
+{
+    if (a.n_ids == 0)
+        return cudaSuccess;
+    cudaFuncSetAttribute(dedup_smem_kernel<16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    dedup_smem_kernel<16384><<<a.n_ids, 256, 16384 * 8, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dedup_global(const DedupArgs &a, cudaStream_t st)
+{
+    if (a.n_ids == 0)
+        return cudaSuccess;
+    dedup_global_kernel<<<a.n_ids, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_filter(const DedupArgs &a, cudaStream_t st)
+{
+    if (a.n_ids == 0)
+        return cudaSuccess;
+    filter_kernel<<<a.n_ids, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+} // namespace txr

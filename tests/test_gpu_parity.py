@@ -1,0 +1,217 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+from taxor_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def lowcomplexity_reads(rng):
+    """Tie-heavy inputs for the syncmer scan: homopolymers, short tandem repeats, A/T-only, palindromes."""
+    seqs = []
+    seqs.append(np.zeros(5000, np.uint8))                                   # poly-A
+    seqs.append(np.full(3000, 3, np.uint8))                                 # poly-T
+    for period in (1, 2, 3, 4, 5, 6, 7, 11, 12, 13):
+        unit = rng.integers(0, 4, period, dtype=np.uint8)
+        x = np.resize(unit, 4000).copy()
+        idx = rng.integers(0, len(x), 12)
+        x[idx] = rng.integers(0, 4, len(idx))
+        seqs.append(x)
+    seqs.append((rng.integers(0, 2, 6000) * 3).astype(np.uint8))            # A/T only
+    half = rng.integers(0, 4, 1500, dtype=np.uint8)
+    seqs.append(np.concatenate([half, (3 - half)[::-1]]))                   # reverse-complement palindrome
+    r = rng.integers(0, 4, 8000, dtype=np.uint8)
+    r[2000:2100] = 0
+    r[5000:5300] = np.resize(np.array([0, 1], np.uint8), 300)
+    seqs.append(r)                                                          # random with embedded repeats
+    big = rng.integers(0, 4, 40000, dtype=np.uint8)
+    big[1000:9000] = 2                                                      # 8 kb homopolymer across many tiles
+    seqs.append(big)
+    return seqs
+
+
+def edge_reads(rng, k):
+    seqs = [np.zeros(0, np.uint8), rng.integers(0, 4, 1, dtype=np.uint8), rng.integers(0, 4, k - 1, dtype=np.uint8),
+            rng.integers(0, 4, k, dtype=np.uint8), rng.integers(0, 4, k + 1, dtype=np.uint8)]
+    for n in (31, 32, 33, 63, 64, 65, 1023 + k - 1, 1024 + k - 1, 1025 + k - 1, 2048 + k, 3000):
+        seqs.append(rng.integers(0, 4, n, dtype=np.uint8))
+    return seqs
+
+
+@pytest.mark.parametrize("k,s", [(22, 12), (20, 10), (24, 12), (30, 16), (16, 8), (21, 11), (28, 20), (12, 11)])
+def test_syncmer_hash_parity(ctx, oracle, k, s):
+    """kernel #1 (fast template or generic fallback) == oracle: raw emission multiset and distinct set per read."""
+    t = oracle.t_syncmer(k, s)
+    ctx.set_params(k=k, s=s, t=t, use_syncmer=True, window_size=20)
+    rng = np.random.default_rng(k * 100 + s)
+    seqs = edge_reads(rng, k) + lowcomplexity_reads(rng)
+    seqs += [rng.integers(0, 4, int(n), dtype=np.uint8) for n in rng.integers(500, 12000, 40)]
+    reads = capi.pack_codes(seqs)
+    off_raw, h_raw = ctx.hash_batch(reads, dedup=False)
+    off, h = ctx.hash_batch(reads, dedup=True)
+    for i, c in enumerate(seqs):
+        exp_raw = oracle.syncmer_hashes_raw(c, k, s, t)
+        got_raw = h_raw[int(off_raw[i]):int(off_raw[i + 1])]
+        assert np.array_equal(np.sort(got_raw), np.sort(exp_raw)), (i, len(c))
+        exp = oracle.syncmer_hashes(c, k, s, t)
+        got = h[int(off[i]):int(off[i + 1])]
+        assert len(got) == len(exp) and np.array_equal(np.sort(got), np.sort(exp)), (i, len(c))
+
+
+def test_syncmer_t_variants(ctx, oracle):
+    """t is read from the index file, not derived: every legal offset must work (generic kernel)."""
+    rng = np.random.default_rng(5)
+    seqs = [rng.integers(0, 4, 3000, dtype=np.uint8) for _ in range(6)] + lowcomplexity_reads(rng)[:6]
+    reads = capi.pack_codes(seqs)
+    for t in (1, 3, 6, 11):
+        ctx.set_params(k=22, s=12, t=t, use_syncmer=True, window_size=20)
+        off, h = ctx.hash_batch(reads, dedup=True)
+        for i, c in enumerate(seqs):
+            exp = oracle.syncmer_hashes(c, 22, 12, t)
+            assert np.array_equal(np.sort(h[int(off[i]):int(off[i + 1])]), np.sort(exp)), (t, i)
+
+
+@pytest.mark.parametrize("k", [20, 22, 31, 32, 8])
+def test_kmer_hash_parity(ctx, oracle, k):
+    """canonical k-mer mode: same values in the same (position) order, duplicates kept."""
+    ctx.set_params(k=k, use_syncmer=False, window_size=k)
+    rng = np.random.default_rng(k)
+    seqs = edge_reads(rng, k) + lowcomplexity_reads(rng)[:4] + [rng.integers(0, 4, int(n), dtype=np.uint8) for n in rng.integers(100, 9000, 20)]
+    reads = capi.pack_codes(seqs)
+    off, h = ctx.hash_batch(reads, dedup=True)
+    for i, c in enumerate(seqs):
+        exp = oracle.kmer_hashes(c, k)
+        assert np.array_equal(h[int(off[i]):int(off[i + 1])], exp), (i, len(c))
+
+
+def test_scaling_filter(ctx, oracle):
+    rng = np.random.default_rng(3)
+    seqs = [rng.integers(0, 4, 6000, dtype=np.uint8) for _ in range(8)]
+    reads = capi.pack_codes(seqs)
+    for scaling in (10, 100):
+        ctx.set_params(k=22, s=12, t=5, use_syncmer=True, window_size=20, scaling=scaling)
+        off, h = ctx.hash_batch(reads, dedup=True)
+        for i, c in enumerate(seqs):
+            exp = [x for x in oracle.syncmer_hashes(c, 22, 12, 5).tolist() if oracle.scaling_keep(x, scaling)]
+            assert np.array_equal(np.sort(h[int(off[i]):int(off[i + 1])]), np.sort(np.array(exp, np.uint64)))
+        ctx.set_params(k=20, use_syncmer=False, window_size=20, scaling=scaling)
+        off, h = ctx.hash_batch(reads, dedup=True)
+        for i, c in enumerate(seqs):
+            exp = [x for x in oracle.kmer_hashes(c, 20).tolist() if oracle.scaling_keep(x, scaling)]
+            assert np.array_equal(h[int(off[i]):int(off[i + 1])], np.array(exp, np.uint64))
+
+
+def test_long_sequence_hash(ctx, oracle):
+    """a genome-sized input (many tiles, global-memory dedup class)"""
+    from taxor_b200 import tools
+    n = 700_000
+    g = tools.genome(77, n)
+    reads = capi.PackedReads(g, np.zeros(1, np.uint64), np.array([n], np.uint32))
+    ctx.set_params(k=22, s=12, t=5, use_syncmer=True, window_size=20)
+    off, h = ctx.hash_batch(reads, dedup=True)
+    exp = oracle.syncmer_hashes(H.codes_of(g, n), 22, 12, 5)
+    assert np.array_equal(np.sort(h), np.sort(exp))
+
+
+@pytest.mark.parametrize("t_max", [8, 64])
+def test_bulk_count_parity(ctx, oracle, t_max):
+    """kernel #2's probe/count against bulk_count of the oracle, every IXF of a small hierarchy."""
+    ds = H.make_dataset(oracle, n_genomes=20, genome_len=40_000, t_max=t_max)
+    H.upload(ctx, ds)
+    oh = oracle.make_hixf(ds.arrays)
+    rng = np.random.default_rng(0)
+    member = np.concatenate([ds.hixf._ub[3][:500], ds.hixf._ub[7][:300]])
+    values = np.concatenate([member, rng.integers(0, 2**63, 2000, dtype=np.uint64)])
+    for x in range(ds.hixf.n_ixf):
+        got = ctx.ixf_bulk_count(x, values, int(ds.hixf.bins[x]))
+        exp = oracle.ixf_bulk_count(oh, x, values)
+        assert np.array_equal(got, exp), x
+    assert np.array_equal(ctx.ixf_bulk_count(0, np.zeros(0, np.uint64), int(ds.hixf.bins[0])), np.zeros(int(ds.hixf.bins[0]), np.uint32))
+
+
+def _search_case(ctx, oracle, ds, reads, **par):
+    H.upload(ctx, ds)
+    ctx.set_params(k=ds.k, s=ds.s, t=ds.t, use_syncmer=ds.use_syncmer, window_size=par.get("window_size", 20),
+                   scaling=par.get("scaling", 1), percentage=par.get("percentage", -1.0), error_rate=par.get("error_rate", 0.1))
+    res = ctx.search(reads)
+    codes, off = H.reads_to_codes(reads)
+    ora = oracle.search_batch(oracle.make_hixf(ds.arrays), codes, off, k=ds.k, s=ds.s, t=ds.t, use_syncmer=ds.use_syncmer,
+                              window_size=par.get("window_size", 20), scaling=par.get("scaling", 1),
+                              percentage=par.get("percentage", -1.0), error_rate=par.get("error_rate", 0.1))
+    H.assert_same_search(res, ora, reads.n)
+    return res, ora
+
+
+@pytest.mark.parametrize("t_max,n_genomes", [(8, 40), (64, 100), (4, 70)])
+def test_search_parity_syncmer(ctx, oracle, t_max, n_genomes):
+    """whole hot path == oracle: hash counts, thresholds, per-(read,user bin) counts, DFS order, 0.8*max filter."""
+    ds = H.make_dataset(oracle, n_genomes=n_genomes, genome_len=50_000, t_max=t_max)
+    rng = np.random.default_rng(1)
+    lengths = rng.integers(300, 12000, 300)
+    reads = H.make_reads(ds, lengths, err=0.05)
+    res, ora = _search_case(ctx, oracle, ds, reads, error_rate=0.1)
+    assert int(res.hit_begin[-1]) > 50          # the workload really descends and reports
+    assert ds.hixf.n_ixf > 1
+    # resident path gives the same answer
+    h = ctx.upload_reads(reads)
+    res2 = ctx.search_resident(h, fetch=True)
+    ctx.free_reads(h)
+    H.assert_same_search(res2, ora, reads.n)
+
+
+def test_search_threshold_zero_flood(ctx, oracle):
+    """H5: reads shorter than k have hash_count 0 -> threshold 0 -> every user bin reported, every merged bin descended."""
+    ds = H.make_dataset(oracle, n_genomes=30, genome_len=30_000, t_max=4)
+    rng = np.random.default_rng(2)
+    seqs = [rng.integers(0, 4, n, dtype=np.uint8) for n in (0, 5, 21, 22, 40, 500)]
+    reads = capi.pack_codes(seqs)
+    res, ora = _search_case(ctx, oracle, ds, reads, error_rate=0.05)
+    assert len(res.hits(0)[0]) == 30 and len(res.hits(1)[0]) == 30
+
+
+def test_search_percentage_and_batching(ctx, oracle):
+    ds = H.make_dataset(oracle, n_genomes=50, genome_len=40_000, t_max=8)
+    rng = np.random.default_rng(4)
+    reads = H.make_reads(ds, rng.integers(1000, 9000, 500), err=0.03)
+    ctx.configure(max_batch_reads=64, max_batch_bases=200_000, n_slots=3)   # many small batches through 3 slots
+    try:
+        _search_case(ctx, oracle, ds, reads, percentage=0.2)
+        ctx.configure(max_batch_reads=64, max_batch_bases=200_000, n_slots=1)
+        _search_case(ctx, oracle, ds, reads, percentage=0.05)
+    finally:
+        ctx.configure()
+
+
+def test_search_parity_kmer_mode(ctx, oracle):
+    """config-4 shape at test size: canonical 20-mers, no dedup, k-mer-model threshold."""
+    ds = H.make_dataset(oracle, n_genomes=24, genome_len=20_000, k=20, s=0, t=0, use_syncmer=False, t_max=8)
+    rng = np.random.default_rng(6)
+    lengths = np.exp(rng.uniform(np.log(1000), np.log(20000), 60)).astype(np.int64)
+    reads = H.make_reads(ds, lengths, err=0.02)
+    res, ora = _search_case(ctx, oracle, ds, reads, window_size=20, error_rate=0.02)
+    assert int(res.hit_begin[-1]) > 10
+
+
+def test_search_large_rows(ctx, oracle):
+    """IXFs wider than 512 technical bins take the CTA-per-item kernel (root T up to 4096 in real layouts)."""
+    ds = H.make_dataset(oracle, n_genomes=700, genome_len=3_000, t_max=640, size_jitter=True)
+    assert int(ds.hixf.tbins.max()) > 512
+    rng = np.random.default_rng(8)
+    reads = H.make_reads(ds, rng.integers(500, 2500, 120), err=0.02)
+    res, ora = _search_case(ctx, oracle, ds, reads, error_rate=0.1)
+    assert int(res.hit_begin[-1]) > 20
+    ds2 = H.make_dataset(oracle, n_genomes=1500, genome_len=2_500, t_max=576, size_jitter=True, seed=5000)
+    assert ds2.hixf.n_ixf > 1 and int(ds2.hixf.tbins.max()) > 512
+    reads2 = H.make_reads(ds2, rng.integers(500, 2400, 100), err=0.02)
+    _search_case(ctx, oracle, ds2, reads2, error_rate=0.1)
+
+
+def test_errors_are_loud(ctx):
+    with pytest.raises(capi.TaxorError):
+        ctx.set_params(k=20, use_syncmer=False, window_size=24)       # minimiser windows: unsupported, not silently wrong
+    with pytest.raises(capi.TaxorError):
+        capi.pack_ascii(["ACGTX"])
+    with pytest.raises(capi.TaxorError):
+        capi.Context(4096)
