@@ -186,7 +186,7 @@ def test_search_percentage_and_batching(ctx, oracle):
 
 def test_search_parity_kmer_mode(ctx, oracle):
     """config-4 shape at test size: canonical 20-mers, no dedup, k-mer-model threshold."""
-    ds = H.make_dataset(oracle, n_genomes=24, genome_len=20_000, k=20, s=0, t=0, use_syncmer=False, t_max=8)
+    ds = H.make_dataset(oracle, n_genomes=24, genome_len=60_000, k=20, s=0, t=0, use_syncmer=False, t_max=8)
     rng = np.random.default_rng(6)
     lengths = np.exp(rng.uniform(np.log(1000), np.log(20000), 60)).astype(np.int64)
     reads = H.make_reads(ds, lengths, err=0.02)
@@ -199,12 +199,12 @@ def test_search_large_rows(ctx, oracle):
     ds = H.make_dataset(oracle, n_genomes=700, genome_len=3_000, t_max=640, size_jitter=True)
     assert int(ds.hixf.tbins.max()) > 512
     rng = np.random.default_rng(8)
-    reads = H.make_reads(ds, rng.integers(500, 2500, 120), err=0.02)
+    reads = H.make_reads(ds, rng.integers(400, 1200, 120), err=0.02)
     res, ora = _search_case(ctx, oracle, ds, reads, error_rate=0.1)
     assert int(res.hit_begin[-1]) > 20
     ds2 = H.make_dataset(oracle, n_genomes=1500, genome_len=2_500, t_max=576, size_jitter=True, seed=5000)
     assert ds2.hixf.n_ixf > 1 and int(ds2.hixf.tbins.max()) > 512
-    reads2 = H.make_reads(ds2, rng.integers(500, 2400, 100), err=0.02)
+    reads2 = H.make_reads(ds2, rng.integers(400, 1000, 100), err=0.02)
     _search_case(ctx, oracle, ds2, reads2, error_rate=0.1)
 
 
