@@ -11,7 +11,7 @@
  *
  * Conventions: plain pointers and sizes only; every function returns 0 (TXR_OK) or a negative error code
  * and never throws; handles are opaque; the caller owns every host buffer it passes in; result views stay
- * valid until the next call on the same context or txr_result_free(); one context per GPU; calls on one
+ * valid until the next search call on the same context; one context per GPU; calls on one
  * context must be serialised by the caller; distinct contexts may be used from distinct host threads.
  * There is NO CPU fallback: without a CUDA device txr_ctx_create fails with TXR_ERR_CUDA.
  */
@@ -112,6 +112,8 @@ int txr_index_upload(txr_ctx *ctx, const txr_hixf_view *index);
 int txr_params_set(txr_ctx *ctx, const txr_params *params);
 /* hixf::threshold::threshold::get (src/hixf/search/threshold.hpp:51-81) with the context's parameters */
 int txr_threshold_get(txr_ctx *ctx, uint64_t hash_count, double scaling_factor, uint64_t *out);
+/* the same without a context (pure host code; usable on a machine without a GPU) */
+int txr_threshold_eval(const txr_params *params, uint64_t hash_count, double scaling_factor, uint64_t *out);
 
 /* ---- reads: 2-bit packing (A0 C1 G2 T3, seqan3::dna4 collapse of IUPAC, src/hixf/build/dna4_traits.hpp:15-18) ----
  * Layout: read r occupies 64-bit words [word_off[r], word_off[r] + ceil(len/32)] (one zero pad word),

@@ -72,6 +72,7 @@ def lib():
     L.txr_index_upload.argtypes = [vp, C.POINTER(HixfView)]
     L.txr_params_set.argtypes = [vp, C.POINTER(Params)]
     L.txr_threshold_get.argtypes = [vp, C.c_uint64, C.c_double, C.POINTER(C.c_uint64)]
+    L.txr_threshold_eval.argtypes = [C.POINTER(Params), C.c_uint64, C.c_double, C.POINTER(C.c_uint64)]
     L.txr_packed_words.argtypes = [C.c_uint64]
     L.txr_packed_words.restype = C.c_uint64
     L.txr_pack_2bit.argtypes = [C.c_char_p, C.c_uint64, vp]
@@ -94,7 +95,7 @@ def lib():
 
 
 EXPORTED = ["txr_last_error", "txr_version", "txr_ctx_create", "txr_ctx_destroy", "txr_ctx_set_stream", "txr_ctx_configure",
-            "txr_index_upload", "txr_params_set", "txr_threshold_get", "txr_packed_words", "txr_pack_2bit",
+            "txr_index_upload", "txr_params_set", "txr_threshold_get", "txr_threshold_eval", "txr_packed_words", "txr_pack_2bit",
             "txr_pack_codes", "txr_unpack_codes", "txr_host_alloc", "txr_host_free", "txr_search",
             "txr_reads_upload", "txr_reads_free", "txr_search_resident", "txr_get_timing", "txr_hash_batch",
             "txr_ixf_bulk_count"]
@@ -199,6 +200,15 @@ class SearchResult:
             k = self.keep[a:b]
             return ub[k], cnt[k]
         return ub, cnt
+
+
+def threshold_eval(count: int, scaling_factor: float = 1.0, *, k, use_syncmer=True, window_size=None, percentage=-1.0,
+                   error_rate=0.04) -> int:
+    """hixf::threshold::threshold::get without a GPU context (host mirror of the reference's threshold models)."""
+    p = Params(k, 0, 0, int(use_syncmer), k if window_size is None else window_size, 1, percentage, error_rate)
+    out = C.c_uint64()
+    _check(lib().txr_threshold_eval(C.byref(p), count, scaling_factor, C.byref(out)))
+    return out.value
 
 
 class Context:

@@ -24,7 +24,9 @@ namespace txr
 {
 cudaError_t launch_syncmer(const HashArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_kmer(const HashArgs &a, int sm_count, cudaStream_t st);
-cudaError_t launch_dedup_small(const DedupArgs &a, cudaStream_t st);
+cudaError_t launch_dedup_warp(const DedupArgs &a, int sm_count, uint32_t *work_counter, uint32_t *deferred, uint32_t *n_deferred,
+                              cudaStream_t st);
+cudaError_t launch_dedup_deferred(const DedupArgs &a, int sm_count, const uint32_t *n_deferred, cudaStream_t st);
 cudaError_t launch_dedup_medium(const DedupArgs &a, cudaStream_t st);
 cudaError_t launch_dedup_global(const DedupArgs &a, cudaStream_t st);
 cudaError_t launch_filter(const DedupArgs &a, cudaStream_t st);
@@ -175,6 +177,8 @@ enum CounterSlot : int
     C_NHITS = 0,
     C_HASH_OVERFLOW = 1,
     C_HASH_WORK = 2,
+    C_DEDUP_WORK = 3,
+    C_DEDUP_DEFERRED = 4,
     C_LEVEL0 = 8, // per level: n_small, n_large, cursor_small, cursor_large
     C_PER_LEVEL = 4,
     C_MAX_LEVELS = 32,
@@ -188,7 +192,7 @@ struct Slot
     cudaEvent_t ev[6]{}; // start, h2d done, hash done, dedup done, query done, d2h done
     DevBuf words;
     BatchDev meta;
-    DevBuf hashes, n_raw, hash_count, gtable;
+    DevBuf hashes, n_raw, hash_count, gtable, deferred;
     DevBuf queues; // per level >= 1: small[cap], large[cap]
     DevBuf hit_read, hit_ub, hit_cnt;
     DevBuf counters;
@@ -406,6 +410,7 @@ static int slot_reserve(txr_ctx *c, Slot &s, const BatchMeta &m)
     TRY(s.hashes.ensure(std::max<uint64_t>(m.total_cap, 1) * 8));
     TRY(s.n_raw.ensure((size_t)n * 4));
     TRY(s.hash_count.ensure((size_t)n * 4));
+    TRY(s.deferred.ensure((size_t)n * 4));
     TRY(s.counters.ensure(C_TOTAL * 4));
     TRY(s.h_counters.ensure(C_TOTAL * 4));
     TRY(s.h_hash_count.ensure((size_t)n * 4));
@@ -467,8 +472,10 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
         {
             dd.read_ids = m.ids_small.size() == m.n_reads ? nullptr : d.ids_small.as<uint32_t>();
             dd.n_ids = (uint32_t)m.ids_small.size();
-            CU(launch_dedup_small(dd, s.stream));
-            c->timing.dedup_launches += 1;
+            CU(launch_dedup_warp(dd, c->sm_count, cnt + C_DEDUP_WORK, s.deferred.as<uint32_t>(), cnt + C_DEDUP_DEFERRED, s.stream));
+            dd.read_ids = s.deferred.as<uint32_t>(); // reads with too many raw hashes for the warp table
+            CU(launch_dedup_deferred(dd, c->sm_count, cnt + C_DEDUP_DEFERRED, s.stream));
+            c->timing.dedup_launches += 2;
         }
         if (!m.ids_medium.empty())
         {
@@ -817,7 +824,7 @@ void txr_ctx_destroy(txr_ctx *c)
     for (auto &s : c->slots)
     {
         for (DevBuf *b : {&s->words, &s->meta.word_off, &s->meta.len, &s->meta.out_off, &s->meta.ids_small, &s->meta.ids_medium,
-                          &s->meta.ids_global, &s->meta.gtable_off, &s->hashes, &s->n_raw, &s->hash_count, &s->gtable, &s->queues,
+                          &s->meta.ids_global, &s->meta.gtable_off, &s->hashes, &s->n_raw, &s->hash_count, &s->gtable, &s->deferred, &s->queues,
                           &s->hit_read, &s->hit_ub, &s->hit_cnt, &s->counters})
             b->release();
         for (PinBuf *b : {&s->h_meta, &s->h_counters, &s->h_hash_count, &s->h_hits})
@@ -1030,6 +1037,14 @@ int txr_threshold_get(txr_ctx *c, uint64_t hash_count, double scaling_factor, ui
     if (!c || !out || !c->have_params)
         return set_error(TXR_ERR_STATE, "no parameters");
     *out = c->thresholder.get(hash_count, scaling_factor);
+    return TXR_OK;
+}
+
+int txr_threshold_eval(const txr_params *p, uint64_t hash_count, double scaling_factor, uint64_t *out)
+{
+    if (!p || !out)
+        return set_error(TXR_ERR_ARG, "null argument");
+    *out = Thresholder(p->window_size, p->kmer_size, p->percentage, p->error_rate, p->use_syncmer != 0).get(hash_count, scaling_factor);
     return TXR_OK;
 }
 

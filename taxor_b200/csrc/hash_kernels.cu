@@ -21,6 +21,8 @@
 #include "device_types.cuh"
 #include "ixf_arith.cuh"
 
+#include <algorithm>
+
 namespace txr
 {
 constexpr int kHashWarps = 4; // warps per CTA of the syncmer kernel
@@ -170,6 +172,103 @@ __device__ ScanState scan_state_at(const uint64_t *w, uint64_t j0, int wn, int s
 // -----------------------------------------------------------------------------------------------------------
 // fast syncmer kernel: one warp per read, 2S <= 32
 // -----------------------------------------------------------------------------------------------------------
+namespace
+{
+// 32 stream bits starting at base START of the 128-bit value x (x[3] most significant), left-aligned
+template <int START>
+__device__ __forceinline__ uint32_t top32(const uint32_t (&x)[4])
+{
+    constexpr int lo_bit = 128 - 2 * START - 32; // bit index of the lowest of the 32 bits (may be negative)
+    static_assert(128 - 2 * START > 0, "field starts beyond the value");
+    if constexpr (lo_bit >= 0)
+    {
+        constexpr int wi = lo_bit >> 5, b = lo_bit & 31;
+        return __funnelshift_r(x[wi], wi + 1 < 4 ? x[wi + 1 < 4 ? wi + 1 : 3] : 0u, b);
+    }
+    else
+        return x[0] << (-lo_bit);
+}
+
+// canonical s-mers Q..QN-1 of a lane: min(forward field, reverse-complement field), right-aligned
+template <int Q, int QN, int S>
+struct CanonFill
+{
+    __device__ __forceinline__ static void run(const uint32_t (&f)[4], const uint32_t (&r)[4], uint32_t (&v)[QN])
+    {
+        // both fields are taken left-aligned (low bits carry stream garbage); the order of the top 2S bits decides
+        // the minimum and the shift drops the garbage of whichever won
+        v[Q] = min(top32<Q>(f), top32<64 - Q - S>(r)) >> (32 - 2 * S);
+        CanonFill<Q + 1, QN, S>::run(f, r, v);
+    }
+};
+template <int QN, int S>
+struct CanonFill<QN, QN, S>
+{
+    __device__ __forceinline__ static void run(const uint32_t (&)[4], const uint32_t (&)[4], uint32_t (&)[QN]) {}
+};
+
+// Exact decision for ONE window j whose candidate s-mer ties the window minimum: replay the reference's state
+// machine (syncmer.cpp:116-140) from the nearest anchor (a window with a unique minimum, or window 0).
+// sv holds the canonical s-mers of the current tile (index q - tile); earlier positions come from the packed read.
+// Returns false through `give_up` when the tied run is longer than the local budget.
+__device__ bool resolve_tie_local(const uint64_t *w, const uint32_t *sv, uint64_t tile, uint64_t j, int wn, int s, int t,
+                                  bool &give_up)
+{
+    auto val = [&](uint64_t q) -> uint32_t { return q >= tile ? sv[q - tile] : (uint32_t)canon_mer_at(w, q, s); };
+    auto wmin = [&](uint64_t a, uint32_t &mv, uint64_t &lm, uint64_t &rm)
+    {
+        mv = 0xffffffffu;
+        lm = rm = a;
+        for (int q = 0; q < wn; ++q)
+        {
+            const uint32_t x = val(a + q);
+            if (x < mv)
+            {
+                mv = x;
+                lm = rm = a + q;
+            }
+            else if (x == mv)
+                rm = a + q;
+        }
+    };
+    uint64_t a = j, lm, rm;
+    uint32_t mv;
+    for (int steps = 0;; ++steps)
+    {
+        wmin(a, mv, lm, rm);
+        if (lm == rm || a == 0)
+            break;
+        if (steps >= 40)
+        {
+            give_up = true;
+            return false;
+        }
+        --a;
+    }
+    uint32_t st_val = mv;
+    uint64_t st_pos = lm; // unique minimum, or the leftmost one in window 0 (syncmer.cpp:116-123)
+    for (uint64_t jj = a + 1; jj <= j; ++jj)
+    {
+        if (st_pos == jj - 1) // popped: rescan, rightmost minimum (syncmer.cpp:128-136)
+        {
+            wmin(jj, mv, lm, rm);
+            st_val = mv;
+            st_pos = rm;
+        }
+        else
+        {
+            const uint32_t x = val(jj + wn - 1);
+            if (x < st_val) // strictly smaller arrival (syncmer.cpp:137-140)
+            {
+                st_val = x;
+                st_pos = jj + wn - 1;
+            }
+        }
+    }
+    return st_pos == j + t - 1;
+}
+} // namespace
+
 template <int K, int S, int T>
 __global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
 {
@@ -177,12 +276,13 @@ __global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
     constexpr int QN = 32 + WN - 1;  // s-mers a lane needs for its 32 windows
     constexpr int NL = T - 1;        // neighbourhood left of the candidate s-mer
     constexpr int NR = WN - T;       // ... and right of it
+    constexpr bool kSignTrick = 2 * S <= 30; // values < 2^31: comparisons through the sign of a difference
     static_assert(32 + K - 1 <= 64, "two packed words per lane");
     static_assert(T >= 1 && T <= WN, "t out of range");
 
-    // per warp: canonical s-mers of the tile (slow path only), later reused for the compacted selected windows
+    // per warp: canonical s-mers of the tile (tie handling only), later reused for the compacted selected windows
     __shared__ uint32_t s_v[kHashWarps][kTileWindows + 32];
-    __shared__ uint32_t s_sel[kHashWarps][32];      // per-lane selection masks written by the slow path
+    __shared__ uint32_t s_sel[kHashWarps][32];      // per-lane selection masks written by the sequential replay
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     while (true)
@@ -215,7 +315,7 @@ __global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
             const uint32_t rc[4] = {(uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32)};
 
             uint32_t v[QN];
-            SmerFill<0, QN, S>::run(f, rc, v);
+            CanonFill<0, QN, S>::run(f, rc, v);
 
             // sliding minima by doubling: mN[q] = min(v[q .. q+N-1]) (clamped at the end of the lane's range)
             uint32_t m2[QN], m4[QN], m8[QN], m16[QN];
@@ -232,91 +332,121 @@ __global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
             for (int q = 0; q < QN; ++q)
                 m16[q] = q + 8 < QN ? min(m8[q], m8[q + 8]) : m8[q];
 
-            // candidate s-mer of window i is v[i+T-1]; strict minimum of NL left and NR right neighbours
-            uint32_t sel = 0, tie = 0;
+            // candidate s-mer of window i is v[i+T-1]; selected iff it is a strict minimum of its NL left and NR
+            // right neighbours; an equality is a tie that the exact rule has to decide
+            uint32_t sel = 0;
+            bool any_tie = false;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
+            for (int i = 31; i >= 0; --i)
             {
                 const uint32_t other = min(range_min<NL>(v, m2, m4, m8, m16, i), range_min<NR>(v, m2, m4, m8, m16, i + T));
                 const uint32_t c = v[i + T - 1];
-                sel |= (c < other ? 1u : 0u) << i;
-                tie |= (c == other ? 1u : 0u) << i;
+                if constexpr (kSignTrick)
+                    sel = __funnelshift_l(c - other, sel, 1); // shifts in the sign bit of (c - other)
+                else
+                    sel = (sel << 1) | (c < other ? 1u : 0u);
+                any_tie |= c == other;
             }
             const uint64_t j0 = tile + 32ull * lane;
             const uint32_t valid = j0 >= W ? 0u : (W - j0 >= 32 ? 0xffffffffu : ((1u << (uint32_t)(W - j0)) - 1u));
             sel &= valid;
-            tie &= valid;
 
-            if (__any_sync(0xffffffffu, tie != 0))
+            bool replayed = false;
+            if (__any_sync(0xffffffffu, any_tie && valid != 0))
             {
-                // exact replay of the tile by lane 0 (reference tie rules)
+                uint32_t tie = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    s_v[wib][32 * lane + i] = v[i];
-                if (lane == 31)
+                for (int i = 31; i >= 0; --i)
+                {
+                    const uint32_t other = min(range_min<NL>(v, m2, m4, m8, m16, i), range_min<NR>(v, m2, m4, m8, m16, i + T));
+                    tie = (tie << 1) | (v[i + T - 1] == other ? 1u : 0u);
+                }
+                tie &= valid;
+                if (__any_sync(0xffffffffu, tie != 0))
                 {
 #pragma unroll
-                    for (int i = 32; i < QN; ++i)
+                    for (int i = 0; i < 32; ++i)
                         s_v[wib][32 * lane + i] = v[i];
-                }
-                s_sel[wib][lane] = 0;
-                __syncwarp();
-                if (lane == 0)
-                {
-                    const uint64_t jend = min(W, tile + (uint64_t)kTileWindows);
-                    ScanState st;
-                    uint64_t j = tile;
-                    if (tile == 0)
+                    if (lane == 31)
                     {
-                        uint64_t mv, lm, rm;
-                        window_min(w, 0, WN, S, mv, lm, rm);
-                        st = ScanState{mv, lm};
-                        if (st.min_pos == (uint64_t)(T - 1))
-                            s_sel[wib][0] |= 1u;
-                        j = 1;
+#pragma unroll
+                        for (int i = 32; i < QN; ++i)
+                            s_v[wib][32 * lane + i] = v[i];
                     }
-                    else
-                        st = carry_valid ? carry : scan_state_at(w, tile - 1, WN, S);
-                    for (; j < jend; ++j)
+                    __syncwarp();
+                    // (1) every lane settles its own tied windows with a short local replay
+                    bool give_up = false;
+                    uint32_t m = tie;
+                    while (m && !give_up)
                     {
-                        const uint32_t lj = (uint32_t)(j - tile);
-                        if (st.min_pos == j - 1)
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (resolve_tie_local(w, s_v[wib], tile, j0 + b, WN, S, T, give_up))
+                            sel |= 1u << b;
+                    }
+                    // (2) long tied runs (low-complexity sequence): exact replay of the whole tile by lane 0
+                    if (__any_sync(0xffffffffu, give_up))
+                    {
+                        replayed = true;
+                        s_sel[wib][lane] = 0;
+                        __syncwarp();
+                        if (lane == 0)
                         {
-                            uint32_t mv = 0xffffffffu, mp = 0;
-                            for (int q = WN - 1; q >= 0; --q) // rightmost minimum
+                            const uint64_t jend = min(W, tile + (uint64_t)kTileWindows);
+                            ScanState st;
+                            uint64_t j = tile;
+                            if (tile == 0)
                             {
-                                const uint32_t x = s_v[wib][lj + q];
-                                if (x < mv)
+                                uint64_t mv, lm, rm;
+                                window_min(w, 0, WN, S, mv, lm, rm);
+                                st = ScanState{mv, lm};
+                                if (st.min_pos == (uint64_t)(T - 1))
+                                    s_sel[wib][0] |= 1u;
+                                j = 1;
+                            }
+                            else
+                                st = carry_valid ? carry : scan_state_at(w, tile - 1, WN, S);
+                            for (; j < jend; ++j)
+                            {
+                                const uint32_t lj = (uint32_t)(j - tile);
+                                if (st.min_pos == j - 1)
                                 {
-                                    mv = x;
-                                    mp = q;
+                                    uint32_t mv = 0xffffffffu, mp = 0;
+                                    for (int q = WN - 1; q >= 0; --q) // rightmost minimum
+                                    {
+                                        const uint32_t x = s_v[wib][lj + q];
+                                        if (x < mv)
+                                        {
+                                            mv = x;
+                                            mp = q;
+                                        }
+                                    }
+                                    st.min_val = mv;
+                                    st.min_pos = j + mp;
                                 }
+                                else
+                                {
+                                    const uint32_t x = s_v[wib][lj + WN - 1];
+                                    if (x < st.min_val)
+                                    {
+                                        st.min_val = x;
+                                        st.min_pos = j + WN - 1;
+                                    }
+                                }
+                                if (st.min_pos == j + T - 1)
+                                    s_sel[wib][lj >> 5] |= 1u << (lj & 31);
                             }
-                            st.min_val = mv;
-                            st.min_pos = j + mp;
+                            carry = st;
                         }
-                        else
-                        {
-                            const uint32_t x = s_v[wib][lj + WN - 1];
-                            if (x < st.min_val)
-                            {
-                                st.min_val = x;
-                                st.min_pos = j + WN - 1;
-                            }
-                        }
-                        if (st.min_pos == j + T - 1)
-                            s_sel[wib][lj >> 5] |= 1u << (lj & 31);
+                        __syncwarp();
+                        sel = s_sel[wib][lane];
+                        carry.min_val = __shfl_sync(0xffffffffu, carry.min_val, 0);
+                        carry.min_pos = __shfl_sync(0xffffffffu, carry.min_pos, 0);
                     }
-                    carry = st;
+                    __syncwarp();
                 }
-                __syncwarp();
-                sel = s_sel[wib][lane];
-                carry.min_val = __shfl_sync(0xffffffffu, carry.min_val, 0);
-                carry.min_pos = __shfl_sync(0xffffffffu, carry.min_pos, 0);
-                carry_valid = true;
             }
-            else
-                carry_valid = false;
+            carry_valid = replayed;
 
             // compact the selected windows of the tile, then hash them with all lanes busy
             const uint32_t n = __popc(sel);
@@ -516,6 +646,91 @@ __device__ uint32_t table_compact(const uint64_t *tab, uint32_t slots, uint64_t 
 }
 } // namespace
 
+// One WARP per read, table of kWarpSlots keys in shared memory.  The keys are streamed in chunks of 32: a lane
+// whose atomicCAS claimed an empty slot owns the first occurrence of its key, the ballot of the owners compacts the
+// chunk in place (first-occurrence order, the same order an ankerl set iterates in).  Reads with more raw hashes
+// than the table can take at load factor 2/3 are appended to `deferred` for the CTA-per-read kernel.
+constexpr int kWarpSlots = 2048;
+constexpr int kDedupWarps = 2; // 32 KB of static shared memory per CTA, 7 CTAs per SM
+__global__ void __launch_bounds__(32 * kDedupWarps) dedup_warp_kernel(DedupArgs a, uint32_t *work_counter, uint32_t *deferred,
+                                                                      uint32_t *n_deferred)
+{
+    __shared__ uint64_t s_tab[kDedupWarps][kWarpSlots];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint64_t *tab = s_tab[wib];
+    while (true)
+    {
+        uint32_t id = 0;
+        if (lane == 0)
+            id = atomicAdd(work_counter, 1u);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= a.n_ids)
+            break;
+        const uint32_t r = a.read_ids ? a.read_ids[id] : id;
+        const uint32_t n = a.n_raw[r];
+        if (n > (uint32_t)(kWarpSlots * 2 / 3))
+        {
+            if (lane == 0)
+                deferred[atomicAdd(n_deferred, 1u)] = r;
+            continue;
+        }
+        ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(tab);
+#pragma unroll
+        for (int i = 0; i < kWarpSlots / 64; ++i)
+            t2[i * 32 + lane] = make_ulonglong2(kEmptyKey, kEmptyKey);
+        __syncwarp();
+        uint64_t *p = a.hashes + a.out_off[r];
+        uint32_t base = 0;
+        bool saw_empty_key = false;
+        uint64_t next = lane < n ? p[lane] : 0;
+        for (uint32_t c0 = 0; c0 < n; c0 += 32)
+        {
+            const uint32_t i = c0 + lane;
+            const uint64_t key = next;
+            if (i + 32 < n)
+                next = p[i + 32]; // prefetch the next chunk before the atomics
+            bool first = false;
+            if (i < n)
+            {
+                if (key == kEmptyKey)
+                    saw_empty_key = true;
+                else
+                {
+                    uint32_t slot = (uint32_t)(key ^ (key >> 32)) & (kWarpSlots - 1);
+                    while (true)
+                    {
+                        const unsigned long long old = atomicCAS((unsigned long long *)&tab[slot], (unsigned long long)kEmptyKey,
+                                                                 (unsigned long long)key);
+                        if (old == kEmptyKey)
+                        {
+                            first = true;
+                            break;
+                        }
+                        if (old == key)
+                            break;
+                        slot = (slot + 1) & (kWarpSlots - 1);
+                    }
+                }
+            }
+            const bool keep = first && scaling_keep(key, a.scaling, a.scaling_limit);
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (keep)
+                p[base + __popc(bal & ((1u << lane) - 1u))] = key; // base + rank <= i: never ahead of the reads
+            base += __popc(bal);
+        }
+        // the sentinel value itself can be a hash: it bypasses the table and is appended once
+        if (__any_sync(0xffffffffu, saw_empty_key) && scaling_keep(kEmptyKey, a.scaling, a.scaling_limit))
+        {
+            if (lane == 0)
+                p[base] = kEmptyKey;
+            ++base;
+        }
+        if (lane == 0)
+            a.hash_count[r] = base;
+        __syncwarp();
+    }
+}
+
 // one CTA per read, table in shared memory (SLOTS a power of two >= 2 * capacity of the class)
 template <int SLOTS>
 __global__ void dedup_smem_kernel(DedupArgs a)
@@ -662,11 +877,53 @@ cudaError_t launch_kmer(const HashArgs &a, int sm_count, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_dedup_small(const DedupArgs &a, cudaStream_t st) // capacity <= 2048
+// capacity <= 2048: warp-per-read kernel; reads it defers (more than 2/3 * 2048 raw hashes) go to `deferred`
+cudaError_t launch_dedup_warp(const DedupArgs &a, int sm_count, uint32_t *work_counter, uint32_t *deferred, uint32_t *n_deferred,
+                              cudaStream_t st)
 {
     if (a.n_ids == 0)
         return cudaSuccess;
-    dedup_smem_kernel<4096><<<a.n_ids, 128, 4096 * 8, st>>>(a);
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sm_count * 7, ((uint64_t)a.n_ids + kDedupWarps - 1) / kDedupWarps);
+    dedup_warp_kernel<<<grid, 32 * kDedupWarps, 0, st>>>(a, work_counter, deferred, n_deferred);
+    return cudaGetLastError();
+}
+
+// CTA-per-read kernel over an explicit list whose length is only known on the device (the deferred reads)
+__global__ void dedup_deferred_kernel(DedupArgs a, const uint32_t *n_deferred)
+{
+    extern __shared__ uint64_t s_tab[];
+    __shared__ uint32_t s_scan[32];
+    __shared__ int s_saw_empty;
+    const uint32_t n_ids = *n_deferred;
+    for (uint32_t id = blockIdx.x; id < n_ids; id += gridDim.x)
+    {
+        const uint32_t r = a.read_ids[id];
+        for (int i = threadIdx.x; i < 4096; i += blockDim.x)
+            s_tab[i] = kEmptyKey;
+        if (threadIdx.x == 0)
+            s_saw_empty = 0;
+        __syncthreads();
+        uint64_t *p = a.hashes + a.out_off[r];
+        const uint32_t n = a.n_raw[r];
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const uint64_t h = p[i];
+            if (h == kEmptyKey)
+                s_saw_empty = 1;
+            else
+                table_insert(s_tab, 4095u, h);
+        }
+        __syncthreads();
+        const uint32_t cnt = table_compact(s_tab, 4096, p, s_saw_empty != 0, a.scaling, a.scaling_limit, s_scan);
+        if (threadIdx.x == 0)
+            a.hash_count[r] = cnt;
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_dedup_deferred(const DedupArgs &a, int sm_count, const uint32_t *n_deferred, cudaStream_t st)
+{
+    dedup_deferred_kernel<<<sm_count * 2, 128, 4096 * 8, st>>>(a, n_deferred);
     return cudaGetLastError();
 }
 

@@ -6,7 +6,7 @@
 // src/main/xorfilter.hpp:22-45 (rotl64 / reduce / getHashFromHash), :60-62 (fingerprint), :336-350 (Contain),
 // :67-68 (arrayLength = 32 + 1.23*size, blockLength = arrayLength/3).
 // Used by the CUDA query kernel (device) and by the CPU synthetic-index builder (host).  If the fork turns
-// out to differ, this file (and oracle/ixf_ref.h on the test side) is all that changes.
+// out to differ, this file (and its independent test-side twin) is all that changes.
 #pragma once
 #include <cstdint>
 
