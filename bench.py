@@ -320,7 +320,7 @@ def main():
         torch.cuda.synchronize()
 
     # (1) device-resident: kernels only.  One pipeline slot so that the per-stage CUDA events are not overlapped
-    ctx.configure(n_slots=1)
+    ctx.configure(n_slots=int(os.environ.get("TAXOR_BENCH_RESIDENT_SLOTS", 1)))
     h = ctx.upload_reads(reads)
     for _ in range(args.warmup):
         ctx.search_resident(h, fetch=False)

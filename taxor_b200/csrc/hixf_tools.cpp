@@ -1,0 +1,130 @@
+// hixf_tools.cpp -- C entry points of libtaxor_tools.so around hixf_file.cpp, for tests and benchmarks:
+// write a synthetic index as a real `.hixf` file and read one back into plain arrays.
+#include "hixf_file.hpp"
+
+#include <cstring>
+#include <string>
+
+using namespace txr;
+
+namespace
+{
+thread_local std::string g_err;
+}
+
+extern "C" {
+
+const char *txs_last_error(void) { return g_err.c_str(); }
+
+// species arrays: n_species entries; strings are NUL-terminated.  ixf arrays as in txr_hixf_view.
+int txs_hixf_write(const char *path, const char *record_spec, uint64_t window_size, uint8_t k, uint8_t s, uint8_t t,
+                   uint8_t use_syncmer, uint16_t scaling, uint64_t n_ixf, const uint64_t *seed, const uint64_t *bins,
+                   const uint64_t *tbins, const uint64_t *seg_len, const uint8_t *const *data, const uint64_t *bin_off,
+                   const int64_t *next_ixf_id, const int64_t *bin_to_ub, uint64_t n_user_bins, const char *const *ub_filenames,
+                   uint64_t n_species, const char *const *organism, const char *const *accession, const char *const *taxid,
+                   const char *const *taxnames, const char *const *taxids, const uint64_t *sp_user_bin, const uint64_t *sp_seq_len)
+{
+    TaxorIndexFile f;
+    f.window_size = window_size;
+    f.shape_size = k;
+    f.shape_bits = k >= 64 ? ~0ull : ((1ull << k) - 1); // ungapped shape: k ones
+    f.kmer_size = k;
+    f.syncmer_size = s;
+    f.t_syncmer = t;
+    f.use_syncmer = use_syncmer != 0;
+    f.scaling = scaling;
+    for (uint64_t i = 0; i < n_user_bins; ++i)
+    {
+        f.user_bin_filenames.emplace_back(ub_filenames[i]);
+        f.bin_path.push_back({std::string(ub_filenames[i])}); // taxor_build.cpp:515
+    }
+    for (uint64_t i = 0; i < n_species; ++i)
+    {
+        SpeciesRecord r;
+        r.organism_name = organism[i];
+        r.accession_id = accession[i];
+        r.taxid = taxid[i];
+        r.taxnames_string = taxnames[i];
+        r.taxid_string = taxids[i];
+        r.user_bin = sp_user_bin[i];
+        r.seq_len = sp_seq_len[i];
+        f.species.push_back(std::move(r));
+    }
+    for (uint64_t i = 0; i < n_ixf; ++i)
+    {
+        IxfRecord x;
+        x.seed = seed[i];
+        x.bins = bins[i];
+        x.tbins = tbins[i];
+        x.seg_len = seg_len[i];
+        x.fp = data[i];
+        x.fp_len = 3 * seg_len[i] * tbins[i];
+        f.ixf.push_back(std::move(x));
+        f.next_ixf_id.emplace_back(next_ixf_id + bin_off[i], next_ixf_id + bin_off[i + 1]);
+        f.ixf_bin_to_filename_position.emplace_back(bin_to_ub + bin_off[i], bin_to_ub + bin_off[i + 1]);
+    }
+    const IxfRecordSpec spec = record_spec && *record_spec ? IxfRecordSpec::parse(record_spec) : IxfRecordSpec::candidates()[0];
+    g_err = write_hixf(path, f, spec);
+    return g_err.empty() ? 0 : -1;
+}
+
+void *txs_hixf_open(const char *path, const char *record_spec)
+{
+    auto *f = new TaxorIndexFile;
+    IxfRecordSpec used;
+    if (record_spec && *record_spec)
+    {
+        const IxfRecordSpec spec = IxfRecordSpec::parse(record_spec);
+        g_err = read_hixf(path, *f, &spec, &used);
+    }
+    else
+        g_err = read_hixf(path, *f, nullptr, &used);
+    if (!g_err.empty())
+    {
+        delete f;
+        return nullptr;
+    }
+    g_err = used.str();
+    return f;
+}
+void txs_hixf_close(void *p) { delete static_cast<TaxorIndexFile *>(p); }
+
+// scalars: [version, window, shape_size, shape_bits, k, s, t, parts, use_syncmer, scaling, compressed, n_ixf, n_user_bins, n_species]
+void txs_hixf_info(void *p, uint64_t *out14)
+{
+    auto *f = static_cast<TaxorIndexFile *>(p);
+    const uint64_t v[14] = {f->version, f->window_size, f->shape_size, f->shape_bits, f->kmer_size, f->syncmer_size, f->t_syncmer,
+                            f->parts, f->use_syncmer, f->scaling, f->compressed, f->ixf.size(), f->user_bin_filenames.size(),
+                            f->species.size()};
+    memcpy(out14, v, sizeof v);
+}
+void txs_hixf_ixf(void *p, uint64_t i, uint64_t *seed, uint64_t *bins, uint64_t *tbins, uint64_t *seg_len, const uint8_t **fp,
+                  const int64_t **next, const int64_t **ub)
+{
+    auto *f = static_cast<TaxorIndexFile *>(p);
+    const IxfRecord &x = f->ixf[i];
+    *seed = x.seed;
+    *bins = x.bins;
+    *tbins = x.tbins;
+    *seg_len = x.seg_len;
+    *fp = x.fp;
+    *next = f->next_ixf_id[i].data();
+    *ub = f->ixf_bin_to_filename_position[i].data();
+}
+const char *txs_hixf_species_field(void *p, uint64_t i, int field, uint64_t *user_bin, uint64_t *seq_len)
+{
+    auto *f = static_cast<TaxorIndexFile *>(p);
+    const SpeciesRecord &s = f->species[i];
+    *user_bin = s.user_bin;
+    *seq_len = s.seq_len;
+    switch (field)
+    {
+    case 0: return s.organism_name.c_str();
+    case 1: return s.accession_id.c_str();
+    case 2: return s.taxid.c_str();
+    case 3: return s.taxnames_string.c_str();
+    default: return s.taxid_string.c_str();
+    }
+}
+
+} // extern "C"

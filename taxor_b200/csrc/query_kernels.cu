@@ -17,6 +17,8 @@
 #include "device_types.cuh"
 #include "ixf_arith.cuh"
 
+#include <cstdlib>
+
 namespace txr
 {
 namespace
@@ -335,9 +337,24 @@ __global__ void __launch_bounds__(256) ixf_bulk_count_kernel(IxfDev d, const uin
 }
 
 // ---- launchers ----
+// CTAs per SM of the persistent query grids (tuning knob, TXR_QUERY_CTAS_PER_SM; 8 = all 32 warps an SM can hold at
+// 61 registers, fewer leaves room for the compute-bound hash/dedup kernels of the neighbouring pipeline slots)
+static int query_ctas_per_sm()
+{
+    static int v = 0;
+    if (!v)
+    {
+        const char *e = getenv("TXR_QUERY_CTAS_PER_SM");
+        v = e ? atoi(e) : 8;
+        if (v < 1 || v > 16)
+            v = 8;
+    }
+    return v;
+}
+
 cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st)
 {
-    ixf_query_small_kernel<<<sm_count * 8, 32 * kQueryWarps, 0, st>>>(a);
+    ixf_query_small_kernel<<<sm_count * query_ctas_per_sm(), 32 * kQueryWarps, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,580 @@
+// taxor_main.cpp -- drop-in `taxor search` command (src/main/main.cpp:51-88 + src/main/taxor_search.cpp) on top of
+// the CUDA library.  Same sub-command, options, validators, stdout banners, result-file format and exit codes as
+// the reference; `build` and `profile` stay with the reference binary (CPU, out of scope).
+// Extra, optional knobs (ignored by the reference): --gpus <n|list>, --ixf-record <field order>.
+#include "../../include/taxor_b200.h"
+#include "hixf_file.hpp"
+#include "seqio.hpp"
+#include "threshold.hpp"
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <sys/resource.h>
+#include <sys/stat.h>
+#include <thread>
+#include <vector>
+
+using namespace txr;
+
+namespace
+{
+struct Config // src/main/taxor_search_configuration.hpp:8-19
+{
+    std::string index_file, query_file, report_file;
+    double threshold{-1.0};
+    double error_rate{0.04};
+    unsigned threads{1};
+    std::string gpus;       // extension
+    std::string ixf_record; // extension
+};
+
+struct ParserError : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+
+double cputime() // main.cpp:37-42
+{
+    struct rusage r;
+    getrusage(RUSAGE_SELF, &r);
+    return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec);
+}
+long peak_rss() // main.cpp:44-49
+{
+    struct rusage r;
+    getrusage(RUSAGE_SELF, &r);
+    return r.ru_maxrss * 1024;
+}
+
+std::vector<std::string> str_split(const std::string &s, char delim) // taxor_search.cpp:82-95
+{
+    std::vector<std::string> out;
+    std::stringstream ss(s);
+    std::string seg;
+    while (std::getline(ss, seg, delim))
+        out.push_back(seg);
+    return out;
+}
+
+bool file_exists(const std::string &p)
+{
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+
+void print_help()
+{
+    std::cout << "taxor-search - Queries files of DNA sequences against a list of HIXF index files\n"
+                 "=================================================================================\n\n"
+                 "DESCRIPTION\n    Query sequences against the taxor HIXF index structure\n\n"
+                 "OPTIONS\n\n  Main options:\n"
+                 "    --index-file (std::string)\n          taxor index file containing HIXF index and reference sequence information\n"
+                 "    --query-file (std::string)\n          file containing sequences to query against the index Default: .\n"
+                 "    --output-file (std::string)\n          A file name for the resulting output. Default: .\n"
+                 "    --threads (unsigned 8 bit integer)\n          The number of threads to use. Default: 1. Value must be in range [1,32].\n"
+                 "    --percentage (double)\n          If set, this threshold is used instead of the k-mer/syncmer models. Default: -1. Value must be in range\n          [0,1].\n"
+                 "    --error-rate (double)\n          Expected error rate of reads that will be queried Default: 0.04. Value must be in range [0,1].\n\n"
+                 "  B200 options (extensions of this implementation):\n"
+                 "    --gpus (std::string)\n          Number of GPUs or comma-separated device list. Default: all visible devices.\n"
+                 "    --ixf-record (std::string)\n          Field order of the interleaved XOR filter records in the index file (see INTEGRATION.md).\n\n"
+                 "VERSION\n    taxor-search version: 0.2.0 (taxor_b200)\n";
+}
+
+double parse_double(const std::string &opt, const std::string &v, double lo, double hi)
+{
+    char *end = nullptr;
+    const double d = strtod(v.c_str(), &end);
+    if (v.empty() || *end)
+        throw ParserError("Value parse failed for --" + opt + ": Argument " + v + " could not be parsed as type double.");
+    if (d < lo || d > hi)
+    {
+        std::ostringstream os;
+        os << "Validation failed for option --" << opt << ": Value " << d << " is not in range [" << lo << "," << hi << "].";
+        throw ParserError(os.str());
+    }
+    return d;
+}
+
+void parse_args(int argc, char const **argv, Config &c) // taxor_search.cpp:32-80
+{
+    bool have_index = false;
+    for (int i = 0; i < argc; ++i)
+    {
+        std::string a = argv[i], v;
+        if (a == "-h" || a == "--help" || a == "-hh" || a == "--advanced-help")
+        {
+            print_help();
+            exit(0);
+        }
+        if (a == "--version")
+        {
+            std::cout << "taxor-search version: 0.2.0 (taxor_b200)\n";
+            exit(0);
+        }
+        if (a == "--output-verbose-statistics" || a == "--debug") // hidden flags, no effect on search (:69-79)
+            continue;
+        if (a.rfind("--", 0) != 0)
+            throw ParserError("Too many arguments provided. Please see -h/--help for more information.");
+        const size_t eq = a.find('=');
+        std::string name = a.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+        if (eq != std::string::npos)
+            v = a.substr(eq + 1);
+        else
+        {
+            if (i + 1 >= argc)
+                throw ParserError("Missing value for option --" + name);
+            v = argv[++i];
+        }
+        if (name == "index-file")
+        {
+            c.index_file = v;
+            have_index = true;
+        }
+        else if (name == "query-file")
+            c.query_file = v;
+        else if (name == "output-file")
+            c.report_file = v;
+        else if (name == "threads")
+        {
+            char *end = nullptr;
+            const long t = strtol(v.c_str(), &end, 10);
+            if (v.empty() || *end)
+                throw ParserError("Value parse failed for --threads: Argument " + v + " could not be parsed as type unsigned 8 bit integer.");
+            if (t < 1 || t > 32)
+                throw ParserError("Validation failed for option --threads: Value " + std::to_string(t) + " is not in range [1,32].");
+            c.threads = (unsigned)t;
+        }
+        else if (name == "percentage")
+            c.threshold = parse_double(name, v, 0.0, 1.0);
+        else if (name == "error-rate")
+            c.error_rate = parse_double(name, v, 0.0, 1.0);
+        else if (name == "gpus")
+            c.gpus = v;
+        else if (name == "ixf-record")
+            c.ixf_record = v;
+        else
+            throw ParserError("Unknown option --" + name + ". In case this is meant to be a non-option/argument/parameter, please specify the start of non-options with '--'. See -h/--help for program information.");
+    }
+    if (!have_index)
+        throw ParserError("Option --index-file is required but not set.");
+}
+
+std::string load_index_file(const std::string &path, const Config &cfg, TaxorIndexFile &idx)
+{
+    if (cfg.ixf_record.empty())
+        return read_hixf(path, idx, nullptr, nullptr);
+    const IxfRecordSpec spec = IxfRecordSpec::parse(cfg.ixf_record);
+    return read_hixf(path, idx, &spec, nullptr);
+}
+
+// ---- one GPU worker: owns a context with the index in HBM ----
+struct Chunk
+{
+    size_t seq{0};
+    std::vector<std::string> ids;
+    std::vector<uint32_t> len;
+    std::vector<uint64_t> word_off;
+    uint64_t *words{nullptr};
+    size_t words_cap{0}, words_used{0};
+    std::string text; // formatted result lines
+};
+
+template <typename T> class Channel
+{
+public:
+    void push(T v)
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            q_.push_back(std::move(v));
+        }
+        cv_.notify_one();
+    }
+    bool pop(T &v)
+    {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return !q_.empty() || closed_; });
+        if (q_.empty())
+            return false;
+        v = std::move(q_.front());
+        q_.pop_front();
+        return true;
+    }
+    void close()
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            closed_ = true;
+        }
+        cv_.notify_all();
+    }
+
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<T> q_;
+    bool closed_{false};
+};
+
+std::vector<int> pick_devices(const std::string &spec)
+{
+    std::vector<int> dev;
+    if (spec.find(',') != std::string::npos)
+    {
+        for (auto &s : str_split(spec, ','))
+            dev.push_back(atoi(s.c_str()));
+        return dev;
+    }
+    int n = spec.empty() ? 64 : atoi(spec.c_str());
+    for (int d = 0; d < n; ++d)
+    {
+        txr_ctx *probe = nullptr;
+        if (txr_ctx_create(d, &probe) != TXR_OK)
+            break;
+        txr_ctx_destroy(probe);
+        dev.push_back(d);
+    }
+    return dev;
+}
+
+// result lines of one chunk, taxor_search.cpp:266-306
+void format_chunk(Chunk &ch, const txr_result &res, const TaxorIndexFile &idx, const std::map<size_t, size_t> &user_bin_index)
+{
+    std::string &out = ch.text;
+    out.clear();
+    for (size_t r = 0; r < ch.ids.size(); ++r)
+    {
+        const std::string &id = ch.ids[r];
+        const uint64_t b = res.hit_begin[r], e = res.hit_begin[r + 1];
+        if (b == e) // :268-273
+        {
+            out += id;
+            out += '\t';
+            out += "-\t-\t-\t-\t";
+            out += std::to_string(ch.len[r]);
+            out += "\n";
+            continue;
+        }
+        for (uint64_t i = b; i < e; ++i)
+        {
+            if (!res.keep[i]) // :285-286 (count < 0.8 * max_count)
+                continue;
+            auto it = user_bin_index.find((size_t)res.user_bin[i]);
+            const SpeciesRecord &sp = idx.species.at(it == user_bin_index.end() ? 0 : it->second);
+            out += id;
+            out += '\t';
+            out += sp.accession_id;
+            out += '\t';
+            out += sp.organism_name;
+            out += '\t';
+            out += sp.taxid;
+            out += '\t';
+            out += std::to_string(sp.seq_len);
+            out += '\t';
+            out += std::to_string(ch.len[r]);
+            out += '\t';
+            out += std::to_string(res.hash_count[r]);
+            out += '\t';
+            out += std::to_string(res.count[i]);
+            out += '\t';
+            out += sp.taxnames_string;
+            out += '\t';
+            out += sp.taxid_string;
+            out += '\n';
+        }
+    }
+}
+
+constexpr size_t kChunkReads = 65536;
+constexpr size_t kChunkBases = 400u << 20;
+
+// search_single, taxor_search.cpp:153-338
+void search_single(const Config &cfg, const std::string &query, const std::string &index_path, std::ofstream &out,
+                   const std::vector<int> &devices)
+{
+    TaxorIndexFile idx;
+    std::string load_error;
+    std::thread loader([&] { load_error = load_index_file(index_path, cfg, idx); }); // the async cereal_worker (:162-180)
+
+    SeqReader fin(query);
+    if (!fin.ok())
+    {
+        loader.join();
+        throw std::runtime_error("cannot open query file " + query);
+    }
+    loader.join();
+    if (!load_error.empty())
+        throw std::runtime_error(load_error);
+
+    Thresholder thresholder(idx.window_size, idx.kmer_size, cfg.threshold, cfg.error_rate, idx.use_syncmer);
+    std::cout << thresholder.banner();
+    if (thresholder.kind() == ThresholdKind::percentage)
+        std::cout << "\t" << cfg.threshold; // threshold.hpp:32
+    std::cout << std::endl << std::flush;
+    std::map<size_t, size_t> user_bin_index; // :172-178
+    for (size_t i = 0; i < idx.species.size(); ++i)
+        user_bin_index.emplace(idx.species[i].user_bin, i);
+
+    // index view shared by all contexts
+    std::vector<txr_ixf_view> views(idx.ixf.size());
+    std::vector<uint64_t> bin_off(idx.ixf.size() + 1, 0);
+    std::vector<int64_t> next_flat, ub_flat;
+    for (size_t i = 0; i < idx.ixf.size(); ++i)
+    {
+        views[i] = txr_ixf_view{idx.ixf[i].seed, idx.ixf[i].bins, idx.ixf[i].tbins, idx.ixf[i].seg_len, idx.ixf[i].fp};
+        next_flat.insert(next_flat.end(), idx.next_ixf_id[i].begin(), idx.next_ixf_id[i].end());
+        ub_flat.insert(ub_flat.end(), idx.ixf_bin_to_filename_position[i].begin(), idx.ixf_bin_to_filename_position[i].end());
+        bin_off[i + 1] = next_flat.size();
+    }
+    txr_hixf_view hv{idx.ixf.size(), views.data(), bin_off.data(), next_flat.data(), ub_flat.data(), idx.user_bin_filenames.size()};
+    txr_params par{};
+    par.kmer_size = idx.kmer_size;
+    par.syncmer_size = idx.syncmer_size;
+    par.t_syncmer = idx.t_syncmer;
+    par.use_syncmer = idx.use_syncmer;
+    par.window_size = (uint32_t)idx.window_size;
+    par.scaling = idx.scaling;
+    par.percentage = cfg.threshold;
+    par.error_rate = cfg.error_rate;
+
+    std::vector<txr_ctx *> ctxs;
+    for (int d : devices)
+    {
+        txr_ctx *c = nullptr;
+        if (txr_ctx_create(d, &c) != TXR_OK || txr_index_upload(c, &hv) != TXR_OK || txr_params_set(c, &par) != TXR_OK)
+            throw std::runtime_error(std::string("GPU ") + std::to_string(d) + ": " + txr_last_error());
+        ctxs.push_back(c);
+    }
+
+    // chunk pool (pinned), parser -> workers -> ordered writer
+    const size_t n_chunks = 2 * ctxs.size() + 1;
+    std::vector<Chunk> pool(n_chunks);
+    Channel<Chunk *> free_q, work_q, done_q;
+    for (auto &ch : pool)
+    {
+        ch.words_cap = kChunkBases / 32 + 2 * kChunkReads + 64;
+        ch.words = static_cast<uint64_t *>(txr_host_alloc(ch.words_cap * 8));
+        if (!ch.words)
+            throw std::runtime_error(txr_last_error());
+        free_q.push(&ch);
+    }
+    std::string worker_error;
+    std::mutex err_m;
+    std::vector<std::thread> workers;
+    for (txr_ctx *c : ctxs)
+        workers.emplace_back([&, c] {
+            Chunk *ch;
+            while (work_q.pop(ch))
+            {
+                txr_result res{};
+                if (txr_search(c, ch->words, ch->word_off.data(), ch->len.data(), ch->ids.size(), &res) != TXR_OK)
+                {
+                    std::lock_guard<std::mutex> l(err_m);
+                    worker_error = txr_last_error();
+                    ch->text.clear();
+                }
+                else
+                    format_chunk(*ch, res, idx, user_bin_index);
+                done_q.push(ch);
+            }
+        });
+    std::thread writer([&] {
+        std::map<size_t, Chunk *> pending;
+        size_t next = 0;
+        Chunk *ch;
+        while (done_q.pop(ch))
+        {
+            pending[ch->seq] = ch;
+            while (!pending.empty() && pending.begin()->first == next)
+            {
+                Chunk *w = pending.begin()->second;
+                pending.erase(pending.begin());
+                out << w->text; // sync_out::write (:311): here in read order
+                ++next;
+                free_q.push(w);
+            }
+        }
+    });
+
+    std::string parse_error;
+    size_t seq = 0;
+    try
+    {
+        std::string id, s;
+        Chunk *ch = nullptr;
+        size_t bases = 0;
+        auto flush = [&] {
+            if (ch && !ch->ids.empty())
+            {
+                ch->seq = seq++;
+                work_q.push(ch);
+            }
+            else if (ch)
+                free_q.push(ch);
+            ch = nullptr;
+        };
+        while (fin.next(id, s))
+        {
+            const uint64_t nw = txr_packed_words(s.size());
+            if (ch && (ch->ids.size() >= kChunkReads || bases + s.size() > kChunkBases || ch->words_used + nw > ch->words_cap))
+                flush();
+            if (!ch)
+            {
+                free_q.pop(ch);
+                ch->ids.clear();
+                ch->len.clear();
+                ch->word_off.clear();
+                ch->words_used = 0;
+                bases = 0;
+                if (nw > ch->words_cap) // a single sequence larger than a chunk: grow this chunk's buffer
+                {
+                    txr_host_free(ch->words);
+                    ch->words_cap = nw + 64;
+                    ch->words = static_cast<uint64_t *>(txr_host_alloc(ch->words_cap * 8));
+                    if (!ch->words)
+                        throw std::runtime_error(txr_last_error());
+                }
+            }
+            if (s.size() > 0xffffffffull)
+                throw std::runtime_error("sequence longer than 2^32 bases");
+            if (txr_pack_2bit(s.data(), s.size(), ch->words + ch->words_used) != TXR_OK)
+                throw std::runtime_error(std::string("read '") + id + "': " + txr_last_error());
+            ch->ids.push_back(id);
+            ch->len.push_back((uint32_t)s.size());
+            ch->word_off.push_back(ch->words_used);
+            ch->words_used += nw;
+            bases += s.size();
+        }
+        flush();
+    }
+    catch (std::exception const &e)
+    {
+        parse_error = e.what();
+    }
+    work_q.close();
+    for (auto &t : workers)
+        t.join();
+    done_q.close();
+    writer.join();
+    for (auto &ch : pool)
+        txr_host_free(ch.words);
+    for (txr_ctx *c : ctxs)
+        txr_ctx_destroy(c);
+    if (!parse_error.empty())
+        throw std::runtime_error(parse_error);
+    if (!worker_error.empty())
+        throw std::runtime_error(worker_error);
+}
+
+int execute_search(int argc, char const **argv) // taxor_search.cpp:364-389
+{
+    Config cfg;
+    std::vector<std::string> index_files, query_files;
+    try
+    {
+        parse_args(argc, argv, cfg);
+        std::cout << "checking input ... " << std::flush;
+        // sanity_checks, taxor_search.cpp:97-151
+        index_files = str_split(cfg.index_file, ',');
+        uint8_t k = 1, s = 1, t = 1;
+        uint64_t window = 1;
+        uint16_t scaling = 1;
+        bool syncmer = false;
+        for (auto &f : index_files)
+        {
+            if (!file_exists(f))
+                throw ParserError("Please check the given index file(s). \nThe following index file does not exist: " + f);
+            if (index_files.size() > 1)
+            {
+                TaxorIndexFile idx;
+                const std::string e = load_index_file(f, cfg, idx);
+                if (!e.empty())
+                    throw ParserError(e);
+                if (k == 1)
+                {
+                    k = idx.kmer_size;
+                    window = idx.window_size;
+                    scaling = idx.scaling;
+                    s = idx.syncmer_size;
+                    t = idx.t_syncmer;
+                    syncmer = idx.use_syncmer;
+                    continue;
+                }
+                if (k != idx.kmer_size || window != idx.window_size || scaling != idx.scaling || s != idx.syncmer_size ||
+                    t != idx.t_syncmer || syncmer != idx.use_syncmer)
+                    throw ParserError("At least two index files have been created with different kmer selection schemes.\n Please provide only index files using the same kmer-/syncmer-/window-size!");
+            }
+        }
+        query_files = str_split(cfg.query_file, ',');
+        for (auto &f : query_files)
+            if (!file_exists(f))
+                throw ParserError("Please check the given input query files. \nThe following query file does not exist: " + f);
+        std::cout << "done!" << std::endl;
+    }
+    catch (ParserError const &e)
+    {
+        std::cerr << "[TAXOR SEARCH ERROR] " << e.what() << '\n';
+        return -1;
+    }
+
+    const std::vector<int> devices = pick_devices(cfg.gpus);
+    if (devices.empty())
+    {
+        std::cerr << "[TAXOR SEARCH ERROR] no CUDA device available: " << txr_last_error() << " (this build has no CPU path)\n";
+        return -1;
+    }
+    // search_hixf, taxor_search.cpp:340-360: one header, then query x index appended
+    std::ofstream out(cfg.report_file);
+    out << "#QUERY_NAME\tACCESSION\tREFERENCE_NAME\tTAXID\tREF_LEN\tQUERY_LEN\tQHASH_COUNT\tQHASH_MATCH\tTAX_STR\tTAX_ID_STR\n";
+    try
+    {
+        for (auto &q : query_files)
+            for (auto &ix : index_files)
+                search_single(cfg, q, ix, out, devices);
+    }
+    catch (std::exception const &e)
+    {
+        std::cerr << "[TAXOR SEARCH ERROR] " << e.what() << '\n';
+        return -1;
+    }
+    return 0;
+}
+} // namespace
+
+int main(int argc, char const **argv)
+{
+    if (argc < 2 || std::string(argv[1]) == "-h" || std::string(argv[1]) == "--help")
+    {
+        std::cout << "taxor (B200 search driver) 0.2.0\n  usage: taxor search --index-file <a.hixf[,b.hixf]> --query-file <reads.fq[.gz][,...]> "
+                     "--output-file <out.tsv> [--threads 1..32] [--percentage 0..1] [--error-rate 0..1]\n"
+                     "  `taxor build` and `taxor profile` are provided by the reference binary (CPU).\n";
+        return argc < 2 ? -1 : 0;
+    }
+    const std::string sub = argv[1];
+    int rc = 0;
+    if (sub == "search")
+        rc = execute_search(argc - 2, argv + 2);
+    else if (sub == "build" || sub == "profile")
+    {
+        std::cerr << "[TAXOR ERROR] sub-command '" << sub << "' is not part of the B200 search driver; use the reference taxor binary.\n";
+        return -1;
+    }
+    else
+    {
+        std::cerr << "[TAXOR ERROR] You either forgot or misspelled the subcommand! Please specify which sub-program you want to use: one of [build, search, profile].\n";
+        return -1;
+    }
+    std::cout << "CPU time  : " << cputime() << " sec" << std::endl;          // main.cpp:79-84
+    std::cout << "Peak RSS  : " << (int)(peak_rss() / (1024 * 1024)) << " MByte" << std::endl;
+    return rc;
+}

@@ -35,6 +35,19 @@ def tlib():
     T.txs_hixf_reseeds.restype = C.c_uint64
     T.txs_hixf_arrays.argtypes = [vp] + [C.POINTER(vp)] * 8
     T.txs_hixf_arrays.restype = None
+    T.txs_last_error.restype = C.c_char_p
+    T.txs_hixf_write.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint16,
+                                 C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp]
+    T.txs_hixf_open.argtypes = [C.c_char_p, C.c_char_p]
+    T.txs_hixf_open.restype = vp
+    T.txs_hixf_close.argtypes = [vp]
+    T.txs_hixf_close.restype = None
+    T.txs_hixf_info.argtypes = [vp, vp]
+    T.txs_hixf_info.restype = None
+    T.txs_hixf_ixf.argtypes = [vp, C.c_uint64] + [C.POINTER(C.c_uint64)] * 4 + [C.POINTER(vp)] * 3
+    T.txs_hixf_ixf.restype = None
+    T.txs_hixf_species_field.argtypes = [vp, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    T.txs_hixf_species_field.restype = C.c_char_p
     _T = T
     return T
 
@@ -120,4 +133,88 @@ class BuiltHixf:
         if self._h:
             self.data = []
             tlib().txs_hixf_free(self._h)
+            self._h = None
+
+
+def _cstr_array(strings):
+    bufs = [s.encode() if isinstance(s, str) else bytes(s) for s in strings]
+    return (C.c_char_p * len(bufs))(*bufs), bufs
+
+
+def write_hixf(path, hx, *, k, s, t, use_syncmer=True, window_size=20, scaling=1, species=None, record_spec=""):
+    """Writes the arrays of `hx` (BuiltHixf or anything with the same attributes) as a `.hixf` file in the cereal
+    binary layout of SURVEY Appendix A.  species: list of dicts (organism_name, accession_id, taxid, taxnames_string,
+    taxid_string, user_bin, seq_len); default: one synthetic species per user bin."""
+    n_ub = int(hx.n_user_bins)
+    if species is None:
+        species = default_species(n_ub)
+    names, _k1 = _cstr_array([f"/synthetic/genome_{i}.fna" for i in range(n_ub)])
+    cols = {f: _cstr_array([sp[f] for sp in species]) for f in ("organism_name", "accession_id", "taxid", "taxnames_string", "taxid_string")}
+    sp_ub = np.array([sp["user_bin"] for sp in species], dtype=np.uint64)
+    sp_len = np.array([sp["seq_len"] for sp in species], dtype=np.uint64)
+    data = [np.ascontiguousarray(d) for d in hx.data]
+    dptr = (C.c_void_p * len(data))(*[d.ctypes.data for d in data])
+    arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (hx.seed, hx.bins, hx.tbins, hx.seg_len, hx.bin_off)]
+    nxt = np.ascontiguousarray(hx.next_ixf_id, dtype=np.int64)
+    ub = np.ascontiguousarray(hx.bin_to_ub, dtype=np.int64)
+    rc = tlib().txs_hixf_write(str(path).encode(), record_spec.encode(), window_size, k, s, t, int(use_syncmer), scaling, len(data),
+                               arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data, dptr,
+                               arrs[4].ctypes.data, nxt.ctypes.data, ub.ctypes.data, n_ub, names, len(species),
+                               cols["organism_name"][0], cols["accession_id"][0], cols["taxid"][0], cols["taxnames_string"][0],
+                               cols["taxid_string"][0], sp_ub.ctypes.data, sp_len.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(tlib().txs_last_error().decode())
+
+
+def default_species(n_ub):
+    """One species per user bin, listed in REVERSE user-bin order so that the user_bin -> species lookup is exercised."""
+    return [dict(organism_name=f"Synthetica species{u}", accession_id=f"GCF_{u:09d}.1", taxid=str(100000 + u),
+                 taxnames_string=f"k__Bacteria;p__Synth;g__Synthetica;s__Synthetica species{u}",
+                 taxid_string=f"2;1239;{100000 + u}", user_bin=u, seq_len=1000 + 7 * u) for u in reversed(range(n_ub))]
+
+
+class HixfFile:
+    """A `.hixf` file opened with the library's reader (mmap); exposes the same arrays as BuiltHixf."""
+
+    def __init__(self, path, record_spec=""):
+        T = tlib()
+        self._h = T.txs_hixf_open(str(path).encode(), record_spec.encode())
+        if not self._h:
+            raise RuntimeError(T.txs_last_error().decode())
+        self.record_spec = T.txs_last_error().decode()
+        info = np.zeros(14, dtype=np.uint64)
+        T.txs_hixf_info(self._h, info.ctypes.data)
+        (self.version, self.window_size, self.shape_size, self.shape_bits, self.k, self.s, self.t, self.parts, self.use_syncmer,
+         self.scaling, self.compressed, n_ixf, self.n_user_bins, self.n_species) = [int(x) for x in info]
+        self.seed, self.bins, self.tbins, self.seg_len = (np.zeros(n_ixf, np.uint64) for _ in range(4))
+        self.data, nxt, ub, off = [], [], [], [0]
+        for i in range(n_ixf):
+            sc = [C.c_uint64() for _ in range(4)]
+            ptr = [C.c_void_p() for _ in range(3)]
+            T.txs_hixf_ixf(self._h, i, *[C.byref(x) for x in sc], *[C.byref(x) for x in ptr])
+            self.seed[i], self.bins[i], self.tbins[i], self.seg_len[i] = [x.value for x in sc]
+            size = 3 * sc[3].value * sc[2].value
+            self.data.append(np.frombuffer((C.c_uint8 * size).from_address(ptr[0].value), dtype=np.uint8))
+            nb = sc[1].value
+            nxt.append(np.ctypeslib.as_array(C.cast(ptr[1], C.POINTER(C.c_int64)), (nb,)).copy())
+            ub.append(np.ctypeslib.as_array(C.cast(ptr[2], C.POINTER(C.c_int64)), (nb,)).copy())
+            off.append(off[-1] + nb)
+        self.bin_off = np.array(off, dtype=np.uint64)
+        self.next_ixf_id = np.concatenate(nxt)
+        self.bin_to_ub = np.concatenate(ub)
+        self.species = []
+        for i in range(self.n_species):
+            u, ln = C.c_uint64(), C.c_uint64()
+            f = [T.txs_hixf_species_field(self._h, i, j, C.byref(u), C.byref(ln)).decode() for j in range(5)]
+            self.species.append(dict(organism_name=f[0], accession_id=f[1], taxid=f[2], taxnames_string=f[3], taxid_string=f[4],
+                                     user_bin=u.value, seq_len=ln.value))
+
+    @property
+    def n_ixf(self):
+        return len(self.seed)
+
+    def close(self):
+        if self._h:
+            self.data = []
+            tlib().txs_hixf_close(self._h)
             self._h = None

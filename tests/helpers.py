@@ -78,3 +78,35 @@ def assert_same_search(res, ora, n):
     kept_ub, kept_cnt = res.user_bin[res.keep], res.count[res.keep]
     assert np.array_equal(kept_ub, ora["ub"])
     assert np.array_equal(kept_cnt, ora["cnt"])
+
+
+HEADER = "#QUERY_NAME\tACCESSION\tREFERENCE_NAME\tTAXID\tREF_LEN\tQUERY_LEN\tQHASH_COUNT\tQHASH_MATCH\tTAX_STR\tTAX_ID_STR\n"
+
+
+def oracle_tsv(oracle, arrays, species, records, *, k, s, t, use_syncmer, window_size=20, scaling=1, percentage=-1.0,
+               error_rate=0.04, header=True):
+    """The result file `taxor search --threads 1` writes (src/main/taxor_search.cpp:268-306, 343), restated on top of
+    the oracle: records = [(id, ascii sequence)]."""
+    codes = [np.array([oracle.dna4_rank(c) for c in seq], dtype=np.uint8) for _, seq in records]
+    off = np.zeros(len(records) + 1, dtype=np.uint64)
+    if records:
+        off[1:] = np.cumsum([len(c) for c in codes])
+    flat = np.concatenate(codes) if codes else np.zeros(0, np.uint8)
+    res = oracle.search_batch(oracle.make_hixf(arrays), np.ascontiguousarray(flat, dtype=np.uint8), off, k=k, s=s, t=t,
+                              use_syncmer=use_syncmer, window_size=window_size, scaling=scaling, percentage=percentage,
+                              error_rate=error_rate)
+    ub_index = {}
+    for i, sp in enumerate(species):                       # std::map::emplace: the first entry for a user bin wins (:172-178)
+        ub_index.setdefault(sp["user_bin"], i)
+    out = [HEADER] if header else []
+    for r, (rid, seq) in enumerate(records):
+        a, b = int(res["hit_off"][r]), int(res["hit_off"][r + 1])
+        if a == b:
+            out.append(f"{rid}\t-\t-\t-\t-\t{len(seq)}\n")
+            continue
+        for i in range(a, b):
+            sp = species[ub_index.get(int(res["ub"][i]), 0)]
+            out.append("\t".join([rid, sp["accession_id"], sp["organism_name"], sp["taxid"], str(sp["seq_len"]), str(len(seq)),
+                                  str(int(res["hash_count"][r])), str(int(res["cnt"][i])), sp["taxnames_string"],
+                                  sp["taxid_string"]]) + "\n")
+    return "".join(out)

@@ -1,0 +1,66 @@
+"""not gpu: `.hixf` writer/reader (cereal binary layout of SURVEY Appendix A, IXF record order as data)."""
+import os
+
+import numpy as np
+import pytest
+
+from taxor_b200 import tools
+
+
+def small_index():
+    rng = np.random.default_rng(2)
+    ub = [np.unique(rng.integers(0, 2**63, size=int(n), dtype=np.uint64)) for n in rng.integers(100, 900, 21)]
+    return tools.BuiltHixf(ub, t_max=4, seed=5)
+
+
+def test_roundtrip_and_header_bytes(tmp_path, built_libs):
+    hx = small_index()
+    path = tmp_path / "t.hixf"
+    tools.write_hixf(path, hx, k=22, s=12, t=5, use_syncmer=True, window_size=20, scaling=1)
+    raw = open(path, "rb").read()
+    # fixed-position header fields: u32 version, u64 window, shape (u64 size, u64 bits), 4 x u8, bool, u16, bool
+    assert raw[:4] == (1).to_bytes(4, "little") and raw[4:12] == (20).to_bytes(8, "little")
+    assert raw[12:20] == (22).to_bytes(8, "little") and raw[20:28] == ((1 << 22) - 1).to_bytes(8, "little")
+    assert raw[28:32] == bytes([22, 12, 5, 1]) and raw[32] == 1 and raw[33:35] == (1).to_bytes(2, "little") and raw[35] == 0
+    f = tools.HixfFile(path)
+    assert (f.version, f.window_size, f.k, f.s, f.t, f.use_syncmer, f.scaling, f.compressed) == (1, 20, 22, 12, 5, 1, 1, 0)
+    assert f.record_spec == "bins,tbins,slots,bin_words,max_elems,seed"          # auto-detected: the writer's order
+    assert f.n_ixf == hx.n_ixf and f.n_user_bins == hx.n_user_bins == f.n_species
+    for a, b in ((f.seed, hx.seed), (f.bins, hx.bins), (f.tbins, hx.tbins), (f.seg_len, hx.seg_len), (f.bin_off, hx.bin_off),
+                 (f.next_ixf_id, hx.next_ixf_id), (f.bin_to_ub, hx.bin_to_ub)):
+        assert np.array_equal(a, b)
+    assert all(np.array_equal(x, y) for x, y in zip(f.data, hx.data))
+    assert f.species == tools.default_species(hx.n_user_bins)
+    f.close()
+    # another record order: written and read back explicitly, and found by the auto-detection
+    spec = "bins,tbins,slots,bin_words,max_elems,seg_len,seed"
+    tools.write_hixf(path, hx, k=20, s=10, t=5, record_spec=spec)
+    g = tools.HixfFile(path, spec)
+    assert np.array_equal(g.seed, hx.seed) and g.k == 20
+    g.close()
+    g = tools.HixfFile(path)
+    assert g.record_spec == spec
+    g.close()
+    hx.close()
+
+
+def test_malformed_files_are_rejected(tmp_path, built_libs):
+    hx = small_index()
+    path = tmp_path / "t.hixf"
+    tools.write_hixf(path, hx, k=22, s=12, t=5)
+    raw = open(path, "rb").read()
+    for cut in (10, 40, len(raw) // 2, len(raw) - 1):
+        open(tmp_path / "cut.hixf", "wb").write(raw[:cut])
+        with pytest.raises(RuntimeError):
+            tools.HixfFile(tmp_path / "cut.hixf")
+    open(tmp_path / "extra.hixf", "wb").write(raw + b"\0" * 8)         # must tile exactly
+    with pytest.raises(RuntimeError):
+        tools.HixfFile(tmp_path / "extra.hixf")
+    open(tmp_path / "v2.hixf", "wb").write((2).to_bytes(4, "little") + raw[4:])
+    with pytest.raises(RuntimeError, match="version"):
+        tools.HixfFile(tmp_path / "v2.hixf")
+    with pytest.raises(RuntimeError):
+        tools.HixfFile(tmp_path / "missing.hixf")
+    with pytest.raises(RuntimeError):
+        tools.HixfFile(path, "bins,tbins,slots,seed")                      # wrong explicit order
+    hx.close()

@@ -91,16 +91,22 @@ def test_syncmer_hand_derived(oracle):
             r = r * 4 + (3 - int(c))
         return min(f, r)
 
-    for _ in range(20):
+    done = 0
+    while done < 20:
         codes = rng.integers(0, 4, 400, dtype=np.uint8)
-        exp = []
+        exp, tied = [], False
         for j in range(len(codes) - k + 1):
             sm = [canon(codes[j + q:j + q + s]) for q in range(k - s + 1)]
-            assert len(set(sm)) == len(sm)                       # random 12-mers: no ties
+            if len(set(sm)) != len(sm):                          # a tie (e.g. an s-mer next to its reverse complement):
+                tied = True                                      # history-dependent, covered by the golden vectors instead
+                break
             if int(np.argmin(sm)) == t - 1:
                 x = canon(codes[j:j + k])
                 p = x * 0x9E3779B97F4A7C15
                 exp.append((p & M64) ^ (p >> 64))
+        if tied:
+            continue
+        done += 1
         got = oracle.syncmer_hashes_raw(codes, k, s, t)
         assert got.tolist() == exp
 
