@@ -88,7 +88,8 @@ def test_cli_end_to_end_result_file(tmp_path, oracle, built_libs):
     body = H.oracle_tsv(oracle, ds.arrays, species, records, k=22, s=12, t=5, use_syncmer=True, percentage=0.15, header=False)
     assert open(out).read() == H.HEADER + body * 4
     # an illegal character aborts loudly
-    open(tmp_path / "bad.fq", "w").write("@r1\nACGT!ACGTACGTACGTACGTACGTACGT\n+\n" + "I" * 30 + "\n")
+    bad = "ACGT!ACGTACGTACGTACGTACGTACGT"
+    open(tmp_path / "bad.fq", "w").write(f"@r1\n{bad}\n+\n{'I' * len(bad)}\n")
     r = run_cli("search", "--index-file", str(idx_path), "--query-file", str(tmp_path / "bad.fq"), "--output-file", str(tmp_path / "b.tsv"))
     assert r.returncode == 255 and "illegal nucleotide" in r.stderr
 
