@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=int(os.environ.get("TAXOR_BENCH_READS", 1_000_000)), help="reads per GPU per step")
     ap.add_argument("--read-len", type=int, default=10_000)
     ap.add_argument("--genomes", type=int, default=int(os.environ.get("TAXOR_BENCH_GENOMES", 1000)))
-    ap.add_argument("--genome-len", type=int, default=int(os.environ.get("TAXOR_BENCH_GENOME_LEN", 1_000_000)), help="mean genome length")
+    ap.add_argument("--genome-len", type=int, default=int(os.environ.get("TAXOR_BENCH_GENOME_LEN", 4_000_000)), help="mean genome length")
     ap.add_argument("--t-max", type=int, default=64)
     ap.add_argument("--read-error", type=float, default=0.05)
     ap.add_argument("--error-rate", type=float, default=0.10, help="taxor search --error-rate (see DESIGN.md workload)")

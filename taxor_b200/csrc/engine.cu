@@ -189,7 +189,9 @@ enum CounterSlot : int
 struct Slot
 {
     cudaStream_t stream{nullptr};
-    cudaEvent_t ev[6]{}; // start, h2d done, hash done, dedup done, query done, d2h done
+    // events: 0 h2d start, 1 h2d done (copy stream) | 6 compute start, 2 hash done, 3 dedup done, 4 query done,
+    // 7 compute done (compute stream) | 5 d2h done (copy stream)
+    cudaEvent_t ev[8]{};
     DevBuf words;
     BatchDev meta;
     DevBuf hashes, n_raw, hash_count, gtable, deferred;
@@ -253,6 +255,7 @@ struct txr_ctx
     std::vector<uint64_t> hb_off, hb_hashes;
     DevBuf scratch_a, scratch_b;
     cudaStream_t primary{nullptr};     // caller's stream: every search forks from it and joins back into it
+    cudaStream_t compute{nullptr};     // ALL kernels run here, in batch order; slot streams only carry copies
     cudaEvent_t fork_ev{nullptr}, join_ev{nullptr};
 };
 
@@ -283,6 +286,8 @@ static uint64_t next_pow2(uint64_t x)
 
 static int ensure_slots(txr_ctx *c)
 {
+    if (!c->compute)
+        CU(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
     while ((int)c->slots.size() < c->n_slots)
     {
         auto s = std::make_unique<Slot>();
@@ -430,7 +435,7 @@ static int slot_reserve(txr_ctx *c, Slot &s, const BatchMeta &m)
 }
 
 static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev &d, const uint64_t *d_words,
-                             bool dedup)
+                             bool dedup, cudaStream_t cs)
 {
     uint32_t *cnt = s.counters.as<uint32_t>();
     HashArgs h{};
@@ -448,15 +453,15 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     h.s = c->params.syncmer_size;
     h.t = c->params.t_syncmer;
     if (c->params.use_syncmer)
-        CU(launch_syncmer(h, c->sm_count, s.stream));
+        CU(launch_syncmer(h, c->sm_count, cs));
     else
-        CU(launch_kmer(h, c->sm_count, s.stream));
+        CU(launch_kmer(h, c->sm_count, cs));
     c->timing.hash_launches += 1;
-    CU(cudaEventRecord(s.ev[2], s.stream));
+    CU(cudaEventRecord(s.ev[2], cs));
 
     if (!dedup)
     {
-        CU(cudaEventRecord(s.ev[3], s.stream));
+        CU(cudaEventRecord(s.ev[3], cs));
         return TXR_OK;
     }
     DedupArgs dd{};
@@ -472,26 +477,26 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
         {
             dd.read_ids = m.ids_small.size() == m.n_reads ? nullptr : d.ids_small.as<uint32_t>();
             dd.n_ids = (uint32_t)m.ids_small.size();
-            CU(launch_dedup_warp(dd, c->sm_count, cnt + C_DEDUP_WORK, s.deferred.as<uint32_t>(), cnt + C_DEDUP_DEFERRED, s.stream));
+            CU(launch_dedup_warp(dd, c->sm_count, cnt + C_DEDUP_WORK, s.deferred.as<uint32_t>(), cnt + C_DEDUP_DEFERRED, cs));
             dd.read_ids = s.deferred.as<uint32_t>(); // reads with too many raw hashes for the warp table
-            CU(launch_dedup_deferred(dd, c->sm_count, cnt + C_DEDUP_DEFERRED, s.stream));
+            CU(launch_dedup_deferred(dd, c->sm_count, cnt + C_DEDUP_DEFERRED, cs));
             c->timing.dedup_launches += 2;
         }
         if (!m.ids_medium.empty())
         {
             dd.read_ids = d.ids_medium.as<uint32_t>();
             dd.n_ids = (uint32_t)m.ids_medium.size();
-            CU(launch_dedup_medium(dd, s.stream));
+            CU(launch_dedup_medium(dd, cs));
             c->timing.dedup_launches += 1;
         }
         if (!m.ids_global.empty())
         {
-            CU(cudaMemsetAsync(s.gtable.p, 0xff, m.gtable_off.back() * 8, s.stream));
+            CU(cudaMemsetAsync(s.gtable.p, 0xff, m.gtable_off.back() * 8, cs));
             dd.read_ids = d.ids_global.as<uint32_t>();
             dd.n_ids = (uint32_t)m.ids_global.size();
             dd.gtable = s.gtable.as<uint64_t>();
             dd.gtable_off = d.gtable_off.as<uint64_t>();
-            CU(launch_dedup_global(dd, s.stream));
+            CU(launch_dedup_global(dd, cs));
             c->timing.dedup_launches += 1;
         }
     }
@@ -499,14 +504,14 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     {
         dd.read_ids = nullptr;
         dd.n_ids = m.n_reads;
-        CU(launch_filter(dd, s.stream));
+        CU(launch_filter(dd, cs));
         c->timing.dedup_launches += 1;
     }
-    CU(cudaEventRecord(s.ev[3], s.stream));
+    CU(cudaEventRecord(s.ev[3], cs));
     return TXR_OK;
 }
 
-static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev &d)
+static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev &d, cudaStream_t cs)
 {
     const DeviceIndex &ix = c->index;
     uint32_t *cnt = s.counters.as<uint32_t>();
@@ -550,9 +555,9 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
             q.items_cap = m.n_reads;
             q.cursor = lc + 2;
             if (ix.ixf[0].tbins <= kSmallRowBytes)
-                CU(launch_query_small(q, c->sm_count, s.stream));
+                CU(launch_query_small(q, c->sm_count, cs));
             else
-                CU(launch_query_large(q, c->sm_count, ix.max_tbins, s.stream));
+                CU(launch_query_large(q, c->sm_count, ix.max_tbins, cs));
             c->timing.query_launches += 1;
         }
         else
@@ -562,19 +567,19 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
             q.items = queues + (size_t)(2 * lv) * s.queue_cap;
             q.n_items_ptr = lc + 0;
             q.cursor = lc + 2;
-            CU(launch_query_small(q, c->sm_count, s.stream));
+            CU(launch_query_small(q, c->sm_count, cs));
             c->timing.query_launches += 1;
             if (ix.any_large)
             {
                 q.items = queues + (size_t)(2 * lv + 1) * s.queue_cap;
                 q.n_items_ptr = lc + 1;
                 q.cursor = lc + 3;
-                CU(launch_query_large(q, c->sm_count, ix.max_tbins, s.stream));
+                CU(launch_query_large(q, c->sm_count, ix.max_tbins, cs));
                 c->timing.query_launches += 1;
             }
         }
     }
-    CU(cudaEventRecord(s.ev[4], s.stream));
+    CU(cudaEventRecord(s.ev[4], cs));
     return TXR_OK;
 }
 
@@ -596,13 +601,20 @@ static int submit_batch(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev 
         bd = &s.meta;
         d_words = s.words.as<uint64_t>();
     }
-    CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, s.stream));
     CU(cudaEventRecord(s.ev[1], s.stream));
-    TRY(launch_hash_stage(c, s, m, *bd, d_words, true));
+    // kernels of all slots share ONE compute stream (in batch order): copies overlap compute, kernels never
+    // compete with each other for SMs / DRAM
+    cudaStream_t cs = c->compute;
+    CU(cudaStreamWaitEvent(cs, s.ev[1], 0));
+    CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, cs));
+    CU(cudaEventRecord(s.ev[6], cs));
+    TRY(launch_hash_stage(c, s, m, *bd, d_words, true, cs));
     if (run_query)
-        TRY(launch_query_stage(c, s, m, *bd));
+        TRY(launch_query_stage(c, s, m, *bd, cs));
     else
-        CU(cudaEventRecord(s.ev[4], s.stream));
+        CU(cudaEventRecord(s.ev[4], cs));
+    CU(cudaEventRecord(s.ev[7], cs));
+    CU(cudaStreamWaitEvent(s.stream, s.ev[7], 0));
     CU(cudaMemcpyAsync(s.h_counters.p, s.counters.p, C_TOTAL * 4, cudaMemcpyDeviceToHost, s.stream));
     s.bm = &m;
     s.bd = bd;
@@ -636,8 +648,10 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
         s.hit_cap = std::max<uint32_t>(s.hit_cap, hc[C_NHITS]) * 2;
         s.queue_cap = std::max(s.queue_cap, need_q) * 2;
         TRY(slot_reserve(c, s, m));
-        CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, s.stream));
-        TRY(launch_query_stage(c, s, m, *s.bd));
+        CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, c->compute));
+        TRY(launch_query_stage(c, s, m, *s.bd, c->compute));
+        CU(cudaEventRecord(s.ev[7], c->compute));
+        CU(cudaStreamWaitEvent(s.stream, s.ev[7], 0));
         CU(cudaMemcpyAsync(s.h_counters.p, s.counters.p, C_TOTAL * 4, cudaMemcpyDeviceToHost, s.stream));
     }
     const uint32_t *hc = s.h_counters.as<uint32_t>();
@@ -650,7 +664,7 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
     float ms = 0;
     cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]);
     c->timing.h2d_ms += ms;
-    cudaEventElapsedTime(&ms, s.ev[1], s.ev[2]);
+    cudaEventElapsedTime(&ms, s.ev[6], s.ev[2]);
     c->timing.hash_ms += ms;
     cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]);
     c->timing.dedup_ms += ms;
@@ -660,7 +674,7 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
     if (fetch)
     {
         const uint32_t n = m.n_reads;
-        CU(cudaEventRecord(s.ev[4], s.stream));
+        CU(cudaEventRecord(s.ev[0], s.stream));
         CU(cudaMemcpyAsync(s.h_hash_count.p, s.hash_count.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
         uint32_t *hh = s.h_hits.as<uint32_t>();
         if (n_hits)
@@ -671,7 +685,7 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
         }
         CU(cudaEventRecord(s.ev[5], s.stream));
         CU(cudaStreamSynchronize(s.stream));
-        cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]);
+        cudaEventElapsedTime(&ms, s.ev[0], s.ev[5]);
         c->timing.d2h_ms += ms;
 
         // ---- host post-pass: group by read, DFS pre-order, threshold, 0.8*max flags ----
@@ -763,6 +777,7 @@ static int fork_streams(txr_ctx *c)
         CU(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
     }
     CU(cudaEventRecord(c->fork_ev, c->primary));
+    CU(cudaStreamWaitEvent(c->compute, c->fork_ev, 0));
     for (auto &s : c->slots)
         CU(cudaStreamWaitEvent(s->stream, c->fork_ev, 0));
     return TXR_OK;
@@ -770,6 +785,8 @@ static int fork_streams(txr_ctx *c)
 // ... and the caller's stream wait for everything the slots did (so events on it bracket the search)
 static int join_streams(txr_ctx *c)
 {
+    CU(cudaEventRecord(c->join_ev, c->compute));
+    CU(cudaStreamWaitEvent(c->primary, c->join_ev, 0));
     for (auto &s : c->slots)
     {
         CU(cudaEventRecord(c->join_ev, s->stream));
@@ -833,6 +850,8 @@ void txr_ctx_destroy(txr_ctx *c)
             cudaEventDestroy(e);
         cudaStreamDestroy(s->stream);
     }
+    if (c->compute)
+        cudaStreamDestroy(c->compute);
     if (c->fork_ev)
     {
         cudaEventDestroy(c->fork_ev);
@@ -1299,7 +1318,7 @@ int txr_hash_batch(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, 
         CU(cudaMemcpyAsync(s.words.p, words + m.first_word, m.n_words * 8, cudaMemcpyHostToDevice, s.stream));
         TRY(upload_batch_meta(m, s.meta, s.stream, nullptr));
         CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, s.stream));
-        TRY(launch_hash_stage(c, s, m, s.meta, s.words.as<uint64_t>(), dedup != 0));
+        TRY(launch_hash_stage(c, s, m, s.meta, s.words.as<uint64_t>(), dedup != 0, s.stream));
         CU(cudaStreamSynchronize(s.stream));
         uint32_t ovf = 0;
         CU(cudaMemcpy(&ovf, s.counters.as<uint32_t>() + C_HASH_OVERFLOW, 4, cudaMemcpyDeviceToHost));

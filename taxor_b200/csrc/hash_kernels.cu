@@ -646,18 +646,22 @@ __device__ uint32_t table_compact(const uint64_t *tab, uint32_t slots, uint64_t 
 }
 } // namespace
 
-// One WARP per read, table of kWarpSlots keys in shared memory.  The keys are streamed in chunks of 32: a lane
-// whose atomicCAS claimed an empty slot owns the first occurrence of its key, the ballot of the owners compacts the
-// chunk in place (first-occurrence order, the same order an ankerl set iterates in).  Reads with more raw hashes
-// than the table can take at load factor 2/3 are appended to `deferred` for the CTA-per-read kernel.
+// One WARP per read.  The table (kWarpSlots x u32 in shared memory) stores 1 + the INDEX of the first occurrence of a
+// key in the read's raw list, so that a slot is claimed with one 32-bit shared-memory atomicCAS and the 64-bit keys
+// stay where kernel #1 wrote them (L2-resident).  Pass 1 marks, per lane and chunk, whether its key is a first
+// occurrence (ties between equal keys of one chunk are broken by the CAS); pass 2 compacts the list in place in
+// first-occurrence order -- the order an ankerl set iterates in -- applying the FracMin filter on the way.
+// Reads with more raw hashes than the table takes at load factor 3/4 are appended to `deferred` for the
+// CTA-per-read kernel.
 constexpr int kWarpSlots = 2048;
-constexpr int kDedupWarps = 2; // 32 KB of static shared memory per CTA, 7 CTAs per SM
+constexpr int kDedupWarps = 4; // 32 KB of static shared memory per CTA
+constexpr uint32_t kWarpMaxKeys = kWarpSlots * 3 / 4;
 __global__ void __launch_bounds__(32 * kDedupWarps) dedup_warp_kernel(DedupArgs a, uint32_t *work_counter, uint32_t *deferred,
                                                                       uint32_t *n_deferred)
 {
-    __shared__ uint64_t s_tab[kDedupWarps][kWarpSlots];
+    __shared__ uint32_t s_tab[kDedupWarps][kWarpSlots];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint64_t *tab = s_tab[wib];
+    uint32_t *tab = s_tab[wib];
     while (true)
     {
         uint32_t id = 0;
@@ -668,62 +672,58 @@ __global__ void __launch_bounds__(32 * kDedupWarps) dedup_warp_kernel(DedupArgs 
             break;
         const uint32_t r = a.read_ids ? a.read_ids[id] : id;
         const uint32_t n = a.n_raw[r];
-        if (n > (uint32_t)(kWarpSlots * 2 / 3))
+        if (n > kWarpMaxKeys)
         {
             if (lane == 0)
                 deferred[atomicAdd(n_deferred, 1u)] = r;
             continue;
         }
-        ulonglong2 *t2 = reinterpret_cast<ulonglong2 *>(tab);
+        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
 #pragma unroll
-        for (int i = 0; i < kWarpSlots / 64; ++i)
-            t2[i * 32 + lane] = make_ulonglong2(kEmptyKey, kEmptyKey);
+        for (int i = 0; i < kWarpSlots / 128; ++i)
+            t4[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
         uint64_t *p = a.hashes + a.out_off[r];
-        uint32_t base = 0;
-        bool saw_empty_key = false;
+        // pass 1: bit c of `firsts` = this lane's key of chunk c is a first occurrence
+        uint64_t firsts = 0; // kWarpMaxKeys / 32 = 48 chunks at most
         uint64_t next = lane < n ? p[lane] : 0;
-        for (uint32_t c0 = 0; c0 < n; c0 += 32)
+        uint32_t chunk = 0;
+        for (uint32_t c0 = 0; c0 < n; c0 += 32, ++chunk)
         {
             const uint32_t i = c0 + lane;
             const uint64_t key = next;
             if (i + 32 < n)
                 next = p[i + 32]; // prefetch the next chunk before the atomics
-            bool first = false;
             if (i < n)
             {
-                if (key == kEmptyKey)
-                    saw_empty_key = true;
-                else
+                uint32_t slot = (uint32_t)(key ^ (key >> 29)) & (kWarpSlots - 1);
+                while (true)
                 {
-                    uint32_t slot = (uint32_t)(key ^ (key >> 32)) & (kWarpSlots - 1);
-                    while (true)
+                    const uint32_t old = atomicCAS(&tab[slot], 0u, i + 1);
+                    if (old == 0)
                     {
-                        const unsigned long long old = atomicCAS((unsigned long long *)&tab[slot], (unsigned long long)kEmptyKey,
-                                                                 (unsigned long long)key);
-                        if (old == kEmptyKey)
-                        {
-                            first = true;
-                            break;
-                        }
-                        if (old == key)
-                            break;
-                        slot = (slot + 1) & (kWarpSlots - 1);
+                        firsts |= 1ull << chunk;
+                        break;
                     }
+                    if (p[old - 1] == key) // an earlier (or same-chunk) occurrence owns this key
+                        break;
+                    slot = (slot + 1) & (kWarpSlots - 1);
                 }
             }
-            const bool keep = first && scaling_keep(key, a.scaling, a.scaling_limit);
+        }
+        __syncwarp();
+        // pass 2: in-place compaction (writes never run ahead of the reads of the same chunk)
+        uint32_t base = 0;
+        chunk = 0;
+        for (uint32_t c0 = 0; c0 < n; c0 += 32, ++chunk)
+        {
+            const uint32_t i = c0 + lane;
+            const uint64_t key = i < n ? p[i] : 0;
+            const bool keep = ((firsts >> chunk) & 1) && scaling_keep(key, a.scaling, a.scaling_limit);
             const uint32_t bal = __ballot_sync(0xffffffffu, keep);
             if (keep)
-                p[base + __popc(bal & ((1u << lane) - 1u))] = key; // base + rank <= i: never ahead of the reads
+                p[base + __popc(bal & ((1u << lane) - 1u))] = key;
             base += __popc(bal);
-        }
-        // the sentinel value itself can be a hash: it bypasses the table and is appended once
-        if (__any_sync(0xffffffffu, saw_empty_key) && scaling_keep(kEmptyKey, a.scaling, a.scaling_limit))
-        {
-            if (lane == 0)
-                p[base] = kEmptyKey;
-            ++base;
         }
         if (lane == 0)
             a.hash_count[r] = base;
@@ -883,7 +883,7 @@ cudaError_t launch_dedup_warp(const DedupArgs &a, int sm_count, uint32_t *work_c
 {
     if (a.n_ids == 0)
         return cudaSuccess;
-    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sm_count * 7, ((uint64_t)a.n_ids + kDedupWarps - 1) / kDedupWarps);
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sm_count * 6, ((uint64_t)a.n_ids + kDedupWarps - 1) / kDedupWarps);
     dedup_warp_kernel<<<grid, 32 * kDedupWarps, 0, st>>>(a, work_counter, deferred, n_deferred);
     return cudaGetLastError();
 }

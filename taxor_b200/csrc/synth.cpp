@@ -15,6 +15,7 @@
 #include <cstring>
 #include <memory>
 #include <numeric>
+#include <parallel/algorithm>
 #include <queue>
 #include <vector>
 #ifdef _OPENMP
@@ -245,6 +246,7 @@ struct Builder
         x.ub = ubv;
         const size_t slots = 3 * x.seg_len;
         x.data.assign(slots * x.tbins, 0);
+        std::vector<uint8_t> cols(slots * bins); // bin-major scratch: cols[b * slots + slot]
         while (true)
         {
             int failed = 0;
@@ -252,29 +254,40 @@ struct Builder
             {
                 std::vector<uint32_t> cnt, queue, stack_s;
                 std::vector<uint64_t> xr, stack_h;
-                std::vector<uint8_t> col(slots);
 #pragma omp for schedule(dynamic, 1)
                 for (long b = 0; b < (long)bins; ++b)
                 {
                     if (failed)
                         continue;
-                    if (!peel_bin(kptr[b], kn[b], x.seed, (uint32_t)x.seg_len, col.data(), cnt, xr, queue, stack_h, stack_s))
+                    if (!peel_bin(kptr[b], kn[b], x.seed, (uint32_t)x.seg_len, cols.data() + (size_t)b * slots, cnt, xr, queue, stack_h,
+                                  stack_s))
                     {
 #pragma omp atomic write
                         failed = 1;
-                        continue;
                     }
-                    uint8_t *dst = x.data.data() + b;
-                    for (size_t s = 0; s < slots; ++s)
-                        dst[s * x.tbins] = col[s];
                 }
             }
             if (!failed)
                 break;
             // construct_ixf.cpp:101-108: clear the whole IXF and draw a new seed
-            std::fill(x.data.begin(), x.data.end(), 0);
             x.seed = splitmix64(seed_state);
             ++out->reseeds;
+        }
+        // interleave: data[slot * tbins + bin]; every thread owns a block of rows, so no cache line is shared
+        {
+            const size_t block = 2048;
+#pragma omp parallel for schedule(static)
+            for (long s0 = 0; s0 < (long)slots; s0 += (long)block)
+            {
+                const size_t s1 = std::min(slots, (size_t)s0 + block);
+                for (size_t b = 0; b < bins; ++b)
+                {
+                    const uint8_t *src = cols.data() + b * slots;
+                    uint8_t *dst = x.data.data() + b;
+                    for (size_t sl = (size_t)s0; sl < s1; ++sl)
+                        dst[sl * x.tbins] = src[sl];
+                }
+            }
         }
         if (want_union)
         {
@@ -285,7 +298,10 @@ struct Builder
             all.reserve(total);
             for (size_t b = 0; b < bins; ++b)
                 all.insert(all.end(), kptr[b], kptr[b] + kn[b]);
-            std::sort(all.begin(), all.end());
+            if (all.size() > (1u << 20))
+                __gnu_parallel::sort(all.begin(), all.end());
+            else
+                std::sort(all.begin(), all.end());
             all.erase(std::unique(all.begin(), all.end()), all.end());
         }
         return my;
@@ -380,6 +396,21 @@ int txs_reads(const uint64_t *const *genome_words, const uint64_t *genome_len, u
             out_genome[r] = (uint32_t)g;
     }
     return bad ? -1 : 0;
+}
+
+// sorts and de-duplicates n_ub key arrays in place (parallel over arrays); counts[i] is updated
+void txs_sort_unique_many(uint64_t *const *keys, uint64_t *counts, uint64_t n_ub, int threads)
+{
+#ifdef _OPENMP
+    if (threads > 0)
+        omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long i = 0; i < (long)n_ub; ++i)
+    {
+        std::sort(keys[i], keys[i] + counts[i]);
+        counts[i] = (uint64_t)(std::unique(keys[i], keys[i] + counts[i]) - keys[i]);
+    }
 }
 
 void *txs_hixf_build(const uint64_t *const *ub_hashes, const uint64_t *ub_n, uint64_t n_ub, uint32_t t_max, uint64_t seed,

@@ -25,6 +25,8 @@ def tlib():
     T.txs_genome.argtypes = [C.c_uint64, C.c_uint64, vp]
     T.txs_genome.restype = None
     T.txs_reads.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_double, C.c_uint64, vp, vp, vp, C.c_int]
+    T.txs_sort_unique_many.argtypes = [vp, vp, C.c_uint64, C.c_int]
+    T.txs_sort_unique_many.restype = None
     T.txs_hixf_build.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
     T.txs_hixf_build.restype = vp
     T.txs_hixf_free.argtypes = [vp]
@@ -88,10 +90,13 @@ class BuiltHixf:
     """An HIXF built by the CPU tooling; exposes the plain arrays every consumer takes."""
 
     def __init__(self, ub_hashes, t_max: int = 64, seed: int = 1, threads: int = 0) -> None:
-        self._ub = [np.ascontiguousarray(np.unique(h), dtype=np.uint64) for h in ub_hashes]
+        # sorted distinct key sets (in place on private copies, parallel over user bins)
+        self._ub = [np.array(h, dtype=np.uint64, copy=True) for h in ub_hashes]
         n = len(self._ub)
         ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in self._ub])
         cnt = np.array([len(a) for a in self._ub], dtype=np.uint64)
+        tlib().txs_sort_unique_many(ptrs, cnt.ctypes.data, n, threads)
+        self._ub = [a[: int(c)] for a, c in zip(self._ub, cnt)]
         self._h = tlib().txs_hixf_build(ptrs, cnt.ctypes.data, n, t_max, seed, threads)
         if not self._h:
             raise RuntimeError("txs_hixf_build failed")
