@@ -303,13 +303,17 @@ __global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
         bool carry_valid = false;
         ScanState carry{0, 0};
 
+        uint64_t hi_next = (uint64_t)lane < nw && W ? w[lane] : 0;
         for (uint64_t tile = 0; tile < W; tile += kTileWindows)
         {
-            const uint64_t g = (tile >> 5) + lane;
-            const uint64_t hi = g < nw ? w[g] : 0;
+            // this tile's word was fetched while the previous tile was processed; start the next fetch now
+            const uint64_t hi = hi_next;
+            const uint64_t g_next = ((tile + kTileWindows) >> 5) + lane;
+            hi_next = g_next < nw ? w[g_next] : 0;
             uint64_t lo = __shfl_down_sync(0xffffffffu, hi, 1);
+            const uint64_t lo31 = __shfl_sync(0xffffffffu, hi_next, 0); // word 32 of this tile = word 0 of the next
             if (lane == 31)
-                lo = g + 1 < nw ? w[g + 1] : 0;
+                lo = lo31;
             const uint64_t rhi = revcomp_block(lo), rlo = revcomp_block(hi);
             const uint32_t f[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
             const uint32_t rc[4] = {(uint32_t)rlo, (uint32_t)(rlo >> 32), (uint32_t)rhi, (uint32_t)(rhi >> 32)};
@@ -647,21 +651,23 @@ __device__ uint32_t table_compact(const uint64_t *tab, uint32_t slots, uint64_t 
 } // namespace
 
 // One WARP per read.  The table (kWarpSlots x u32 in shared memory) stores 1 + the INDEX of the first occurrence of a
-// key in the read's raw list, so that a slot is claimed with one 32-bit shared-memory atomicCAS and the 64-bit keys
-// stay where kernel #1 wrote them (L2-resident).  Pass 1 marks, per lane and chunk, whether its key is a first
-// occurrence (ties between equal keys of one chunk are broken by the CAS); pass 2 compacts the list in place in
-// first-occurrence order -- the order an ankerl set iterates in -- applying the FracMin filter on the way.
-// Reads with more raw hashes than the table takes at load factor 3/4 are appended to `deferred` for the
-// CTA-per-read kernel.
+// key in the read's raw list; the 64-bit keys stay where kernel #1 wrote them.  Shared-memory atomicCAS turned out to
+// be the bottleneck of an atomic version (~4 cycles per lane and SM on B200), so slots are claimed WITHOUT atomics,
+// in warp-synchronous rounds: every pending lane looks at its slot, writes its index if the slot is empty (lanes of
+// the same round may collide: one store lands), and after a __syncwarp() reads the slot back -- seeing its own
+// index means the lane owns the first occurrence, any other index is compared by key (duplicate) or probed past.
+// Pass 2 compacts the list in place in first-occurrence order (the order an ankerl set iterates in) and applies
+// the FracMin filter.  Reads with more raw hashes than the table takes at load factor 3/4 are appended to
+// `deferred` for the CTA-per-read kernel.
 constexpr int kWarpSlots = 2048;
 constexpr int kDedupWarps = 4; // 32 KB of static shared memory per CTA
-constexpr uint32_t kWarpMaxKeys = kWarpSlots * 3 / 4;
+constexpr uint32_t kWarpMaxKeys = kWarpSlots * 3 / 4; // 1536 < 2^11: an index + 1 fits the low 11 bits of a slot
 __global__ void __launch_bounds__(32 * kDedupWarps) dedup_warp_kernel(DedupArgs a, uint32_t *work_counter, uint32_t *deferred,
                                                                       uint32_t *n_deferred)
 {
     __shared__ uint32_t s_tab[kDedupWarps][kWarpSlots];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t *tab = s_tab[wib];
+    volatile uint32_t *tab = s_tab[wib];
     while (true)
     {
         uint32_t id = 0;
@@ -678,52 +684,83 @@ __global__ void __launch_bounds__(32 * kDedupWarps) dedup_warp_kernel(DedupArgs 
                 deferred[atomicAdd(n_deferred, 1u)] = r;
             continue;
         }
-        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+        uint4 *t4 = reinterpret_cast<uint4 *>(s_tab[wib]);
 #pragma unroll
         for (int i = 0; i < kWarpSlots / 128; ++i)
             t4[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
         uint64_t *p = a.hashes + a.out_off[r];
+        // Both passes stream the list in stages of kStage chunks whose loads are all issued before the first use:
+        // the raw list comes from DRAM (a batch's lists exceed L2), and one exposed load latency per CHUNK was what
+        // bounded earlier versions of this kernel (57 dependent round trips per read).
+        constexpr int kStage = 16;
         // pass 1: bit c of `firsts` = this lane's key of chunk c is a first occurrence
         uint64_t firsts = 0; // kWarpMaxKeys / 32 = 48 chunks at most
-        uint64_t next = lane < n ? p[lane] : 0;
-        uint32_t chunk = 0;
-        for (uint32_t c0 = 0; c0 < n; c0 += 32, ++chunk)
+        for (uint32_t s0 = 0; s0 < n; s0 += 32 * kStage)
         {
-            const uint32_t i = c0 + lane;
-            const uint64_t key = next;
-            if (i + 32 < n)
-                next = p[i + 32]; // prefetch the next chunk before the atomics
-            if (i < n)
+            uint64_t keys[kStage];
+#pragma unroll
+            for (int u = 0; u < kStage; ++u)
             {
+                const uint32_t i = s0 + 32 * u + lane;
+                keys[u] = i < n ? p[i] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kStage; ++u)
+            {
+                const uint32_t i = s0 + 32 * u + lane;
+                if (s0 + 32 * u >= n)
+                    break;
+                const uint64_t key = keys[u];
+                bool pending = i < n;
                 uint32_t slot = (uint32_t)(key ^ (key >> 29)) & (kWarpSlots - 1);
-                while (true)
+                // slot word = 21 tag bits of the key | 11 bits (index + 1): a different tag proves a different key
+                // without touching global memory
+                const uint32_t mine = ((uint32_t)(key >> 43) << 11) | (i + 1);
+                while (__any_sync(0xffffffffu, pending))
                 {
-                    const uint32_t old = atomicCAS(&tab[slot], 0u, i + 1);
-                    if (old == 0)
+                    if (pending && tab[slot] == 0)
+                        tab[slot] = mine; // racy on purpose: lanes of this round that share the slot, one store lands
+                    __syncwarp();
+                    if (pending)
                     {
-                        firsts |= 1ull << chunk;
-                        break;
+                        const uint32_t now = tab[slot];
+                        if (now == mine)
+                        {
+                            firsts |= 1ull << ((s0 >> 5) + u);
+                            pending = false;
+                        }
+                        else if ((now >> 11) == (mine >> 11) && p[(now & 2047u) - 1] == key)
+                            pending = false; // an earlier (or concurrent) occurrence owns this key
+                        else
+                            slot = (slot + 1) & (kWarpSlots - 1);
                     }
-                    if (p[old - 1] == key) // an earlier (or same-chunk) occurrence owns this key
-                        break;
-                    slot = (slot + 1) & (kWarpSlots - 1);
                 }
             }
         }
         __syncwarp();
-        // pass 2: in-place compaction (writes never run ahead of the reads of the same chunk)
+        // pass 2: in-place compaction in first-occurrence order (a stage is loaded completely before it is written)
         uint32_t base = 0;
-        chunk = 0;
-        for (uint32_t c0 = 0; c0 < n; c0 += 32, ++chunk)
+        for (uint32_t s0 = 0; s0 < n; s0 += 32 * kStage)
         {
-            const uint32_t i = c0 + lane;
-            const uint64_t key = i < n ? p[i] : 0;
-            const bool keep = ((firsts >> chunk) & 1) && scaling_keep(key, a.scaling, a.scaling_limit);
-            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-            if (keep)
-                p[base + __popc(bal & ((1u << lane) - 1u))] = key;
-            base += __popc(bal);
+            uint64_t keys[kStage];
+#pragma unroll
+            for (int u = 0; u < kStage; ++u)
+            {
+                const uint32_t i = s0 + 32 * u + lane;
+                keys[u] = i < n ? p[i] : 0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < kStage; ++u)
+            {
+                const uint32_t i = s0 + 32 * u + lane;
+                const bool keep = i < n && ((firsts >> ((s0 >> 5) + u)) & 1) && scaling_keep(keys[u], a.scaling, a.scaling_limit);
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (keep)
+                    p[base + __popc(bal & ((1u << lane) - 1u))] = keys[u];
+                base += __popc(bal);
+            }
         }
         if (lane == 0)
             a.hash_count[r] = base;
