@@ -264,8 +264,10 @@ struct txr_ctx
 // ---------------------------------------------------------------------------------------------------------
 static inline uint64_t windows_of(uint64_t len, int k) { return len >= (uint64_t)k ? len - k + 1 : 0; }
 
-// upper bound on the hashes kernel #1 can emit for a read (see DESIGN.md "hash capacity"): two selected windows
-// are at least min(t-1, k-s+1-t)+1 apart
+// Upper bound on the hashes kernel #1 can emit for a read.  Two selected windows j1 < j2 (states p = j+t-1) are at
+// least min(t-1, k-s+1-t)+1 apart: p2 became the state either by a strictly smaller arrival -- then it arrived at
+// window p2-(k-s) > j1, since from its arrival on the state can only be at or right of p2, so
+// j2-j1 > k-s+1-t -- or by a rescan, which happens at window (previous state)+1 >= p1+1 = j1+t, so j2-j1 >= t.
 static uint64_t hash_capacity(const txr_params &p, uint64_t len)
 {
     const uint64_t w = windows_of(len, p.kmer_size);
