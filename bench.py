@@ -42,7 +42,8 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=int(os.environ.get("TAXOR_BENCH_READS", 1_000_000)), help="reads per GPU per step")
     ap.add_argument("--read-len", type=int, default=10_000)
     ap.add_argument("--genomes", type=int, default=int(os.environ.get("TAXOR_BENCH_GENOMES", 1000)))
-    ap.add_argument("--genome-len", type=int, default=int(os.environ.get("TAXOR_BENCH_GENOME_LEN", 4_000_000)), help="mean genome length")
+    ap.add_argument("--genome-len", type=int, default=int(os.environ.get("TAXOR_BENCH_GENOME_LEN", 40_000_000)),
+                    help="mean genome length; 40 Mbp x 1,000 genomes gives the ~10 GB HIXF configs[1] names")
     ap.add_argument("--t-max", type=int, default=64)
     ap.add_argument("--read-error", type=float, default=0.05)
     ap.add_argument("--error-rate", type=float, default=0.10, help="taxor search --error-rate (see DESIGN.md workload)")
@@ -63,10 +64,33 @@ def genome_lengths(n, mean, seed=7):
     return np.maximum(x.astype(np.int64), 20_000)
 
 
-def make_genomes(args):
+def make_genomes(args, rank=0, barrier=None):
+    """Packed synthetic genomes, generated once (rank 0) into a /dev/shm file that every rank maps: at the default
+    size they are 10 GB, too much to hold once per rank."""
     from taxor_b200 import tools
     lens = genome_lengths(args.genomes, args.genome_len)
-    return [tools.genome(1000 + g, int(lens[g])) for g in range(args.genomes)], lens
+    nw = np.array([tools.packed_words(int(x)) for x in lens], dtype=np.uint64)
+    off = np.zeros(args.genomes + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(nw)
+    d = os.path.join(args.cache, f"genomes_g{args.genomes}_l{args.genome_len}")
+    path, done = os.path.join(d, "words.bin"), os.path.join(d, "DONE")
+    if rank == 0 and not os.path.exists(done):
+        os.makedirs(d, exist_ok=True)
+        mm = np.lib.format.open_memmap(path, mode="w+", dtype=np.uint64, shape=(int(off[-1]),))
+        T = tools.tlib()
+        from concurrent.futures import ThreadPoolExecutor
+
+        def gen(g):
+            T.txs_genome(1000 + g, int(lens[g]), mm.ctypes.data + 8 * int(off[g]))
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+            list(ex.map(gen, range(args.genomes)))
+        mm.flush()
+        del mm
+        open(done, "w").close()
+    if barrier is not None:
+        barrier()
+    mm = np.load(path, mmap_mode="r")
+    return [mm[int(off[g]):int(off[g + 1])] for g in range(args.genomes)], lens
 
 
 def index_cache_paths(args):
@@ -92,10 +116,11 @@ def build_index_arrays(args, genomes, lens, ctx):
         for i in range(len(part)):
             ub.append(h[int(o[i]):int(o[i + 1])])
     t1 = time.time()
-    hx = tools.BuiltHixf(ub, t_max=args.t_max, seed=1)
+    hx = tools.BuiltHixf(ub, t_max=args.t_max, seed=1, inplace=True)
+    del ub
     t2 = time.time()
     info = dict(hash_s=round(t1 - t0, 2), build_s=round(t2 - t1, 2), n_ixf=hx.n_ixf, fp_bytes=hx.fp_bytes,
-                n_hashes=int(sum(len(x) for x in ub)), reseeds=hx.reseeds)
+                n_hashes=int(hx.n_keys), reseeds=hx.reseeds)
     return hx, info
 
 
@@ -263,7 +288,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = capi.Context(local_rank)
-    genomes, lens = make_genomes(args)
+    genomes, lens = make_genomes(args, rank, dist.barrier if dist is not None else None)
 
     # ---- index: rank 0 builds (GPU hashing + CPU peeling), everybody loads it from /dev/shm ----
     d, done = index_cache_paths(args)

@@ -85,6 +85,8 @@ class Oracle:
             f.argtypes = [u8p, C.c_int64, C.c_int, C.c_int, C.c_int, u64p, C.c_int64]
         L.orc_kmer_hashes.restype = C.c_int64
         L.orc_kmer_hashes.argtypes = [u8p, C.c_int64, C.c_int, C.c_uint64, u64p, C.c_int64]
+        L.orc_minimiser_hashes.restype = C.c_int64
+        L.orc_minimiser_hashes.argtypes = [u8p, C.c_int64, C.c_int, C.c_int, C.c_uint64, u64p, C.c_int64]
         L.orc_threshold_init.restype = None
         L.orc_threshold_init.argtypes = [C.POINTER(_Thr), C.c_uint32, C.c_uint8, C.c_double, C.c_double, C.c_int, C.c_int]
         L.orc_threshold_get.restype = C.c_uint64
@@ -141,6 +143,10 @@ class Oracle:
     def kmer_hashes(self, codes, k, seed=None):
         seed = self.adjust_seed(k) if seed is None else seed
         return self._hash_call(self.lib.orc_kmer_hashes, codes, k, seed)
+
+    def minimiser_hashes(self, codes, k, w, seed=None):
+        seed = self.adjust_seed(k) if seed is None else seed
+        return self._hash_call(self.lib.orc_minimiser_hashes, codes, k, w, seed)
 
     # ---- thresholds
     def thresholder(self, window_size, kmer_size, percentage, error_rate, use_syncmer, fracminhash=False):

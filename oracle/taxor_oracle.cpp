@@ -203,6 +203,60 @@ extern "C" int64_t orc_kmer_hashes(const uint8_t *codes, int64_t len, int k, uin
     return n <= cap ? n : -n;
 }
 
+/* seq | seqan3::views::minimiser_hash(ungapped k, window_size w > k, seed) (taxor_search.cpp:210-212,242;
+ * build side compute_hashes.cpp:120-124).  UPSTREAM SeqAn3 3.3.0 semantics of views::minimiser over the
+ * per-position values min(fwd ^ seed, rc ^ seed) (fork unverified -> parity unpinned):
+ *   - W = w - k + 1 values per window; a range with fewer values than W is ONE window (the iterator
+ *     constructor clamps window_size to the range size); no values -> no output;
+ *   - first window: the RIGHTMOST minimum (min_element with std::less_equal) is reported;
+ *   - every shift: if the tracked minimiser was the value that left the window, the window is rescanned
+ *     (rightmost minimum again) and the result is reported EVEN IF ITS VALUE IS UNCHANGED; else a new value
+ *     STRICTLY smaller than the tracked one becomes the minimiser and is reported; an equal one is ignored.
+ * Output = the reported values in order, duplicates kept (taxor_search.cpp:242-255 pushes every one). */
+extern "C" int64_t orc_minimiser_hashes(const uint8_t *codes, int64_t len, int k, int w, uint64_t seed,
+                                        uint64_t *out, int64_t cap)
+{
+    const int64_t n = len >= k ? len - k + 1 : 0;
+    if (n == 0)
+        return 0;
+    std::vector<uint64_t> v((size_t)n);
+    if (orc_kmer_hashes(codes, len, k, seed, v.data(), n) != n)
+        return 0;
+    const int64_t W = std::min<int64_t>(std::max(w - k + 1, 1), n);
+    int64_t cnt = 0;
+    auto report = [&](uint64_t x)
+    {
+        if (cnt < cap)
+            out[cnt] = x;
+        ++cnt;
+    };
+    auto rightmost_min = [&](int64_t first)
+    {
+        int64_t pos = first;
+        for (int64_t j = first + 1; j < first + W; ++j)
+            if (v[(size_t)j] <= v[(size_t)pos])
+                pos = j;
+        return pos;
+    };
+    int64_t pos = rightmost_min(0);
+    report(v[(size_t)pos]);
+    for (int64_t first = 1; first + W <= n; ++first)
+    {
+        const int64_t arriving = first + W - 1;
+        if (pos < first)
+        {
+            pos = rightmost_min(first);
+            report(v[(size_t)pos]);
+        }
+        else if (v[(size_t)arriving] < v[(size_t)pos])
+        {
+            pos = arriving;
+            report(v[(size_t)pos]);
+        }
+    }
+    return cnt <= cap ? cnt : -cnt;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * thresholds  (src/hixf/search/)
  * ---------------------------------------------------------------------------------------------- */
@@ -485,7 +539,9 @@ extern "C" int orc_search_batch(const orc_hixf *h, const orc_search_params *p,
         }
         else                                                                       /* :240-256 */
         {
-            int64_t n = orc_kmer_hashes(seq, len, p->k, kseed, tmp.data(), windows + 1);
+            int64_t n = (int64_t)p->window_size > p->k
+                            ? orc_minimiser_hashes(seq, len, p->k, (int)p->window_size, kseed, tmp.data(), windows + 1)
+                            : orc_kmer_hashes(seq, len, p->k, kseed, tmp.data(), windows + 1);
             for (int64_t i = 0; i < n; ++i)
                 if (p->scaling <= 1 || orc_scaling_keep(tmp[i], p->scaling))
                     hashes.push_back(tmp[i]);

@@ -50,6 +50,11 @@ int64_t orc_syncmer_hashes_raw(const uint8_t *codes, int64_t len, int k, int s, 
 int64_t orc_kmer_hashes(const uint8_t *codes, int64_t len, int k, uint64_t seed,
                         uint64_t *out, int64_t cap);     /* src/main/taxor_search.cpp:210-212,240-256 */
 
+/* minimiser mode, window w > k: seqan3::views::minimiser over the values above, W = w-k+1 values per window,
+ * rightmost minimum, re-reported whenever the tracked minimiser leaves the window (upstream SeqAn3 3.3.0). */
+int64_t orc_minimiser_hashes(const uint8_t *codes, int64_t len, int k, int w, uint64_t seed,
+                             uint64_t *out, int64_t cap);
+
 /* ---------- thresholds ---------- */
 enum { ORC_THR_FRACMINHASH = 0, ORC_THR_PERCENTAGE = 1, ORC_THR_KMER = 2, ORC_THR_SYNCMER = 3 };
 typedef struct {

@@ -89,14 +89,20 @@ def simulate_reads(genomes, genome_len, read_len, err: float, seed: int, out_wor
 class BuiltHixf:
     """An HIXF built by the CPU tooling; exposes the plain arrays every consumer takes."""
 
-    def __init__(self, ub_hashes, t_max: int = 64, seed: int = 1, threads: int = 0) -> None:
-        # sorted distinct key sets (in place on private copies, parallel over user bins)
-        self._ub = [np.array(h, dtype=np.uint64, copy=True) for h in ub_hashes]
+    def __init__(self, ub_hashes, t_max: int = 64, seed: int = 1, threads: int = 0, inplace: bool = False) -> None:
+        # sorted distinct key sets (in place on private copies -- or on the caller's arrays with inplace=True, which
+        # halves the footprint of a multi-GB build -- parallel over user bins)
+        if inplace:
+            self._ub = [h if (h.dtype == np.uint64 and h.flags.c_contiguous and h.flags.writeable) else np.array(h, dtype=np.uint64)
+                        for h in ub_hashes]
+        else:
+            self._ub = [np.array(h, dtype=np.uint64, copy=True) for h in ub_hashes]
         n = len(self._ub)
         ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in self._ub])
         cnt = np.array([len(a) for a in self._ub], dtype=np.uint64)
         tlib().txs_sort_unique_many(ptrs, cnt.ctypes.data, n, threads)
         self._ub = [a[: int(c)] for a, c in zip(self._ub, cnt)]
+        self.n_keys = int(cnt.sum())
         self._h = tlib().txs_hixf_build(ptrs, cnt.ctypes.data, n, t_max, seed, threads)
         if not self._h:
             raise RuntimeError("txs_hixf_build failed")
