@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--error-rate", type=float, default=0.10, help="taxor search --error-rate (see DESIGN.md workload)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("TAXOR_BENCH_BATCH_READS", 0)),
+                    help="reads per internal batch (0: library default)")
     ap.add_argument("--cache", default=os.environ.get("TAXOR_BENCH_CACHE", "/dev/shm/taxor_b200_bench"))
     return ap.parse_args()
 
@@ -345,7 +347,8 @@ def main():
         torch.cuda.synchronize()
 
     # (1) device-resident: kernels only.  One pipeline slot so that the per-stage CUDA events are not overlapped
-    ctx.configure(n_slots=int(os.environ.get("TAXOR_BENCH_RESIDENT_SLOTS", 1)))
+    batch_kw = dict(max_batch_reads=args.batch_reads, max_batch_bases=int(args.batch_reads * args.read_len * 1.1)) if args.batch_reads else {}
+    ctx.configure(n_slots=int(os.environ.get("TAXOR_BENCH_RESIDENT_SLOTS", 1)), **batch_kw)
     h = ctx.upload_reads(reads)
     for _ in range(args.warmup):
         ctx.search_resident(h, fetch=False)
@@ -374,7 +377,7 @@ def main():
     ctx.free_reads(h)
 
     # (2) end to end from pinned host buffers through txr_search (3 pipeline slots)
-    ctx.configure(n_slots=3)
+    ctx.configure(n_slots=3, **batch_kw)
     for _ in range(max(1, min(args.warmup, 2))):
         ctx.search_raw(pin.ptr, off_pin.ptr, len_pin.ptr, n_reads)
     barrier()

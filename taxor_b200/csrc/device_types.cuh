@@ -7,6 +7,7 @@ namespace txr
 {
 constexpr int kTileWindows = 1024;         // windows per warp tile in the hash kernels (32 per lane)
 constexpr uint64_t kEmptyKey = ~0ULL;      // sentinel of the dedup tables
+constexpr int kMaxMinimiserValues = 96;    // taxor build --window-size <= 96 (taxor_build.cpp:78-80)
 constexpr uint32_t kSmallRowBytes = 512;   // IXFs with tbins <= this are probed by one warp per (read, IXF)
 
 // ---- kernel #1 (hashing) ----
@@ -23,6 +24,7 @@ struct HashArgs
     uint32_t *overflow;        // set to 1 when a read needed more than its capacity
     uint64_t kmer_seed;        // k-mer mode: adjust_seed(k)
     int k, s, t;               // generic kernel only
+    int window;                // minimiser mode: k-mer values per window, window_size - k + 1 (2..kMaxMinimiserValues)
 };
 
 struct DedupArgs
@@ -65,6 +67,7 @@ struct QueryArgs
     const uint32_t *hash_count;
     const uint64_t *thr_lut;       // threshold by hash_count
     uint32_t lut_len;
+    const uint64_t *thr_read;      // per-read thresholds (FracMinHash model: depends on the read length too); nullptr: use the LUT
 
     const uint2 *items;            // (read, ixf) work items of this level; nullptr: item i = (i, 0)
     const uint32_t *n_items_ptr;   // device counter written by the previous level
@@ -86,5 +89,22 @@ struct QueryArgs
 
     unsigned long long *stat_bytes; // algorithmic bytes: sum H*3*tbins + 8*H
     unsigned long long *stat_items;
+};
+
+// ---- kernel #2, root level of a batch, slot-partitioned (query_kernels.cu: "partitioned root") ----
+struct RootPartArgs
+{
+    IxfDev root;
+    const uint64_t *hashes;        // per-read lists (as in QueryArgs)
+    const uint64_t *hash_off;
+    const uint32_t *hash_count;
+    uint32_t n_reads;
+    uint32_t log2_parts;           // partitions = 1 << log2_parts, by the top bits of the segment-0 slot
+    uint32_t *hist;                // [parts + 1] element counts per partition, then their sum
+    uint32_t *cursor;              // [parts] write cursors (start at the exclusive scan of hist)
+    uint64_t *part_hash;           // elements grouped by partition ...
+    uint32_t *part_read;           // ... and the read each one belongs to
+    uint32_t *counts;              // [n_reads * root.tbins / 2] 16-bit counters packed in pairs
+    uint32_t *work;                // work-stealing cursors: [0] hist, [1] scatter, [2] probe, [3] scan
 };
 } // namespace txr

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -24,6 +25,7 @@ namespace txr
 {
 cudaError_t launch_syncmer(const HashArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_kmer(const HashArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_minimiser(const HashArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_dedup_warp(const DedupArgs &a, int sm_count, uint32_t *work_counter, uint32_t *deferred, uint32_t *n_deferred,
                               cudaStream_t st);
 cudaError_t launch_dedup_deferred(const DedupArgs &a, int sm_count, const uint32_t *n_deferred, cudaStream_t st);
@@ -32,6 +34,9 @@ cudaError_t launch_dedup_global(const DedupArgs &a, cudaStream_t st);
 cudaError_t launch_filter(const DedupArgs &a, cudaStream_t st);
 cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_query_large(const QueryArgs &a, int sm_count, uint32_t max_tbins, cudaStream_t st);
+cudaError_t launch_sort_items(const uint2 *items, const uint32_t *n_ptr, uint32_t cap, uint32_t *hist, uint32_t n_ixf, uint2 *out,
+                              int sm_count, cudaStream_t st);
+cudaError_t launch_root_partitioned(const QueryArgs &q, const RootPartArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_bulk_count(const IxfDev &d, const uint64_t *values, uint32_t n, uint32_t *counts, cudaStream_t st);
 } // namespace txr
 
@@ -195,10 +200,13 @@ struct Slot
     DevBuf words;
     BatchDev meta;
     DevBuf hashes, n_raw, hash_count, gtable, deferred;
-    DevBuf queues; // per level >= 1: small[cap], large[cap]
+    DevBuf queues; // per level >= 1: small[cap], large[cap]; then two more arrays: the current level grouped by IXF
+    DevBuf ixf_hist;
+    DevBuf part_hash, part_read, part_counts, part_ctl; // partitioned root level (query_kernels.cu)
     DevBuf hit_read, hit_ub, hit_cnt;
     DevBuf counters;
-    PinBuf h_meta, h_counters, h_hash_count, h_hits;
+    DevBuf thr;    // per-read thresholds (FracMinHash model only)
+    PinBuf h_meta, h_counters, h_hash_count, h_hits, h_thr;
     uint32_t queue_cap{0}, hit_cap{0};
     // state of the batch in flight
     const BatchMeta *bm{nullptr};
@@ -246,6 +254,9 @@ struct txr_ctx
     txr_params params{};
     Thresholder thresholder;
     uint64_t kmer_seed{0};
+    bool sort_items{true};     // group level queues by IXF (TXR_SORT_ITEMS=0 disables, for A/B measurements)
+    int root_partition{1};     // group the root level's probes by segment-0 slot: 1 auto, 0 off, 2 always (TXR_ROOT_PARTITION)
+    bool per_read_thr{false};  // FracMinHash model: the threshold depends on hash_count AND the read length
     std::vector<uint64_t> lut; // threshold by hash_count (host)
     DevBuf d_lut;
     uint64_t d_lut_len{0};
@@ -408,6 +419,27 @@ static int upload_batch_meta(const BatchMeta &m, BatchDev &d, cudaStream_t st, u
     return TXR_OK;
 }
 
+// The partitioned root level pays when the root's segment does not fit L2 anyway and the 16-bit counters and 32-bit
+// element indices are wide enough for the batch.  Returns log2(partitions), 0 = use the item-per-warp kernel.
+constexpr uint32_t kPartCtlWords = 4 + 1025 + 1024;
+static uint32_t root_partition_bits(const txr_ctx *c, const BatchMeta &m)
+{
+    if (!c->root_partition || !c->index.loaded)
+        return 0;
+    const IxfDev &root = c->index.ixf[0];
+    const uint64_t seg_bytes = (uint64_t)root.seg_len * root.tbins;
+    if (root.tbins > kSmallRowBytes || m.max_cap > 65535 || m.total_cap >= (1ull << 32))
+        return 0;
+    if (c->root_partition == 2)
+        return 3; // forced (tests): 8 partitions whatever the size
+    if (seg_bytes < (48ull << 20))
+        return 0;
+    uint32_t bits = 1;
+    while (bits < 10 && (seg_bytes >> bits) > (16ull << 20))
+        ++bits;
+    return bits;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // launching one batch on a slot
 // ---------------------------------------------------------------------------------------------------------
@@ -421,6 +453,11 @@ static int slot_reserve(txr_ctx *c, Slot &s, const BatchMeta &m)
     TRY(s.counters.ensure(C_TOTAL * 4));
     TRY(s.h_counters.ensure(C_TOTAL * 4));
     TRY(s.h_hash_count.ensure((size_t)n * 4));
+    if (c->per_read_thr)
+    {
+        TRY(s.thr.ensure((size_t)n * 8));
+        TRY(s.h_thr.ensure((size_t)n * 8));
+    }
     if (!m.ids_global.empty())
         TRY(s.gtable.ensure(m.gtable_off.back() * 8));
     if (s.queue_cap < 2 * n + 1024)
@@ -428,7 +465,15 @@ static int slot_reserve(txr_ctx *c, Slot &s, const BatchMeta &m)
     if (s.hit_cap < 4 * n + 1024)
         s.hit_cap = 4 * n + 1024;
     const uint32_t levels = std::max<uint32_t>(c->index.depth, 1);
-    TRY(s.queues.ensure((size_t)levels * 2 * s.queue_cap * sizeof(uint2)));
+    TRY(s.queues.ensure((size_t)(levels + 1) * 2 * s.queue_cap * sizeof(uint2)));
+    TRY(s.ixf_hist.ensure((c->index.ixf.size() + 1) * 4));
+    if (root_partition_bits(c, m))
+    {
+        TRY(s.part_hash.ensure(std::max<uint64_t>(m.total_cap, 1) * 8));
+        TRY(s.part_read.ensure(std::max<uint64_t>(m.total_cap, 1) * 4));
+        TRY(s.part_counts.ensure((size_t)n * c->index.ixf[0].tbins * 2));
+        TRY(s.part_ctl.ensure(kPartCtlWords * 4));
+    }
     TRY(s.hit_read.ensure((size_t)s.hit_cap * 4));
     TRY(s.hit_ub.ensure((size_t)s.hit_cap * 4));
     TRY(s.hit_cnt.ensure((size_t)s.hit_cap * 4));
@@ -454,8 +499,11 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     h.k = c->params.kmer_size;
     h.s = c->params.syncmer_size;
     h.t = c->params.t_syncmer;
+    h.window = (int)c->params.window_size - (int)c->params.kmer_size + 1;
     if (c->params.use_syncmer)
         CU(launch_syncmer(h, c->sm_count, cs));
+    else if (h.window > 1)
+        CU(launch_minimiser(h, c->sm_count, cs));
     else
         CU(launch_kmer(h, c->sm_count, cs));
     c->timing.hash_launches += 1;
@@ -528,6 +576,7 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
     q.hash_count = s.hash_count.as<uint32_t>();
     q.thr_lut = c->d_lut.as<uint64_t>();
     q.lut_len = (uint32_t)std::min<uint64_t>(c->d_lut_len, 0xffffffffu);
+    q.thr_read = c->per_read_thr ? s.thr.as<uint64_t>() : nullptr;
     q.hit_read = s.hit_read.as<uint32_t>();
     q.hit_ub = s.hit_ub.as<int32_t>();
     q.hit_cnt = s.hit_cnt.as<uint32_t>();
@@ -556,32 +605,86 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
             q.n_items_direct = m.n_reads;
             q.items_cap = m.n_reads;
             q.cursor = lc + 2;
-            if (ix.ixf[0].tbins <= kSmallRowBytes)
+            if (const uint32_t bits = root_partition_bits(c, m))
+            {
+                RootPartArgs rp{};
+                rp.root = ix.ixf[0];
+                rp.hashes = q.hashes;
+                rp.hash_off = q.hash_off;
+                rp.hash_count = q.hash_count;
+                rp.n_reads = m.n_reads;
+                rp.log2_parts = bits;
+                uint32_t *ctl = s.part_ctl.as<uint32_t>();
+                rp.work = ctl;
+                rp.hist = ctl + 4;
+                rp.cursor = ctl + 4 + 1025;
+                rp.part_hash = s.part_hash.as<uint64_t>();
+                rp.part_read = s.part_read.as<uint32_t>();
+                rp.counts = s.part_counts.as<uint32_t>();
+                CU(cudaMemsetAsync(ctl, 0, kPartCtlWords * 4, cs));
+                CU(cudaMemsetAsync(rp.counts, 0, (size_t)m.n_reads * ix.ixf[0].tbins * 2, cs));
+                CU(launch_root_partitioned(q, rp, c->sm_count, cs));
+                c->timing.query_launches += 5;
+            }
+            else if (ix.ixf[0].tbins <= kSmallRowBytes)
+            {
                 CU(launch_query_small(q, c->sm_count, cs));
+                c->timing.query_launches += 1;
+            }
             else
+            {
                 CU(launch_query_large(q, c->sm_count, ix.max_tbins, cs));
-            c->timing.query_launches += 1;
+                c->timing.query_launches += 1;
+            }
         }
         else
         {
             q.items_cap = s.queue_cap;
             q.n_items_direct = 0;
-            q.items = queues + (size_t)(2 * lv) * s.queue_cap;
+            // group the level's items by IXF first (L2 reuse of the child IXFs, see query_kernels.cu)
+            uint2 *sorted = queues + (size_t)(2 * levels) * s.queue_cap;
+            const uint2 *raw = queues + (size_t)(2 * lv) * s.queue_cap;
+            if (c->sort_items)
+                CU(launch_sort_items(raw, lc + 0, s.queue_cap, s.ixf_hist.as<uint32_t>(), (uint32_t)ix.ixf.size(), sorted, c->sm_count, cs));
+            q.items = c->sort_items ? sorted : raw;
             q.n_items_ptr = lc + 0;
             q.cursor = lc + 2;
             CU(launch_query_small(q, c->sm_count, cs));
-            c->timing.query_launches += 1;
+            c->timing.query_launches += c->sort_items ? 4 : 1;
             if (ix.any_large)
             {
-                q.items = queues + (size_t)(2 * lv + 1) * s.queue_cap;
+                sorted += s.queue_cap;
+                raw = queues + (size_t)(2 * lv + 1) * s.queue_cap;
+                if (c->sort_items)
+                    CU(launch_sort_items(raw, lc + 1, s.queue_cap, s.ixf_hist.as<uint32_t>(), (uint32_t)ix.ixf.size(), sorted, c->sm_count, cs));
+                q.items = c->sort_items ? sorted : raw;
                 q.n_items_ptr = lc + 1;
                 q.cursor = lc + 3;
                 CU(launch_query_large(q, c->sm_count, ix.max_tbins, cs));
-                c->timing.query_launches += 1;
+                c->timing.query_launches += c->sort_items ? 4 : 1;
             }
         }
     }
     CU(cudaEventRecord(s.ev[4], cs));
+    return TXR_OK;
+}
+
+// hixf::threshold::threshold::get for every read of the batch (taxor_search.cpp:263): the scaling factor
+// hash_count / (L - k + 1) of the FracMinHash model makes the threshold a function of the read, not of hash_count
+// alone, and its double/libm arithmetic stays on the host -- so this stage waits for the hash counts, evaluates
+// the model per read and ships the integers back.  Only minimiser indexes (window_size > k) pay this round trip.
+static int per_read_thresholds(txr_ctx *c, Slot &s, const BatchMeta &m, cudaStream_t cs)
+{
+    const uint32_t n = m.n_reads;
+    CU(cudaMemcpyAsync(s.h_hash_count.p, s.hash_count.p, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
+    CU(cudaStreamSynchronize(cs));
+    const uint32_t *hc = s.h_hash_count.as<uint32_t>();
+    uint64_t *thr = s.h_thr.as<uint64_t>();
+    const double k = (double)c->params.kmer_size;
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (long r = 0; r < (long)n; ++r)
+        thr[r] = c->thresholder.get(hc[r], (double)hc[r] / ((double)m.len[r] - k + 1.0));
+    CU(cudaMemcpyAsync(s.thr.p, thr, (size_t)n * 8, cudaMemcpyHostToDevice, cs));
     return TXR_OK;
 }
 
@@ -611,6 +714,8 @@ static int submit_batch(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev 
     CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, cs));
     CU(cudaEventRecord(s.ev[6], cs));
     TRY(launch_hash_stage(c, s, m, *bd, d_words, true, cs));
+    if (run_query && c->per_read_thr)
+        TRY(per_read_thresholds(c, s, m, cs));
     if (run_query)
         TRY(launch_query_stage(c, s, m, *bd, cs));
     else
@@ -728,7 +833,10 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
                 R.keep[at] = !(static_cast<double>(h_cnt[o[i]]) < static_cast<double>(max_count) * 0.8);
             }
             R.hash_count.push_back(h_count[r]);
-            R.threshold.push_back(h_count[r] < c->lut.size() ? c->lut[h_count[r]] : c->thresholder.get(h_count[r], 1.0));
+            if (c->per_read_thr)
+                R.threshold.push_back(s.h_thr.as<uint64_t>()[r]);
+            else
+                R.threshold.push_back(h_count[r] < c->lut.size() ? c->lut[h_count[r]] : c->thresholder.get(h_count[r], 1.0));
             R.hit_begin.push_back(base_hits + begin[r]);
             n_hashes += h_count[r];
             hash_bytes += (m.len[r] + 3) / 4;
@@ -830,6 +938,10 @@ int txr_ctx_create(int device, txr_ctx **out)
     auto c = std::make_unique<txr_ctx>();
     c->device = device;
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (const char *e = getenv("TXR_SORT_ITEMS"))
+        c->sort_items = atoi(e) != 0;
+    if (const char *e = getenv("TXR_ROOT_PARTITION"))
+        c->root_partition = atoi(e);
     *out = c.release();
     return TXR_OK;
 }
@@ -844,9 +956,10 @@ void txr_ctx_destroy(txr_ctx *c)
     {
         for (DevBuf *b : {&s->words, &s->meta.word_off, &s->meta.len, &s->meta.out_off, &s->meta.ids_small, &s->meta.ids_medium,
                           &s->meta.ids_global, &s->meta.gtable_off, &s->hashes, &s->n_raw, &s->hash_count, &s->gtable, &s->deferred, &s->queues,
-                          &s->hit_read, &s->hit_ub, &s->hit_cnt, &s->counters})
+                          &s->hit_read, &s->hit_ub, &s->hit_cnt, &s->counters, &s->thr, &s->ixf_hist, &s->part_hash,
+                          &s->part_read, &s->part_counts, &s->part_ctl})
             b->release();
-        for (PinBuf *b : {&s->h_meta, &s->h_counters, &s->h_hash_count, &s->h_hits})
+        for (PinBuf *b : {&s->h_meta, &s->h_counters, &s->h_hash_count, &s->h_hits, &s->h_thr})
             b->release();
         for (auto &e : s->ev)
             cudaEventDestroy(e);
@@ -1039,14 +1152,18 @@ int txr_params_set(txr_ctx *c, const txr_params *p)
         if (p->syncmer_size < 1 || p->syncmer_size >= p->kmer_size || p->t_syncmer < 1 || p->t_syncmer > wn)
             return set_error(TXR_ERR_ARG, "syncmer parameters k=%d s=%d t=%d out of range", p->kmer_size, p->syncmer_size, p->t_syncmer);
     }
-    else if (p->window_size != p->kmer_size)
-        return set_error(TXR_ERR_UNSUPPORTED, "k-mer mode requires window_size == kmer_size (minimiser windows are not on the GPU path)");
+    else if (p->window_size < p->kmer_size)
+        return set_error(TXR_ERR_ARG, "window_size %u smaller than kmer_size %d", p->window_size, p->kmer_size);
+    else if (p->window_size - p->kmer_size + 1 > (uint32_t)kMaxMinimiserValues)
+        return set_error(TXR_ERR_UNSUPPORTED, "minimiser windows of more than %d k-mers are not supported (taxor build limits --window-size to 96)",
+                         kMaxMinimiserValues);
     CU(cudaSetDevice(c->device));
     c->params = *p;
     if (c->params.scaling == 0)
         c->params.scaling = 1;
     c->thresholder = Thresholder(p->window_size, p->kmer_size, p->percentage, p->error_rate, p->use_syncmer != 0);
     c->kmer_seed = 0x8F3F73B5CF1C9ADEULL >> (64u - 2u * p->kmer_size); // src/hixf/build/adjust_seed.hpp:40-44
+    c->per_read_thr = c->thresholder.kind() == ThresholdKind::fracminhash;
     c->lut.clear();
     c->d_lut_len = 0;
     c->have_params = true;

@@ -586,6 +586,180 @@ __global__ void __launch_bounds__(256) kmer_kernel(HashArgs a)
 }
 
 // -----------------------------------------------------------------------------------------------------------
+// minimiser kernel (window_size > k): seq | seqan3::views::minimiser_hash(ungapped k, window_size, seed)
+// (taxor_search.cpp:210-212,242).  Upstream SeqAn3 3.3.0 semantics of views::minimiser over the canonical k-mer
+// values v[q] = min(fwd ^ seed, rc ^ seed): W = window_size - k + 1 values per window (clamped to the number of
+// values of a short read); the tracked minimiser is the RIGHTMOST minimum of the first window; on every shift it is
+// re-chosen (rightmost minimum of the new window) and reported again when it was the value that left, replaced and
+// reported when the arriving value is STRICTLY smaller, kept silently otherwise.  Duplicates are kept.
+//
+// One warp per read, tiles of kTileWindows windows.  The values a tile needs are staged in shared memory once
+// (coalesced extraction from the packed words); lane l then runs the state machine over its 32 consecutive windows.
+// The state a lane starts from is history dependent only where the preceding window holds its minimum more than
+// once (repeats, palindromic k-mer pairs): a window with a unique minimum pins the state whatever came before.  Lane 0
+// starts from the state carried across tiles; a lane whose preceding window is tied waits for its left neighbour
+// (sequential hand-over, homopolymers and tandem repeats only).  Reported positions are buffered per lane and written
+// in window order after a warp prefix sum.
+// -----------------------------------------------------------------------------------------------------------
+constexpr int kMinWarps = 4;
+constexpr int kMinVals = kTileWindows + kMaxMinimiserValues - 1;       // values a tile can need
+constexpr int kMinValsPadded = kMinVals + kMinVals / 32 + 1;           // one pad slot per 32: lanes 32 windows apart hit different banks
+namespace
+{
+__device__ __forceinline__ int mpad(int e) { return e + (e >> 5); }
+
+struct MinState
+{
+    int pos;       // tile-relative index of the tracked minimiser (may be -1: it just left the window)
+};
+
+// rightmost / leftmost minimum of the W values starting at tile-relative index `first`
+__device__ __forceinline__ void window_extrema(const uint64_t *sv, int first, int W, int &leftmost, int &rightmost)
+{
+    uint64_t best = sv[mpad(first)];
+    leftmost = rightmost = first;
+    for (int j = first + 1; j < first + W; ++j)
+    {
+        const uint64_t x = sv[mpad(j)];
+        if (x < best)
+        {
+            best = x;
+            leftmost = rightmost = j;
+        }
+        else if (x == best)
+            rightmost = j;
+    }
+}
+
+// runs windows [a, b) (tile-relative) from state `pos`; records the reported positions; returns the final state
+__device__ __forceinline__ int minimiser_run(const uint64_t *sv, int a, int b, int W, int pos, uint16_t *ev, int &n_ev)
+{
+    for (int i = a; i < b; ++i)
+    {
+        if (pos < i)
+        {
+            int lm, rm;
+            window_extrema(sv, i, W, lm, rm);
+            pos = rm;
+            ev[n_ev++] = (uint16_t)pos;
+        }
+        else
+        {
+            const int arriving = i + W - 1;
+            if (sv[mpad(arriving)] < sv[mpad(pos)])
+            {
+                pos = arriving;
+                ev[n_ev++] = (uint16_t)pos;
+            }
+        }
+    }
+    return pos;
+}
+} // namespace
+
+__global__ void __launch_bounds__(32 * kMinWarps) minimiser_kernel(HashArgs a)
+{
+    __shared__ uint64_t s_val[kMinWarps][kMinValsPadded];
+    __shared__ uint16_t s_ev[kMinWarps][32][34]; // 34: lanes land on different banks
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint64_t *sv = s_val[wib];
+    uint16_t *ev = s_ev[wib][lane];
+    const int K = a.k;
+    while (true)
+    {
+        uint32_t r = 0;
+        if (lane == 0)
+            r = atomicAdd(a.work_counter, 1u);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= a.n_reads)
+            break;
+        const uint32_t L = a.len[r];
+        const uint64_t n_val = L >= (uint32_t)K ? (uint64_t)L - K + 1 : 0;
+        const uint64_t *__restrict__ w = a.words + a.word_off[r];
+        uint64_t *__restrict__ out = a.out + a.out_off[r];
+        const uint64_t cap = a.out_off[r + 1] - a.out_off[r];
+        const int W = (int)min((uint64_t)a.window, n_val);           // clamped window (iterator constructor)
+        const uint64_t n_win = n_val ? n_val - W + 1 : 0;
+        uint64_t cursor = 0;
+        int carried = 0;                                              // tracked position relative to the NEXT tile
+        for (uint64_t tile = 0; tile < n_win; tile += kTileWindows)
+        {
+            const int tw = (int)min((uint64_t)kTileWindows, n_win - tile);
+            const int nv = tw + W - 1;
+            __syncwarp();
+            for (int e = lane; e < nv; e += 32)
+            {
+                const uint64_t fw = mer_at(w, tile + e, K);
+                const uint64_t rv = revcomp_mer(fw, K);
+                const uint64_t fs = fw ^ a.kmer_seed, rs = rv ^ a.kmer_seed;
+                sv[mpad(e)] = fs < rs ? fs : rs;
+            }
+            __syncwarp();
+            const int wa = lane * 32, wb = min(wa + 32, tw);
+            const bool active = wa < tw;
+            int n_ev = 0, pos = 0;
+            bool resolved = true;
+            if (active)
+            {
+                int start = wa;
+                if (tile == 0 && lane == 0)
+                {
+                    int lm, rm;
+                    window_extrema(sv, 0, W, lm, rm);                 // first window: rightmost minimum, reported
+                    pos = rm;
+                    ev[n_ev++] = (uint16_t)pos;
+                    start = 1;
+                }
+                else if (lane == 0)
+                    pos = carried;
+                else
+                {
+                    int lm, rm;
+                    window_extrema(sv, wa - 1, W, lm, rm);
+                    pos = rm;
+                    resolved = lm == rm;                              // unique minimum: the state is that position
+                }
+                if (resolved)
+                    pos = minimiser_run(sv, start, wb, W, pos, ev, n_ev);
+            }
+            // sequential hand-over for lanes whose preceding window is tied (ascending, so the left neighbour is done)
+            uint32_t pending = __ballot_sync(0xffffffffu, active && !resolved);
+            while (pending)
+            {
+                const int l = __ffs(pending) - 1;
+                const int from_left = __shfl_sync(0xffffffffu, pos, l - 1);
+                if (lane == l)
+                    pos = minimiser_run(sv, wa, wb, W, from_left, ev, n_ev);
+                pending &= pending - 1;
+            }
+            const int last_lane = (tw - 1) >> 5;
+            carried = __shfl_sync(0xffffffffu, pos, last_lane) - tw;  // may become -1: left the window, rescan next
+            // ordered output
+            int incl = n_ev;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d)
+                    incl += up;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint64_t base = cursor + (uint64_t)(incl - n_ev);
+            for (int e = 0; e < n_ev; ++e)
+                if (base + e < cap)
+                    out[base + e] = sv[mpad(ev[e])];
+            cursor += (uint64_t)total;
+        }
+        if (lane == 0)
+        {
+            a.n_out[r] = (uint32_t)min(cursor, cap);
+            if (cursor > cap)
+                *a.overflow = 1u;
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------------
 // per-read distinct set + FracMin scaling filter
 // -----------------------------------------------------------------------------------------------------------
 namespace
@@ -911,6 +1085,12 @@ cudaError_t launch_syncmer_generic(const HashArgs &a, cudaStream_t st)
 cudaError_t launch_kmer(const HashArgs &a, int sm_count, cudaStream_t st)
 {
     kmer_kernel<<<sm_count * 4, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_minimiser(const HashArgs &a, int sm_count, cudaStream_t st)
+{
+    minimiser_kernel<<<sm_count * 4, 32 * kMinWarps, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -21,6 +21,9 @@
 
 namespace txr
 {
+constexpr int kQueryWarps = 4;
+constexpr int kQueryUnroll = 2;
+
 namespace
 {
 __device__ __forceinline__ uint4 ldg_row16(const uint8_t *p)
@@ -216,9 +219,6 @@ __device__ __forceinline__ void scan_bins(const QueryArgs &a, const IxfDev &d, u
 }
 } // namespace
 
-constexpr int kQueryWarps = 4;
-constexpr int kQueryUnroll = 2;
-
 // ---- IXFs with tbins <= 512: one warp per (read, IXF) ----
 __global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(QueryArgs a)
 {
@@ -248,13 +248,255 @@ __global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(Query
         const IxfDev d = a.ixf[x];
         const uint32_t H = a.hash_count[read];
         const uint64_t *hp = a.hashes + a.hash_off[read];
-        const uint64_t thr = H < a.lut_len ? a.thr_lut[H] : ~0ULL;
+        const uint64_t thr = a.thr_read ? a.thr_read[read] : (H < a.lut_len ? a.thr_lut[H] : ~0ULL);
         probe_chunk<kQueryUnroll>(d, hp, H, 0u, d.tbins >> 4, cnt, lane);
         __syncwarp();
         scan_bins(a, d, read, thr, cnt, (uint32_t)lane, 32u);
         __syncwarp();
         for (uint32_t i = lane; i < d.tbins; i += 32)
             cnt[i] = 0;
+        __syncwarp();
+        bytes += (unsigned long long)H * 3ull * d.tbins + 8ull * H;
+        ++items;
+    }
+    if (lane == 0 && items)
+    {
+        atomicAdd(a.stat_bytes, bytes);
+        atomicAdd(a.stat_items, items);
+    }
+}
+
+// ---- partitioned root: the first level of a batch, probes grouped by their segment-0 slot ----
+// Every read probes the root IXF, which is GBs for a 1,000-genome index: three random rows per hash, each a whole
+// 128-byte DRAM line on B200 whatever the row size (profiles/r1_gather_bench3_ncu.txt) -- the kernel above already
+// runs at that random-line ceiling.  The slot in segment 0 is a monotone function of the low hash word, so grouping
+// ALL hashes of a batch by its top bits makes the segment-0 rows of one group a contiguous block of a few MB that
+// stays in L2 while the group is processed: one of the three DRAM lines per probe disappears (microbenchmark:
+// 12.4 -> 17.3 G probes/s, profiles/r1_gather_bench2.json).  The price is one streaming pass over the hashes (8 B
+// read, 12 B written, 12 B read per hash against 384 B of line traffic per probe) and per-(read, bin) counters in
+// global memory (16 bit, L2 resident, touched only on a match) instead of shared memory.
+//   hist -> scatter (counting sort by partition, CTA-aggregated) -> probe (partition-major chunks) -> scan (per read)
+constexpr uint32_t kPartReadsPerUnit = 16;  // reads a CTA groups at a time (about 15k hashes)
+constexpr uint32_t kPartMaxLog2 = 10;
+constexpr uint32_t kProbeChunk = 256;       // elements per work unit of the probe kernel: ~1.2 M elements in flight on 148 SMs
+
+__device__ __forceinline__ uint32_t root_partition_of(const IxfDev &d, uint64_t key, uint32_t log2_parts)
+{
+    // ixf_slots: p0 = ((uint32)h * seg_len) >> 32 is monotone in (uint32)h, so its top bits select a slot range
+    return log2_parts ? (uint32_t)ixf_mix(key, d.seed) >> (32u - log2_parts) : 0u;
+}
+
+__global__ void __launch_bounds__(256) root_part_hist_kernel(RootPartArgs a)
+{
+    __shared__ uint32_t s_hist[1u << kPartMaxLog2];
+    __shared__ uint32_t s_unit;
+    const uint32_t parts = 1u << a.log2_parts;
+    for (uint32_t i = threadIdx.x; i < parts; i += blockDim.x)
+        s_hist[i] = 0;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t n_units = (a.n_reads + kPartReadsPerUnit - 1) / kPartReadsPerUnit;
+    while (true)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_unit = atomicAdd(&a.work[0], 1u);
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= n_units)
+            break;
+        for (uint32_t r = u * kPartReadsPerUnit + wib; r < min(a.n_reads, (u + 1) * kPartReadsPerUnit); r += nw)
+        {
+            const uint32_t H = a.hash_count[r];
+            const uint64_t *hp = a.hashes + a.hash_off[r];
+            for (uint32_t i = lane; i < H; i += 32)
+                atomicAdd(&s_hist[root_partition_of(a.root, hp[i], a.log2_parts)], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < parts; i += blockDim.x)
+        if (s_hist[i])
+            atomicAdd(&a.hist[i], s_hist[i]);
+}
+
+// one CTA: cursor = exclusive scan of hist, hist[parts] = total
+__global__ void __launch_bounds__(1024) root_part_scan_kernel(RootPartArgs a)
+{
+    __shared__ uint32_t s_warp[32];
+    const uint32_t parts = 1u << a.log2_parts; // <= 1024
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t v = threadIdx.x < parts ? a.hist[threadIdx.x] : 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += up;
+    }
+    if (lane == 31)
+        s_warp[wib] = incl;
+    __syncthreads();
+    if (wib == 0)
+    {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d)
+                w += up;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t before = wib ? s_warp[wib - 1] : 0;
+    if (threadIdx.x < parts)
+        a.cursor[threadIdx.x] = before + incl - v;
+    if (threadIdx.x == 1023)
+        a.hist[parts] = before + incl;
+}
+
+__global__ void __launch_bounds__(256) root_part_scatter_kernel(RootPartArgs a)
+{
+    __shared__ uint32_t s_cnt[1u << kPartMaxLog2];  // elements of this unit per partition, then the local cursor
+    __shared__ uint32_t s_base[1u << kPartMaxLog2]; // reserved global position per partition
+    __shared__ uint32_t s_unit;
+    const uint32_t parts = 1u << a.log2_parts;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t n_units = (a.n_reads + kPartReadsPerUnit - 1) / kPartReadsPerUnit;
+    while (true)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_unit = atomicAdd(&a.work[1], 1u);
+        for (uint32_t i = threadIdx.x; i < parts; i += blockDim.x)
+            s_cnt[i] = 0;
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= n_units)
+            break;
+        const uint32_t r_end = min(a.n_reads, (u + 1) * kPartReadsPerUnit);
+        for (uint32_t r = u * kPartReadsPerUnit + wib; r < r_end; r += nw)
+        {
+            const uint32_t H = a.hash_count[r];
+            const uint64_t *hp = a.hashes + a.hash_off[r];
+            for (uint32_t i = lane; i < H; i += 32)
+                atomicAdd(&s_cnt[root_partition_of(a.root, hp[i], a.log2_parts)], 1u);
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < parts; i += blockDim.x)
+        {
+            const uint32_t c = s_cnt[i];
+            s_base[i] = c ? atomicAdd(&a.cursor[i], c) : 0;
+            s_cnt[i] = 0;
+        }
+        __syncthreads();
+        for (uint32_t r = u * kPartReadsPerUnit + wib; r < r_end; r += nw)
+        {
+            const uint32_t H = a.hash_count[r];
+            const uint64_t *hp = a.hashes + a.hash_off[r];
+            for (uint32_t i = lane; i < H; i += 32)
+            {
+                const uint64_t key = hp[i];
+                const uint32_t b = root_partition_of(a.root, key, a.log2_parts);
+                const uint32_t at = s_base[b] + atomicAdd(&s_cnt[b], 1u);
+                a.part_hash[at] = key;
+                a.part_read[at] = r;
+            }
+        }
+    }
+}
+
+// probes the grouped elements; a match adds 1 to the 16-bit counter of (read, bin)
+__global__ void __launch_bounds__(32 * kQueryWarps) root_part_probe_kernel(RootPartArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const IxfDev d = a.root;
+    const uint32_t total = a.hist[1u << a.log2_parts];
+    const uint32_t lpr = d.tbins >> 4, G = 32u / lpr;
+    const uint32_t sub = (uint32_t)lane / lpr, col = (uint32_t)lane - sub * lpr;
+    const bool active = sub < G;
+    const uint8_t *col_base = d.fp + 16u * col;
+    while (true)
+    {
+        uint32_t c0 = 0;
+        if (lane == 0)
+            c0 = atomicAdd(&a.work[2], 1u);
+        c0 = __shfl_sync(0xffffffffu, c0, 0);
+        if ((uint64_t)c0 * kProbeChunk >= total)
+            break;
+        const uint32_t e0 = c0 * kProbeChunk, e1 = min(total, e0 + kProbeChunk);
+        Probe pr[kQueryUnroll];
+        uint32_t rd[kQueryUnroll];
+        for (uint32_t e = e0; e < e1; e += G * kQueryUnroll)
+        {
+#pragma unroll
+            for (int u = 0; u < kQueryUnroll; ++u)
+            {
+                const uint32_t idx = e + u * G + sub;
+                const bool live = active && idx < e1;
+                const uint64_t key = live ? a.part_hash[idx] : 0;
+                rd[u] = live ? a.part_read[idx] : 0;
+                probe_issue(pr[u], d, col_base, key, live);
+            }
+#pragma unroll
+            for (int u = 0; u < kQueryUnroll; ++u)
+            {
+                if (!pr[u].live)
+                    continue;
+                const uint32_t m[4] = {zero_bytes(pr[u].r0.x ^ pr[u].r1.x ^ pr[u].r2.x ^ pr[u].fs),
+                                       zero_bytes(pr[u].r0.y ^ pr[u].r1.y ^ pr[u].r2.y ^ pr[u].fs),
+                                       zero_bytes(pr[u].r0.z ^ pr[u].r1.z ^ pr[u].r2.z ^ pr[u].fs),
+                                       zero_bytes(pr[u].r0.w ^ pr[u].r1.w ^ pr[u].r2.w ^ pr[u].fs)};
+                if (m[0] | m[1] | m[2] | m[3])
+                {
+                    // bins 16*col + 4*wd + b; counters of bins 2j, 2j+1 share one 32-bit word (low, high half)
+                    uint32_t *cw = a.counts + ((size_t)rd[u] * d.tbins + 16u * col) / 2;
+#pragma unroll
+                    for (int wd = 0; wd < 4; ++wd)
+                    {
+                        if (!m[wd])
+                            continue;
+                        const uint32_t lo = (m[wd] & 1u) | ((m[wd] >> 8 & 1u) << 16);        // bins 4wd, 4wd+1
+                        const uint32_t hi = (m[wd] >> 16 & 1u) | ((m[wd] >> 24 & 1u) << 16); // bins 4wd+2, 4wd+3
+                        if (lo)
+                            atomicAdd(&cw[2 * wd], lo);
+                        if (hi)
+                            atomicAdd(&cw[2 * wd + 1], hi);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// per read: counters -> bin scan (thresholds, split runs, descents, hits)
+__global__ void __launch_bounds__(32 * kQueryWarps) root_part_scan_kernel2(QueryArgs a, RootPartArgs p)
+{
+    __shared__ uint32_t s_cnt[kQueryWarps][kSmallRowBytes];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t *cnt = s_cnt[wib];
+    const IxfDev d = p.root;
+    unsigned long long bytes = 0, items = 0;
+    while (true)
+    {
+        uint32_t read = 0;
+        if (lane == 0)
+            read = atomicAdd(&p.work[3], 1u);
+        read = __shfl_sync(0xffffffffu, read, 0);
+        if (read >= p.n_reads)
+            break;
+        const uint32_t *cw = p.counts + (size_t)read * d.tbins / 2;
+        for (uint32_t i = lane; i < d.tbins / 2; i += 32)
+        {
+            const uint32_t w = cw[i];
+            cnt[2 * i] = w & 0xffffu;
+            cnt[2 * i + 1] = w >> 16;
+        }
+        __syncwarp();
+        const uint32_t H = a.hash_count[read];
+        const uint64_t thr = a.thr_read ? a.thr_read[read] : (H < a.lut_len ? a.thr_lut[H] : ~0ULL);
+        scan_bins(a, d, read, thr, cnt, (uint32_t)lane, 32u);
         __syncwarp();
         bytes += (unsigned long long)H * 3ull * d.tbins + 8ull * H;
         ++items;
@@ -295,7 +537,7 @@ __global__ void __launch_bounds__(256) ixf_query_large_kernel(QueryArgs a)
         __syncthreads();
         const uint32_t H = a.hash_count[read];
         const uint64_t *hp = a.hashes + a.hash_off[read];
-        const uint64_t thr = H < a.lut_len ? a.thr_lut[H] : ~0ULL;
+        const uint64_t thr = a.thr_read ? a.thr_read[read] : (H < a.lut_len ? a.thr_lut[H] : ~0ULL);
         const uint32_t n_chunks = (d.tbins + kSmallRowBytes - 1) / kSmallRowBytes;
         for (uint32_t c = wib; c < n_chunks; c += nwarps)
         {
@@ -336,6 +578,88 @@ __global__ void __launch_bounds__(256) ixf_bulk_count_kernel(IxfDev d, const uin
         counts[i] = s_cnt_dyn[i];
 }
 
+// ---- level queues grouped by IXF ----
+// Work items of a level are appended in the order reads finish, i.e. all child IXFs interleaved: the rows a warp
+// gathers then come from the whole level (GBs) and nothing is reused.  Grouping the queue by IXF makes the few
+// thousand warps in flight work on two or three IXFs at a time; a child IXF of a 1,000-genome index is tens of MB
+// and stays in the 126 MB L2 while its reads are processed, so most of its rows are fetched from HBM once per
+// batch instead of once per probe.  Counting sort in three small launches (counts are device-resident).
+__global__ void __launch_bounds__(256) items_hist_kernel(const uint2 *items, const uint32_t *n_ptr, uint32_t cap, uint32_t *hist)
+{
+    const uint32_t n = min(*n_ptr, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&hist[items[i].y], 1u);
+}
+
+// exclusive scan of hist[0..n) in place, one CTA
+__global__ void __launch_bounds__(1024) items_scan_kernel(uint32_t *hist, uint32_t n)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0)
+        s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? hist[i] : 0;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d)
+                incl += up;
+        }
+        if (lane == 31)
+            s_warp[wib] = incl;
+        __syncthreads();
+        if (wib == 0)
+        {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d)
+                    w += up;
+            }
+            s_warp[lane] = w; // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t before = s_carry + (wib ? s_warp[wib - 1] : 0);
+        if (i < n)
+            hist[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            s_carry = before + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) items_scatter_kernel(const uint2 *items, const uint32_t *n_ptr, uint32_t cap, uint32_t *offs, uint2 *out)
+{
+    const uint32_t n = min(*n_ptr, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint2 it = items[i];
+        out[atomicAdd(&offs[it.y], 1u)] = it;
+    }
+}
+
+cudaError_t launch_sort_items(const uint2 *items, const uint32_t *n_ptr, uint32_t cap, uint32_t *hist, uint32_t n_ixf, uint2 *out,
+                              int sm_count, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)n_ixf * 4, st);
+    if (e != cudaSuccess)
+        return e;
+    items_hist_kernel<<<sm_count * 2, 256, 0, st>>>(items, n_ptr, cap, hist);
+    items_scan_kernel<<<1, 1024, 0, st>>>(hist, n_ixf);
+    items_scatter_kernel<<<sm_count * 2, 256, 0, st>>>(items, n_ptr, cap, hist, out);
+    return cudaGetLastError();
+}
+
 // ---- launchers ----
 // CTAs per SM of the persistent query grids (tuning knob, TXR_QUERY_CTAS_PER_SM; 8 = all 32 warps an SM can hold at
 // 61 registers, fewer leaves room for the compute-bound hash/dedup kernels of the neighbouring pipeline slots)
@@ -355,6 +679,17 @@ static int query_ctas_per_sm()
 cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st)
 {
     ixf_query_small_kernel<<<sm_count * query_ctas_per_sm(), 32 * kQueryWarps, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// partitioned root level: `a.work` and `a.hist` must be zero on entry (the engine clears them with the counters)
+cudaError_t launch_root_partitioned(const QueryArgs &q, const RootPartArgs &a, int sm_count, cudaStream_t st)
+{
+    root_part_hist_kernel<<<sm_count * 4, 256, 0, st>>>(a);
+    root_part_scan_kernel<<<1, 1024, 0, st>>>(a);
+    root_part_scatter_kernel<<<sm_count * 4, 256, 0, st>>>(a);
+    root_part_probe_kernel<<<sm_count * query_ctas_per_sm(), 32 * kQueryWarps, 0, st>>>(a);
+    root_part_scan_kernel2<<<sm_count * 8, 32 * kQueryWarps, 0, st>>>(q, a);
     return cudaGetLastError();
 }
 

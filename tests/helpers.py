@@ -28,7 +28,7 @@ class Dataset:
 
 
 def make_dataset(oracle, *, n_genomes=24, genome_len=60_000, k=22, s=12, t=None, use_syncmer=True, t_max=8,
-                 seed=1000, size_jitter=True, scaling=1) -> Dataset:
+                 seed=1000, size_jitter=True, scaling=1, window_size=None) -> Dataset:
     rng = np.random.default_rng(seed)
     lens = [int(genome_len * (0.5 + rng.random())) if size_jitter else genome_len for _ in range(n_genomes)]
     genomes = [tools.genome(seed + g, lens[g]) for g in range(n_genomes)]
@@ -37,7 +37,12 @@ def make_dataset(oracle, *, n_genomes=24, genome_len=60_000, k=22, s=12, t=None,
     ub = []
     for g in range(n_genomes):
         c = codes_of(genomes[g], lens[g])
-        h = oracle.syncmer_hashes(c, k, s, t) if use_syncmer else np.unique(oracle.kmer_hashes(c, k))
+        if use_syncmer:
+            h = oracle.syncmer_hashes(c, k, s, t)
+        elif window_size is not None and window_size > k:
+            h = np.unique(oracle.minimiser_hashes(c, k, window_size))     # compute_hashes.cpp:120-124
+        else:
+            h = np.unique(oracle.kmer_hashes(c, k))
         if scaling > 1:
             h = np.array([x for x in h.tolist() if oracle.scaling_keep(x, scaling)], dtype=np.uint64)
         ub.append(h)

@@ -208,9 +208,71 @@ def test_search_large_rows(ctx, oracle):
     _search_case(ctx, oracle, ds2, reads2, error_rate=0.1)
 
 
+@pytest.mark.parametrize("k,w", [(20, 24), (20, 40), (8, 12), (31, 126), (16, 17), (4, 8)])
+def test_minimiser_hash_parity(ctx, oracle, k, w):
+    """minimiser windows (window_size > k): same values, same order, same repeats as views::minimiser_hash; the
+    low-complexity inputs are all ties (sequential hand-over between lanes), small k makes ties common everywhere."""
+    ctx.set_params(k=k, use_syncmer=False, window_size=w)
+    rng = np.random.default_rng(k * 131 + w)
+    seqs = edge_reads(rng, k) + lowcomplexity_reads(rng)
+    seqs += [rng.integers(0, 4, n, dtype=np.uint8) for n in (w - 1, w, w + 1, w + 30, 1023 + w - 1, 1024 + w - 1, 1025 + w - 1, 2048 + w)]
+    seqs += [rng.integers(0, 4, int(n), dtype=np.uint8) for n in rng.integers(100, 12000, 30)]
+    reads = capi.pack_codes(seqs)
+    off, h = ctx.hash_batch(reads, dedup=True)
+    for i, c in enumerate(seqs):
+        exp = oracle.minimiser_hashes(c, k, w)
+        got = h[int(off[i]):int(off[i + 1])]
+        assert len(got) == len(exp) and np.array_equal(got, exp), (i, len(c), len(got), len(exp))
+
+
+@pytest.mark.parametrize("k,w,scaling", [(20, 32, 1), (20, 24, 10)])
+def test_search_parity_minimiser_mode(ctx, oracle, k, w, scaling):
+    """minimiser index end to end: FracMinHash threshold per read (hash_count AND read length), duplicates kept."""
+    ds = H.make_dataset(oracle, n_genomes=24, genome_len=60_000, k=k, s=0, t=0, use_syncmer=False, t_max=8, window_size=w,
+                        scaling=scaling)
+    rng = np.random.default_rng(16)
+    lengths = np.concatenate([np.exp(rng.uniform(np.log(300), np.log(20000), 80)).astype(np.int64), [0, 5, k - 1, k, k + 1, w - 1, w, w + 1]])
+    reads = H.make_reads(ds, np.maximum(lengths, 1), err=0.02)
+    res, ora = _search_case(ctx, oracle, ds, reads, window_size=w, error_rate=0.02, scaling=scaling)
+    assert int(res.hit_begin[-1]) > 10
+    ctx.configure(max_batch_reads=16, max_batch_bases=100_000, n_slots=3)     # several batches through the host round trip
+    try:
+        _search_case(ctx, oracle, ds, reads, window_size=w, error_rate=0.02, scaling=scaling)
+        _search_case(ctx, oracle, ds, reads, window_size=w, percentage=0.3, scaling=scaling)
+    finally:
+        ctx.configure()
+
+
+@pytest.fixture()
+def ctx_partitioned(monkeypatch):
+    """a context that takes the slot-partitioned root level whatever the index size (auto mode needs a >=48 MB segment)"""
+    monkeypatch.setenv("TXR_ROOT_PARTITION", "2")
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("t_max,n_genomes", [(8, 40), (64, 100), (128, 300)])
+def test_search_parity_partitioned_root(ctx_partitioned, oracle, t_max, n_genomes):
+    """root level through hist -> scatter -> probe -> scan (16-bit global counters): same hits, counts, order."""
+    ds = H.make_dataset(oracle, n_genomes=n_genomes, genome_len=40_000, t_max=t_max)
+    rng = np.random.default_rng(21)
+    lengths = np.concatenate([rng.integers(300, 12000, 400), [0, 1, 21, 22, 23]])
+    reads = H.make_reads(ds, np.maximum(lengths, 1), err=0.05)
+    res, ora = _search_case(ctx_partitioned, oracle, ds, reads, error_rate=0.1)
+    assert int(res.hit_begin[-1]) > 50
+    tm = ctx_partitioned.timing()
+    assert tm["query_launches"] >= 5                 # the five launches of the partitioned root were taken
+    ctx_partitioned.configure(max_batch_reads=37, max_batch_bases=300_000, n_slots=3)
+    _search_case(ctx_partitioned, oracle, ds, reads, error_rate=0.05)
+    _search_case(ctx_partitioned, oracle, ds, reads, percentage=0.1)
+
+
 def test_errors_are_loud(ctx):
     with pytest.raises(capi.TaxorError):
-        ctx.set_params(k=20, use_syncmer=False, window_size=24)       # minimiser windows: unsupported, not silently wrong
+        ctx.set_params(k=20, use_syncmer=False, window_size=19)       # window smaller than k
+    with pytest.raises(capi.TaxorError):
+        ctx.set_params(k=20, use_syncmer=False, window_size=116)      # 97 k-mers per window: beyond taxor build's limit
     with pytest.raises(capi.TaxorError):
         capi.pack_ascii(["ACGTX"])
     with pytest.raises(capi.TaxorError):

@@ -189,3 +189,69 @@ def test_live_reference_dfs(oracle, reference):
             a, b = oracle.bulk_contains(oh, vals, thr), reference.bulk_contains(rh, vals, thr)
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     reference.free_hixf(rh)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# minimiser windows (window_size > k): seqan3::views::minimiser_hash, upstream SeqAn3 3.3.0 semantics
+# ---------------------------------------------------------------------------------------------------------
+def _minimiser_model(values, w_vals):
+    """Independent pure-Python statement of views::minimiser (deque of the window, rightmost minimum,
+    re-report when the tracked minimiser leaves, strict replacement on arrival)."""
+    from collections import deque
+    n = len(values)
+    if n == 0:
+        return []
+    W = min(w_vals, n)
+    win = deque(values[:W])
+
+    def rightmost(d):
+        best, pos = None, 0
+        for i, x in enumerate(d):
+            if best is None or x <= best:
+                best, pos = x, i
+        return best, pos
+    val, off = rightmost(win)
+    out = [val]
+    for x in values[W:]:
+        win.popleft()
+        win.append(x)
+        if off == 0:
+            val, off = rightmost(win)
+            out.append(val)
+        elif x < val:
+            val, off = x, W - 1
+            out.append(val)
+        else:
+            off -= 1
+    return out
+
+
+def test_minimiser_known_answers(oracle):
+    m = {c: i for i, c in enumerate("ACGT")}
+    enc = lambda t: np.array([m[c] for c in t], dtype=np.uint8)
+    # known answers of upstream SeqAn3's own unit test for views::minimiser_hash (ungapped 4-mers, window 8, seed 0;
+    # test/unit/search/views/minimiser_hash_test.cpp, recalled -- the fork is not in /root/reference):
+    #   ACGGCGACGTTTAG -> ACGG, CGAC, ACGT, aacg, aaac (lower case = reverse strand);  poly-A -> one 0 per W shifts
+    assert oracle.minimiser_hashes(enc("ACGGCGACGTTTAG"), 4, 8, seed=0).tolist() == [26, 97, 27, 6, 1]
+    assert oracle.minimiser_hashes(enc("A" * 20), 4, 8, seed=0).tolist() == [0, 0, 0]
+    # hand-derived: CCACGTCGACGGTT has the canonical values 81 70 27 109 97 216 97 109 26 22 5; windows of 5:
+    # 27 (first window), rescan when it leaves -> RIGHTMOST 97, then the strictly smaller arrivals 26, 22, 5
+    assert oracle.minimiser_hashes(enc("CCACGTCGACGGTT"), 4, 8, seed=0).tolist() == [27, 97, 26, 22, 5]
+    # shorter than k: nothing; fewer k-mers than a window: ONE window over all of them (ACGT=27, CGTT/aacg=6)
+    assert len(oracle.minimiser_hashes(enc("ACG"), 4, 8, seed=0)) == 0
+    assert oracle.minimiser_hashes(enc("ACGTT"), 4, 8, seed=0).tolist() == [6]
+    # homopolymer: first window, then one report each time the tracked (rightmost) value leaves: every W=5 shifts
+    assert oracle.minimiser_hashes(np.zeros(37, np.uint8), 4, 8, seed=0).tolist() == [0] * 6
+
+
+@pytest.mark.parametrize("k,w", [(4, 8), (6, 7), (8, 20), (20, 24), (20, 40), (31, 126), (12, 12)])
+def test_minimiser_against_model(oracle, k, w):
+    rng = np.random.default_rng(k * 1000 + w)
+    seqs = [rng.integers(0, 4, int(n), dtype=np.uint8) for n in list(rng.integers(0, 400, 30)) + [k - 1, k, k + 1, w - 1, w, w + 1]]
+    seqs.append(np.zeros(300, np.uint8))
+    seqs.append(np.resize(np.array([0, 1], np.uint8), 500))
+    seqs.append(np.resize(np.array([0, 1, 2, 3, 3, 2, 1, 0], np.uint8), 700))
+    seqs.append((rng.integers(0, 2, 600) * 3).astype(np.uint8))
+    for c in seqs:
+        vals = oracle.kmer_hashes(c, k).tolist()
+        assert oracle.minimiser_hashes(c, k, w).tolist() == _minimiser_model(vals, w - k + 1), (k, w, len(c))
