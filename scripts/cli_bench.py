@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""End-to-end timing of the drop-in `taxor search` binary (read ingest and index load):
+.hixf file -> FASTQ file -> result file, with the phase times the binary prints under TAXOR_TIMING=1.
+
+Uses the index bench.py cached in /dev/shm (run bench.py first, or pass --genome-len for a smaller one), writes it as
+a real .hixf, simulates reads into a FASTQ file and runs the CLI with 1 and with N pack threads.  One JSON line."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads", type=int, default=200_000)
+    ap.add_argument("--read-len", type=int, default=10_000)
+    ap.add_argument("--genomes", type=int, default=1000)
+    ap.add_argument("--genome-len", type=int, default=40_000_000)
+    ap.add_argument("--t-max", type=int, default=64)
+    ap.add_argument("--cache", default="/dev/shm/taxor_b200_bench")
+    ap.add_argument("--work", default="/dev/shm/taxor_b200_cli")
+    ap.add_argument("--threads", type=int, default=16)
+    ap.add_argument("--gz", action="store_true", help="also time a gzip-compressed copy of the reads")
+    args = ap.parse_args()
+    from taxor_b200 import capi, tools
+    import taxor_b200
+
+    d, done = bench.index_cache_paths(args)
+    if not os.path.exists(done):
+        raise SystemExit(f"no cached index in {d}: run bench.py with the same --genomes/--genome-len first")
+    ix = bench.LoadedIndex(d)
+    os.makedirs(args.work, exist_ok=True)
+    hixf = os.path.join(args.work, "bench.hixf")
+    t0 = time.time()
+    if not os.path.exists(hixf):
+        tools.write_hixf(hixf, ix, k=bench.K, s=bench.S, t=bench.T, use_syncmer=True, window_size=20)
+    t_write = time.time() - t0
+
+    genomes, lens = bench.make_genomes(args)
+    fq = os.path.join(args.work, f"reads_{args.reads}.fastq")
+    if not os.path.exists(fq):
+        words, off, ln, _ = tools.simulate_reads(genomes, lens, np.full(args.reads, args.read_len, np.uint32), 0.05, seed=4242)
+        reads = capi.PackedReads(words, off, ln)
+        lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+        qual = b"I" * args.read_len
+        with open(fq, "wb") as f:
+            for i in range(args.reads):
+                f.write(b"@read_%d runid=synthetic ch=%d\n" % (i, i % 512))
+                f.write(lut[capi.unpack_codes(reads, i)].tobytes())
+                f.write(b"\n+\n")
+                f.write(qual[: int(ln[i])])
+                f.write(b"\n")
+    runs = {}
+    files = [("fastq", fq)]
+    if args.gz:
+        gz = fq + ".gz"
+        if not os.path.exists(gz):
+            subprocess.run(f"gzip -1 -c {fq} > {gz}", shell=True, check=True)
+        files.append(("fastq.gz", gz))
+    for tag, path in files:
+        for th in sorted({1, args.threads}):
+            out = os.path.join(args.work, "out.tsv")
+            env = dict(os.environ, TAXOR_TIMING="1")
+            t0 = time.time()
+            r = subprocess.run([taxor_b200.CLI_PATH, "search", "--index-file", hixf, "--query-file", path, "--output-file", out,
+                                "--error-rate", "0.1", "--threads", str(th), "--gpus", "1"], capture_output=True, text=True, env=env)
+            wall = time.time() - t0
+            if r.returncode != 0:
+                raise SystemExit(r.stderr)
+            m = re.search(r"index load ([\d.e+-]+) s, upload to \d+ GPU\(s\) ([\d.e+-]+) s \(([\d.e+-]+) GB\), ingest\+search\+write ([\d.e+-]+) s", r.stderr)
+            load, upload, gb, search = (float(x) for x in m.groups())
+            runs[f"{tag}_threads{th}"] = {"wall_s": round(wall, 2), "index_load_s": load, "index_upload_s": upload, "index_GB": gb,
+                                          "ingest_search_write_s": search, "file_GB": round(os.path.getsize(path) / 1e9, 2),
+                                          "Mbases_per_s_search_phase": round(args.reads * args.read_len / search / 1e6),
+                                          "hit_lines": sum(1 for line in open(out) if "\t-\t-\t" not in line) - 1}
+    print(json.dumps({"what": "taxor search CLI end to end (file -> file), 1 GPU", "reads": args.reads, "read_len": args.read_len,
+                      "hixf_write_s": round(t_write, 1), "host_cores": os.cpu_count(), "runs": runs}))
+
+
+if __name__ == "__main__":
+    main()

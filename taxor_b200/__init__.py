@@ -7,6 +7,6 @@ The product is the C-ABI shared library ``libtaxor_b200.so`` (``include/taxor_b2
   CUDA device is missing; there is no CPU fallback).
 * :mod:`taxor_b200.tools` -- CPU tooling (synthetic genomes/reads, XOR-filter construction, ``.hixf`` I/O).
 """
-from .build import build_all, LIB_PATH, TOOLS_PATH  # noqa: F401
+from .build import build_all, CLI_PATH, LIB_PATH, TOOLS_PATH  # noqa: F401
 
-__all__ = ["build_all", "LIB_PATH", "TOOLS_PATH"]
+__all__ = ["build_all", "CLI_PATH", "LIB_PATH", "TOOLS_PATH"]

@@ -87,6 +87,7 @@ struct QueryArgs
     uint32_t *n_hits;
     uint32_t hit_cap;
 
+    uint32_t l2_hints;              // 1: items are grouped by IXF, use the L2 eviction-priority plan (query_kernels.cu)
     unsigned long long *stat_bytes; // algorithmic bytes: sum H*3*tbins + 8*H
     unsigned long long *stat_items;
 };

@@ -26,6 +26,8 @@ namespace txr
 cudaError_t launch_syncmer(const HashArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_kmer(const HashArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_minimiser(const HashArgs &a, int sm_count, cudaStream_t st);
+void set_hash_launch_shape(int hash_ctas_per_sm, int dedup_ctas_per_sm);
+void set_query_launch_shape(int ctas_per_sm);
 cudaError_t launch_dedup_warp(const DedupArgs &a, int sm_count, uint32_t *work_counter, uint32_t *deferred, uint32_t *n_deferred,
                               cudaStream_t st);
 cudaError_t launch_dedup_deferred(const DedupArgs &a, int sm_count, const uint32_t *n_deferred, cudaStream_t st);
@@ -196,7 +198,7 @@ struct Slot
     cudaStream_t stream{nullptr};
     // events: 0 h2d start, 1 h2d done (copy stream) | 6 compute start, 2 hash done, 3 dedup done, 4 query done,
     // 7 compute done (compute stream) | 5 d2h done (copy stream)
-    cudaEvent_t ev[8]{};
+    cudaEvent_t ev[10]{}; // ... 8 query start (compute stream), 9 hash stage + thresholds done (hash stream)
     DevBuf words;
     BatchDev meta;
     DevBuf hashes, n_raw, hash_count, gtable, deferred;
@@ -255,7 +257,8 @@ struct txr_ctx
     Thresholder thresholder;
     uint64_t kmer_seed{0};
     bool sort_items{true};     // group level queues by IXF (TXR_SORT_ITEMS=0 disables, for A/B measurements)
-    int root_partition{1};     // group the root level's probes by segment-0 slot: 1 auto, 0 off, 2 always (TXR_ROOT_PARTITION)
+    bool l2_hints{true};       // L2 eviction-priority plan for small child IXFs (TXR_L2_HINTS=0 disables)
+    int root_partition{0};     // root level grouped by segment-0 slot: 0 off (default: measured slower), 1 auto, 2 always (TXR_ROOT_PARTITION)
     bool per_read_thr{false};  // FracMinHash model: the threshold depends on hash_count AND the read length
     std::vector<uint64_t> lut; // threshold by hash_count (host)
     DevBuf d_lut;
@@ -266,7 +269,10 @@ struct txr_ctx
     std::vector<uint64_t> hb_off, hb_hashes;
     DevBuf scratch_a, scratch_b;
     cudaStream_t primary{nullptr};     // caller's stream: every search forks from it and joins back into it
-    cudaStream_t compute{nullptr};     // ALL kernels run here, in batch order; slot streams only carry copies
+    cudaStream_t compute{nullptr};     // the query kernels of all batches run here, in batch order; slot streams only carry copies
+    cudaStream_t compute_hash{nullptr}; // overlap mode: hash + dedup (ALU bound) of batch i+1 beside the query (DRAM bound) of batch i
+    bool overlap{true};
+    int query_ctas{0}, hash_ctas{0}, dedup_ctas{0}; // CTAs per SM (0: defaults for the mode)
     cudaEvent_t fork_ev{nullptr}, join_ev{nullptr};
 };
 
@@ -300,7 +306,10 @@ static uint64_t next_pow2(uint64_t x)
 static int ensure_slots(txr_ctx *c)
 {
     if (!c->compute)
+    {
         CU(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->compute_hash, cudaStreamNonBlocking));
+    }
     while ((int)c->slots.size() < c->n_slots)
     {
         auto s = std::make_unique<Slot>();
@@ -647,6 +656,7 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
             if (c->sort_items)
                 CU(launch_sort_items(raw, lc + 0, s.queue_cap, s.ixf_hist.as<uint32_t>(), (uint32_t)ix.ixf.size(), sorted, c->sm_count, cs));
             q.items = c->sort_items ? sorted : raw;
+            q.l2_hints = c->sort_items && c->l2_hints;
             q.n_items_ptr = lc + 0;
             q.cursor = lc + 2;
             CU(launch_query_small(q, c->sm_count, cs));
@@ -709,13 +719,21 @@ static int submit_batch(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev 
     CU(cudaEventRecord(s.ev[1], s.stream));
     // kernels of all slots share ONE compute stream (in batch order): copies overlap compute, kernels never
     // compete with each other for SMs / DRAM
-    cudaStream_t cs = c->compute;
-    CU(cudaStreamWaitEvent(cs, s.ev[1], 0));
-    CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, cs));
-    CU(cudaEventRecord(s.ev[6], cs));
-    TRY(launch_hash_stage(c, s, m, *bd, d_words, true, cs));
+    // Overlap mode (several slots): hash + dedup run on their own stream with small grids, so that these ALU-bound
+    // kernels of batch i+1 share the SMs with the DRAM-bound query kernels of batch i.
+    const bool overlap = c->overlap && c->n_slots > 1;
+    set_query_launch_shape(c->query_ctas ? c->query_ctas : overlap ? 5 : 8);
+    set_hash_launch_shape(c->hash_ctas ? c->hash_ctas : overlap ? 1 : 8, c->dedup_ctas ? c->dedup_ctas : overlap ? 2 : 6);
+    cudaStream_t cs = c->compute, hs = overlap ? c->compute_hash : c->compute;
+    CU(cudaStreamWaitEvent(hs, s.ev[1], 0));
+    CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, hs));
+    CU(cudaEventRecord(s.ev[6], hs));
+    TRY(launch_hash_stage(c, s, m, *bd, d_words, true, hs));
     if (run_query && c->per_read_thr)
-        TRY(per_read_thresholds(c, s, m, cs));
+        TRY(per_read_thresholds(c, s, m, hs));
+    CU(cudaEventRecord(s.ev[9], hs));
+    CU(cudaStreamWaitEvent(cs, s.ev[9], 0));
+    CU(cudaEventRecord(s.ev[8], cs));
     if (run_query)
         TRY(launch_query_stage(c, s, m, *bd, cs));
     else
@@ -775,7 +793,7 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
     c->timing.hash_ms += ms;
     cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]);
     c->timing.dedup_ms += ms;
-    cudaEventElapsedTime(&ms, s.ev[3], s.ev[4]);
+    cudaEventElapsedTime(&ms, s.ev[8], s.ev[4]);
     c->timing.query_ms += ms;
 
     if (fetch)
@@ -863,15 +881,19 @@ static void finish_result(txr_ctx *c, txr_result *out)
     out->keep = R.keep.data();
 }
 
-// split reads [0, n) into batches bounded by reads and bases
-static void plan_batches(const txr_ctx *c, const uint32_t *len, uint64_t n, std::vector<std::pair<uint64_t, uint32_t>> &out)
+// split reads [0, n) into batches bounded by reads and bases.  `ramp`: when the reads come from the host, the first
+// batch is an eighth and the second a half of the limits, so that the copy nothing can overlap with is short.
+static void plan_batches(const txr_ctx *c, const uint32_t *len, uint64_t n, std::vector<std::pair<uint64_t, uint32_t>> &out,
+                         bool ramp = false)
 {
     out.clear();
     uint64_t i = 0;
     while (i < n)
     {
+        const uint64_t div = !ramp ? 1 : out.empty() ? 8 : out.size() == 1 ? 2 : 1;
+        const uint64_t max_reads = std::max<uint64_t>(c->max_batch_reads / div, 1), max_bases = std::max<uint64_t>(c->max_batch_bases / div, 1);
         uint64_t bases = 0, j = i;
-        while (j < n && j - i < c->max_batch_reads && (j == i || bases + len[j] <= c->max_batch_bases))
+        while (j < n && j - i < max_reads && (j == i || bases + len[j] <= max_bases))
             bases += len[j++];
         out.emplace_back(i, (uint32_t)(j - i));
         i = j;
@@ -888,6 +910,7 @@ static int fork_streams(txr_ctx *c)
     }
     CU(cudaEventRecord(c->fork_ev, c->primary));
     CU(cudaStreamWaitEvent(c->compute, c->fork_ev, 0));
+    CU(cudaStreamWaitEvent(c->compute_hash, c->fork_ev, 0));
     for (auto &s : c->slots)
         CU(cudaStreamWaitEvent(s->stream, c->fork_ev, 0));
     return TXR_OK;
@@ -896,6 +919,8 @@ static int fork_streams(txr_ctx *c)
 static int join_streams(txr_ctx *c)
 {
     CU(cudaEventRecord(c->join_ev, c->compute));
+    CU(cudaStreamWaitEvent(c->primary, c->join_ev, 0));
+    CU(cudaEventRecord(c->join_ev, c->compute_hash));
     CU(cudaStreamWaitEvent(c->primary, c->join_ev, 0));
     for (auto &s : c->slots)
     {
@@ -940,6 +965,16 @@ int txr_ctx_create(int device, txr_ctx **out)
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     if (const char *e = getenv("TXR_SORT_ITEMS"))
         c->sort_items = atoi(e) != 0;
+    if (const char *e = getenv("TXR_OVERLAP"))
+        c->overlap = atoi(e) != 0;
+    if (const char *e = getenv("TXR_QUERY_CTAS_PER_SM"))
+        c->query_ctas = atoi(e);
+    if (const char *e = getenv("TXR_HASH_CTAS_PER_SM"))
+        c->hash_ctas = atoi(e);
+    if (const char *e = getenv("TXR_DEDUP_CTAS_PER_SM"))
+        c->dedup_ctas = atoi(e);
+    if (const char *e = getenv("TXR_L2_HINTS"))
+        c->l2_hints = atoi(e) != 0;
     if (const char *e = getenv("TXR_ROOT_PARTITION"))
         c->root_partition = atoi(e);
     *out = c.release();
@@ -966,7 +1001,10 @@ void txr_ctx_destroy(txr_ctx *c)
         cudaStreamDestroy(s->stream);
     }
     if (c->compute)
+    {
         cudaStreamDestroy(c->compute);
+        cudaStreamDestroy(c->compute_hash);
+    }
     if (c->fork_ev)
     {
         cudaEventDestroy(c->fork_ev);
@@ -1297,7 +1335,7 @@ int txr_search(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, cons
     const auto t0 = std::chrono::steady_clock::now();
     TRY(fork_streams(c));
     std::vector<std::pair<uint64_t, uint32_t>> plan;
-    plan_batches(c, len, n_reads, plan);
+    plan_batches(c, len, n_reads, plan, c->n_slots > 1);
     std::vector<BatchMeta> metas(c->n_slots);
     const size_t S = (size_t)c->n_slots;
     for (size_t b = 0; b < plan.size() + S - 1; ++b)
@@ -1423,6 +1461,7 @@ int txr_hash_batch(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, 
     TRY(validate_reads(word_off, len, n_reads));
     c->hb_off.assign(1, 0);
     c->hb_hashes.clear();
+    set_hash_launch_shape(8, 6); // this entry point runs the hash stage alone: full grids
     std::vector<std::pair<uint64_t, uint32_t>> plan;
     plan_batches(c, len, n_reads, plan);
     Slot &s = *c->slots[0];

@@ -1,6 +1,7 @@
 // hixf_tools.cpp -- C entry points of libtaxor_tools.so around hixf_file.cpp, for tests and benchmarks:
 // write a synthetic index as a real `.hixf` file and read one back into plain arrays.
 #include "hixf_file.hpp"
+#include "ingest.hpp"
 
 #include <cstring>
 #include <string>
@@ -124,6 +125,53 @@ const char *txs_hixf_species_field(void *p, uint64_t i, int field, uint64_t *use
     case 2: return s.taxid.c_str();
     case 3: return s.taxnames_string.c_str();
     default: return s.taxid_string.c_str();
+    }
+}
+
+// Test hook for the CLI's parallel ingest (ingest.cpp): scans `path` with raw buffers of `target` bytes and writes one
+// "id<TAB>sequence" line per record to `out_path`.  Returns the number of records, -1 on error (txs_last_error).
+int64_t txs_ingest_dump(const char *path, uint64_t target, const char *out_path)
+{
+    try
+    {
+        txr::RecordScanner scan(path);
+        if (!scan.ok())
+        {
+            g_err = std::string("cannot open ") + path;
+            return -1;
+        }
+        FILE *f = fopen(out_path, "wb");
+        if (!f)
+        {
+            g_err = std::string("cannot write ") + out_path;
+            return -1;
+        }
+        std::vector<char> buf;
+        std::vector<txr::RecordRef> recs;
+        std::string joined;
+        int64_t n = 0;
+        while (scan.next(buf, recs, target))
+            for (const auto &r : recs)
+            {
+                fwrite(buf.data() + r.id_off, 1, r.id_len, f);
+                fputc('\t', f);
+                if (r.single_line)
+                    fwrite(buf.data() + r.seq_off, 1, r.seq_len, f);
+                else
+                {
+                    txr::join_record(buf.data(), r, joined);
+                    fwrite(joined.data(), 1, joined.size(), f);
+                }
+                fputc('\n', f);
+                ++n;
+            }
+        fclose(f);
+        return n;
+    }
+    catch (std::exception const &e)
+    {
+        g_err = e.what();
+        return -1;
     }
 }
 

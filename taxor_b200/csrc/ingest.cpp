@@ -1,0 +1,214 @@
+#include "ingest.hpp"
+
+#include <cstring>
+#include <fcntl.h>
+#include <stdexcept>
+#include <unistd.h>
+
+namespace txr
+{
+RecordScanner::RecordScanner(const std::string &path)
+{
+    fd_ = ::open(path.c_str(), O_RDONLY);
+    if (fd_ < 0)
+        return;
+    unsigned char magic[2] = {0, 0};
+    const ssize_t n = ::pread(fd_, magic, 2, 0);
+    if (n == 2 && magic[0] == 0x1f && magic[1] == 0x8b) // gzip: inflate through zlib, everything else is read() directly
+    {
+        gz_ = gzdopen(fd_, "rb");
+        if (!gz_)
+        {
+            ::close(fd_);
+            fd_ = -1;
+            return;
+        }
+        fd_ = -1; // owned by gz_ now
+        gzbuffer(gz_, 1 << 20);
+    }
+#ifdef POSIX_FADV_SEQUENTIAL
+    else
+        posix_fadvise(fd_, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+}
+
+RecordScanner::~RecordScanner()
+{
+    if (gz_)
+        gzclose(gz_);
+    if (fd_ >= 0)
+        ::close(fd_);
+}
+
+size_t RecordScanner::fill(char *dst, size_t cap)
+{
+    size_t got = 0;
+    while (got < cap && !eof_)
+    {
+        long n;
+        if (gz_)
+        {
+            n = gzread(gz_, dst + got, (unsigned)std::min<size_t>(cap - got, 1u << 30));
+            if (n < 0)
+                throw std::runtime_error("read error (corrupt gzip stream?)");
+        }
+        else
+        {
+            n = ::read(fd_, dst + got, cap - got);
+            if (n < 0)
+                throw std::runtime_error("read error");
+        }
+        if (n == 0)
+            eof_ = true;
+        got += (size_t)n;
+    }
+    return got;
+}
+
+namespace
+{
+inline size_t line_len(const char *b, const char *e) // without one trailing '\r'
+{
+    return (size_t)(e - b) - ((e > b && e[-1] == '\r') ? 1 : 0);
+}
+
+// Scans one record starting at data[pos] (which is '>' or '@').  Returns false when the record is not complete
+// in [pos, n) and more data may follow.
+bool scan_record(const char *data, size_t n, size_t pos, bool at_eof, RecordRef &r, size_t &next_pos)
+{
+    const char marker = data[pos];
+    const char *end = data + n;
+    const char *p = data + pos;
+    const char *nl = static_cast<const char *>(memchr(p, '\n', (size_t)(end - p)));
+    if (!nl && !at_eof)
+        return false;
+    const char *hdr_end = nl ? nl : end;
+    r.id_off = (uint32_t)(pos + 1);
+    r.id_len = (uint32_t)line_len(p + 1, hdr_end);
+    p = nl ? nl + 1 : end;
+    r.seq_off = (uint32_t)(p - data);
+    size_t seq_len = 0, lines = 0;
+    const char *seq_end = p;
+    const char stop = marker == '>' ? '>' : '+';
+    while (true)
+    {
+        if (p >= end)
+        {
+            if (!at_eof)
+                return false;
+            if (marker == '@')
+                throw std::runtime_error("FASTQ record without a '+' line");
+            break;
+        }
+        if (*p == stop)
+            break;
+        const char *e = static_cast<const char *>(memchr(p, '\n', (size_t)(end - p)));
+        if (!e && !at_eof)
+            return false;
+        const char *le = e ? e : end;
+        const size_t ll = line_len(p, le);
+        if (ll)
+        {
+            if (lines == 0)
+                r.seq_off = (uint32_t)(p - data);
+            ++lines;
+            seq_end = p + ll;
+        }
+        seq_len += ll;
+        p = e ? e + 1 : end;
+    }
+    if (seq_len > 0xffffffffull)
+        throw std::runtime_error("sequence longer than 2^32 bases");
+    r.seq_len = (uint32_t)seq_len;
+    r.seq_span = (uint32_t)(seq_end - (data + r.seq_off));
+    r.single_line = lines <= 1;
+    if (marker == '@')
+    {
+        // '+' line, then quality lines until as many characters as bases were seen
+        const char *e = static_cast<const char *>(memchr(p, '\n', (size_t)(end - p)));
+        if (!e && !at_eof)
+            return false;
+        p = e ? e + 1 : end;
+        size_t q = 0;
+        while (q < seq_len)
+        {
+            if (p >= end)
+            {
+                if (!at_eof)
+                    return false;
+                break;
+            }
+            const char *qe = static_cast<const char *>(memchr(p, '\n', (size_t)(end - p)));
+            if (!qe && !at_eof)
+                return false;
+            const char *le = qe ? qe : end;
+            q += line_len(p, le);
+            p = qe ? qe + 1 : end;
+        }
+        if (q != seq_len)
+            throw std::runtime_error("FASTQ quality string length differs from the sequence length");
+    }
+    next_pos = (size_t)(p - data);
+    return true;
+}
+} // namespace
+
+bool RecordScanner::next(std::vector<char> &buf, std::vector<RecordRef> &recs, size_t target)
+{
+    recs.clear();
+    if (!ok())
+        return false;
+    size_t have = carry_.size();
+    if (buf.size() < std::max(target, have + (1u << 16)))
+        buf.resize(std::max(target, have + (1u << 16)));
+    if (have)
+        memcpy(buf.data(), carry_.data(), have);
+    carry_.clear();
+    while (true)
+    {
+        have += fill(buf.data() + have, buf.size() - have);
+        const char *data = buf.data();
+        size_t pos = 0;
+        while (true)
+        {
+            while (pos < have && (data[pos] == '\n' || data[pos] == '\r')) // blank lines between records
+                ++pos;
+            if (pos >= have)
+                break;
+            if (data[pos] != '>' && data[pos] != '@')
+                throw std::runtime_error("sequence file: record does not start with '>' or '@'");
+            RecordRef r{};
+            size_t next_pos = pos;
+            if (!scan_record(data, have, pos, eof_, r, next_pos))
+                break;
+            recs.push_back(r);
+            pos = next_pos;
+        }
+        if (!recs.empty() || (eof_ && pos >= have))
+        {
+            carry_.assign(data + pos, data + have); // incomplete tail (empty at end of file)
+            return !recs.empty();
+        }
+        if (eof_)
+            throw std::runtime_error("sequence file: truncated record at end of file");
+        // not even one complete record fits: grow and read on
+        if (buf.size() > (size_t)0xfffffff0ull)
+            throw std::runtime_error("sequence record larger than 4 GiB");
+        buf.resize(std::min<size_t>(buf.size() * 2, 0xfffffff0ull));
+    }
+}
+
+void join_record(const char *raw, const RecordRef &r, std::string &out)
+{
+    out.clear();
+    out.reserve(r.seq_len);
+    const char *p = raw + r.seq_off, *end = p + r.seq_span;
+    while (p < end)
+    {
+        const char *e = static_cast<const char *>(memchr(p, '\n', (size_t)(end - p)));
+        const char *le = e ? e : end;
+        out.append(p, line_len(p, le));
+        p = e ? e + 1 : end;
+    }
+}
+} // namespace txr

@@ -1,0 +1,51 @@
+// ingest.hpp -- parallel FASTA / FASTQ (plain or gzip) ingest for the `taxor search` driver.
+//
+// Replaces seqan3::sequence_file_input<dna4_traits, fields<id, seq>> + views::chunk(1024) on the main thread
+// (src/main/taxor_search.cpp:181-184, 315-321), which parses serially while the workers idle.  Here ONE thread
+// streams the file (inflating if it is gzip) and only finds record boundaries (memchr per line, no copying);
+// the byte work -- IUPAC -> dna4 collapse and 2-bit packing straight into the pinned batch buffer, id strings --
+// is done by a pool of threads on disjoint record ranges.  Record semantics are those of seqio.cpp (the serial
+// reader kept for tests): id = header line without '>' / '@', sequence = all sequence lines joined, one trailing
+// '\r' stripped per line, blank lines between records skipped, FASTQ quality length checked.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <zlib.h>
+
+namespace txr
+{
+struct RecordRef // one record inside a raw buffer
+{
+    uint32_t id_off, id_len;   // header line without the marker and without "\r"
+    uint32_t seq_off, seq_span; // first sequence byte .. end of the last sequence line (may contain line breaks)
+    uint32_t seq_len;          // bases (line breaks excluded)
+    uint32_t single_line;      // 1: the seq_len bases are contiguous at seq_off
+};
+
+// Streams a sequence file as raw buffers that each start at a record boundary.
+class RecordScanner
+{
+public:
+    explicit RecordScanner(const std::string &path);
+    ~RecordScanner();
+    RecordScanner(const RecordScanner &) = delete;
+    RecordScanner &operator=(const RecordScanner &) = delete;
+    bool ok() const { return fd_ >= 0 || gz_ != nullptr; }
+    // Fills `buf` (resized as needed; `target` bytes unless one record needs more) and appends the descriptors of
+    // the complete records it holds to `recs` (cleared first).  The incomplete tail is kept for the next call.
+    // Returns false when the file is exhausted and nothing was produced; throws std::runtime_error on malformed input.
+    bool next(std::vector<char> &buf, std::vector<RecordRef> &recs, size_t target);
+
+private:
+    size_t fill(char *dst, size_t cap);
+    int fd_{-1};
+    gzFile gz_{nullptr};
+    bool eof_{false};
+    std::vector<char> carry_;
+};
+
+// The sequence of `r` with its line breaks removed (multi-line records); single-line records need no copy.
+void join_record(const char *raw, const RecordRef &r, std::string &out);
+} // namespace txr

@@ -49,7 +49,50 @@ struct Probe
     bool live;
 };
 
-__device__ __forceinline__ void probe_issue(Probe &p, const IxfDev &d, const uint8_t *col_base, uint64_t key, bool live)
+// the same load with an L2 eviction-priority policy (createpolicy): rows worth keeping against rows that stream
+__device__ __forceinline__ uint4 ldg_row16_hint(const uint8_t *p, uint64_t policy)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// L2 residency plan of an IXF.  What survives in L2 between two touches is far less than the nominal 126 MB
+// (profiles/r1_launches_root_partitioned_10GB.txt: a 33 MB reuse distance already misses half the time), so only
+// IXFs whose FIRST segment is small are worth it: its rows are loaded evict_last and the other two segments'
+// rows evict_first, which keeps one of the three lines of a probe in L2 while the level queue (grouped by IXF)
+// works through that IXF.
+struct L2Plan
+{
+    bool split;        // segment 0 evict_last, segments 1 and 2 evict_first
+    uint64_t keep, stream;
+};
+constexpr uint64_t kL2KeepBytes = 28ull << 20;
+__device__ __forceinline__ L2Plan l2_plan_for(const IxfDev &d, bool enabled)
+{
+    L2Plan p;
+    p.split = enabled && (uint64_t)d.seg_len * d.tbins <= kL2KeepBytes && (uint64_t)d.seg_len * d.tbins * 3 > kL2KeepBytes;
+    p.keep = l2_policy_evict_last();
+    p.stream = l2_policy_evict_first();
+    return p;
+}
+
+__device__ __forceinline__ void probe_issue(Probe &p, const IxfDev &d, const uint8_t *col_base, uint64_t key, bool live,
+                                            const L2Plan &l2 = L2Plan{false, 0, 0})
 {
     p.live = live;
     if (live)
@@ -58,9 +101,18 @@ __device__ __forceinline__ void probe_issue(Probe &p, const IxfDev &d, const uin
         uint32_t p0, p1, p2;
         ixf_slots(h, d.seg_len, p0, p1, p2);
         p.fs = ixf_fingerprint(h) * 0x01010101u;
-        p.r0 = ldg_row16(col_base + (uint64_t)p0 * d.tbins);
-        p.r1 = ldg_row16(col_base + (uint64_t)p1 * d.tbins);
-        p.r2 = ldg_row16(col_base + (uint64_t)p2 * d.tbins);
+        if (l2.split)
+        {
+            p.r0 = ldg_row16_hint(col_base + (uint64_t)p0 * d.tbins, l2.keep);
+            p.r1 = ldg_row16_hint(col_base + (uint64_t)p1 * d.tbins, l2.stream);
+            p.r2 = ldg_row16_hint(col_base + (uint64_t)p2 * d.tbins, l2.stream);
+        }
+        else
+        {
+            p.r0 = ldg_row16(col_base + (uint64_t)p0 * d.tbins);
+            p.r1 = ldg_row16(col_base + (uint64_t)p1 * d.tbins);
+            p.r2 = ldg_row16(col_base + (uint64_t)p2 * d.tbins);
+        }
     }
 }
 
@@ -102,7 +154,8 @@ __device__ __forceinline__ void acc_flush(uint32_t (&acc)[4], uint32_t *cnt16)
 //   cnt       : shared counters of the chunk's first bin
 template <int UNROLL>
 __device__ __forceinline__ void probe_chunk(const IxfDev &d, const uint64_t *__restrict__ hp, uint32_t H,
-                                            uint32_t chunk_off, uint32_t lpr, uint32_t *cnt, int lane)
+                                            uint32_t chunk_off, uint32_t lpr, uint32_t *cnt, int lane,
+                                            const L2Plan &l2 = L2Plan{false, 0, 0})
 {
     const uint32_t G = 32u / lpr;         // hashes per step
     const uint32_t sub = (uint32_t)lane / lpr;
@@ -120,7 +173,7 @@ __device__ __forceinline__ void probe_chunk(const IxfDev &d, const uint64_t *__r
             const uint32_t idx = h0 + u * G + sub;
             const bool live = active && idx < H;
             const uint64_t key = live ? hp[idx] : 0;
-            probe_issue(pr[u], d, col_base, key, live);
+            probe_issue(pr[u], d, col_base, key, live, l2);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
@@ -249,7 +302,7 @@ __global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(Query
         const uint32_t H = a.hash_count[read];
         const uint64_t *hp = a.hashes + a.hash_off[read];
         const uint64_t thr = a.thr_read ? a.thr_read[read] : (H < a.lut_len ? a.thr_lut[H] : ~0ULL);
-        probe_chunk<kQueryUnroll>(d, hp, H, 0u, d.tbins >> 4, cnt, lane);
+        probe_chunk<kQueryUnroll>(d, hp, H, 0u, d.tbins >> 4, cnt, lane, l2_plan_for(d, a.l2_hints != 0));
         __syncwarp();
         scan_bins(a, d, read, thr, cnt, (uint32_t)lane, 32u);
         __syncwarp();
@@ -661,20 +714,12 @@ cudaError_t launch_sort_items(const uint2 *items, const uint32_t *n_ptr, uint32_
 }
 
 // ---- launchers ----
-// CTAs per SM of the persistent query grids (tuning knob, TXR_QUERY_CTAS_PER_SM; 8 = all 32 warps an SM can hold at
-// 61 registers, fewer leaves room for the compute-bound hash/dedup kernels of the neighbouring pipeline slots)
-static int query_ctas_per_sm()
-{
-    static int v = 0;
-    if (!v)
-    {
-        const char *e = getenv("TXR_QUERY_CTAS_PER_SM");
-        v = e ? atoi(e) : 8;
-        if (v < 1 || v > 16)
-            v = 8;
-    }
-    return v;
-}
+// CTAs per SM of the persistent query grids: 8 = all 32 warps an SM can hold at 56 registers.  The random-line rate
+// of HBM is already saturated by 16 warps per SM (profiles/r1_gather_bench2.json), so the engine lowers this when
+// the hash / dedup kernels of the next batch run beside it.
+static int g_query_ctas_per_sm = 8;
+void set_query_launch_shape(int ctas_per_sm) { g_query_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm > 16 ? 16 : ctas_per_sm; }
+static int query_ctas_per_sm() { return g_query_ctas_per_sm; }
 
 cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st)
 {

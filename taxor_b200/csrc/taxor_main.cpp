@@ -4,10 +4,12 @@
 // Extra, optional knobs (ignored by the reference): --gpus <n|list>, --ixf-record <field order>.
 #include "../../include/taxor_b200.h"
 #include "hixf_file.hpp"
-#include "seqio.hpp"
+#include "ingest.hpp"
 #include "threshold.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +36,7 @@ struct Config // src/main/taxor_search_configuration.hpp:8-19
     double threshold{-1.0};
     double error_rate{0.04};
     unsigned threads{1};
+    bool threads_given{false};
     std::string gpus;       // extension
     std::string ixf_record; // extension
 };
@@ -153,6 +156,7 @@ void parse_args(int argc, char const **argv, Config &c) // taxor_search.cpp:32-8
             if (t < 1 || t > 32)
                 throw ParserError("Validation failed for option --threads: Value " + std::to_string(t) + " is not in range [1,32].");
             c.threads = (unsigned)t;
+            c.threads_given = true;
         }
         else if (name == "percentage")
             c.threshold = parse_double(name, v, 0.0, 1.0);
@@ -181,12 +185,29 @@ std::string load_index_file(const std::string &path, const Config &cfg, TaxorInd
 struct Chunk
 {
     size_t seq{0};
-    std::vector<std::string> ids;
+    size_t n{0};                    // reads in this chunk
+    std::vector<std::string> ids;   // pre-sized to kChunkReads: filled by the pack threads, never reallocated
     std::vector<uint32_t> len;
     std::vector<uint64_t> word_off;
     uint64_t *words{nullptr};
     size_t words_cap{0}, words_used{0};
+    std::atomic<int> pending{0};    // pack tasks still running + 1 while the reader may add more
     std::string text; // formatted result lines
+};
+
+struct RawBuf // a stretch of the input file that starts at a record boundary
+{
+    std::vector<char> data;
+    std::vector<RecordRef> recs;
+    std::atomic<int> refs{0};
+};
+
+struct PackTask // records [rec_begin, rec_end) of raw -> reads first_read.. of chunk
+{
+    RawBuf *raw{nullptr};
+    uint32_t rec_begin{0}, rec_end{0};
+    Chunk *chunk{nullptr};
+    uint32_t first_read{0};
 };
 
 template <typename T> class Channel
@@ -252,7 +273,7 @@ void format_chunk(Chunk &ch, const txr_result &res, const TaxorIndexFile &idx, c
 {
     std::string &out = ch.text;
     out.clear();
-    for (size_t r = 0; r < ch.ids.size(); ++r)
+    for (size_t r = 0; r < ch.n; ++r)
     {
         const std::string &id = ch.ids[r];
         const uint64_t b = res.hit_begin[r], e = res.hit_begin[r + 1];
@@ -297,16 +318,20 @@ void format_chunk(Chunk &ch, const txr_result &res, const TaxorIndexFile &idx, c
 
 constexpr size_t kChunkReads = 65536;
 constexpr size_t kChunkBases = 400u << 20;
+constexpr size_t kRawTarget = 32u << 20; // bytes of input per pack task
 
 // search_single, taxor_search.cpp:153-338
 void search_single(const Config &cfg, const std::string &query, const std::string &index_path, std::ofstream &out,
                    const std::vector<int> &devices)
 {
+    const bool timing = getenv("TAXOR_TIMING") != nullptr; // stderr: wall time of the load / upload / search phases
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
     TaxorIndexFile idx;
     std::string load_error;
     std::thread loader([&] { load_error = load_index_file(index_path, cfg, idx); }); // the async cereal_worker (:162-180)
 
-    SeqReader fin(query);
+    RecordScanner fin(query);
     if (!fin.ok())
     {
         loader.join();
@@ -347,6 +372,8 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     par.percentage = cfg.threshold;
     par.error_rate = cfg.error_rate;
 
+    const double t_load = since(t_start);
+    const auto t_up = std::chrono::steady_clock::now();
     std::vector<txr_ctx *> ctxs;
     for (int d : devices)
     {
@@ -356,18 +383,30 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
         ctxs.push_back(c);
     }
 
-    // chunk pool (pinned), parser -> workers -> ordered writer
-    const size_t n_chunks = 2 * ctxs.size() + 1;
+    const double t_upload = since(t_up);
+    const auto t_search = std::chrono::steady_clock::now();
+    // chunk pool (pinned): scanner -> pack threads -> GPU workers -> ordered writer
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned n_pack = cfg.threads_given ? cfg.threads : std::min(16u, hw);
+    const size_t n_chunks = 2 * ctxs.size() + 2;
     std::vector<Chunk> pool(n_chunks);
+    std::vector<RawBuf> raw_pool(n_pack + 2);
     Channel<Chunk *> free_q, work_q, done_q;
+    Channel<RawBuf *> raw_free;
+    Channel<PackTask> task_q;
     for (auto &ch : pool)
     {
         ch.words_cap = kChunkBases / 32 + 2 * kChunkReads + 64;
         ch.words = static_cast<uint64_t *>(txr_host_alloc(ch.words_cap * 8));
         if (!ch.words)
             throw std::runtime_error(txr_last_error());
+        ch.ids.resize(kChunkReads);
+        ch.len.resize(kChunkReads);
+        ch.word_off.resize(kChunkReads);
         free_q.push(&ch);
     }
+    for (auto &rb : raw_pool)
+        raw_free.push(&rb);
     std::string worker_error;
     std::mutex err_m;
     std::vector<std::thread> workers;
@@ -377,7 +416,7 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
             while (work_q.pop(ch))
             {
                 txr_result res{};
-                if (txr_search(c, ch->words, ch->word_off.data(), ch->len.data(), ch->ids.size(), &res) != TXR_OK)
+                if (txr_search(c, ch->words, ch->word_off.data(), ch->len.data(), ch->n, &res) != TXR_OK)
                 {
                     std::lock_guard<std::mutex> l(err_m);
                     worker_error = txr_last_error();
@@ -406,66 +445,143 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
         }
     });
 
+    // pack threads: IUPAC -> dna4 -> 2 bit straight into the chunk's pinned buffer, ids copied
     std::string parse_error;
+    std::atomic<bool> failed{false};
+    std::vector<std::thread> packers;
+    for (unsigned t = 0; t < n_pack; ++t)
+        packers.emplace_back([&] {
+            PackTask task;
+            std::string scratch;
+            while (task_q.pop(task))
+            {
+                Chunk &ch = *task.chunk;
+                const char *raw = task.raw->data.data();
+                for (uint32_t k = task.rec_begin; k < task.rec_end && !failed.load(std::memory_order_relaxed); ++k)
+                {
+                    const RecordRef &r = task.raw->recs[k];
+                    const uint32_t idx = task.first_read + (k - task.rec_begin);
+                    ch.ids[idx].assign(raw + r.id_off, r.id_len);
+                    const char *bases = raw + r.seq_off;
+                    if (!r.single_line)
+                    {
+                        join_record(raw, r, scratch);
+                        bases = scratch.data();
+                    }
+                    if (txr_pack_2bit(bases, r.seq_len, ch.words + ch.word_off[idx]) != TXR_OK)
+                    {
+                        std::lock_guard<std::mutex> l(err_m);
+                        if (parse_error.empty())
+                            parse_error = "read '" + ch.ids[idx] + "': " + txr_last_error();
+                        failed = true;
+                    }
+                }
+                if (task.raw->refs.fetch_sub(1) == 1)
+                    raw_free.push(task.raw);
+                if (ch.pending.fetch_sub(1) == 1)
+                    work_q.push(&ch);
+            }
+        });
+
+    // scanner (this thread): record boundaries only; chunks are taken and sealed in file order
     size_t seq = 0;
     try
     {
-        std::string id, s;
         Chunk *ch = nullptr;
         size_t bases = 0;
-        auto flush = [&] {
-            if (ch && !ch->ids.empty())
-            {
-                ch->seq = seq++;
+        auto seal = [&] {
+            if (!ch)
+                return;
+            ch->seq = seq++;
+            if (ch->pending.fetch_sub(1) == 1)
                 work_q.push(ch);
-            }
-            else if (ch)
-                free_q.push(ch);
             ch = nullptr;
         };
-        while (fin.next(id, s))
+        while (!failed)
         {
-            const uint64_t nw = txr_packed_words(s.size());
-            if (ch && (ch->ids.size() >= kChunkReads || bases + s.size() > kChunkBases || ch->words_used + nw > ch->words_cap))
-                flush();
-            if (!ch)
+            RawBuf *rb = nullptr;
+            raw_free.pop(rb);
+            if (!fin.next(rb->data, rb->recs, kRawTarget))
             {
-                free_q.pop(ch);
-                ch->ids.clear();
-                ch->len.clear();
-                ch->word_off.clear();
-                ch->words_used = 0;
-                bases = 0;
-                if (nw > ch->words_cap) // a single sequence larger than a chunk: grow this chunk's buffer
+                raw_free.push(rb);
+                break;
+            }
+            rb->refs = 1;
+            size_t i = 0;
+            const size_t n_rec = rb->recs.size();
+            while (i < n_rec)
+            {
+                if (!ch)
                 {
+                    free_q.pop(ch);
+                    ch->n = 0;
+                    ch->words_used = 0;
+                    ch->pending = 1;
+                    bases = 0;
+                }
+                size_t j = i;
+                while (j < n_rec)
+                {
+                    const uint64_t L = rb->recs[j].seq_len, nw = txr_packed_words(L);
+                    if (ch->n >= kChunkReads || (ch->n && bases + L > kChunkBases) || ch->words_used + nw > ch->words_cap)
+                        break;
+                    ch->len[ch->n] = (uint32_t)L;
+                    ch->word_off[ch->n] = ch->words_used;
+                    ch->words_used += nw;
+                    bases += L;
+                    ++ch->n;
+                    ++j;
+                }
+                if (j == i)
+                {
+                    if (ch->n) // full: hand it over and start the next one
+                    {
+                        seal();
+                        continue;
+                    }
+                    // a single sequence larger than a chunk: grow this (empty, task-free) chunk's buffer
+                    const uint64_t nw = txr_packed_words(rb->recs[i].seq_len);
                     txr_host_free(ch->words);
                     ch->words_cap = nw + 64;
                     ch->words = static_cast<uint64_t *>(txr_host_alloc(ch->words_cap * 8));
                     if (!ch->words)
                         throw std::runtime_error(txr_last_error());
+                    continue;
                 }
+                ch->pending.fetch_add(1);
+                rb->refs.fetch_add(1);
+                task_q.push(PackTask{rb, (uint32_t)i, (uint32_t)j, ch, (uint32_t)(ch->n - (j - i))});
+                i = j;
             }
-            if (s.size() > 0xffffffffull)
-                throw std::runtime_error("sequence longer than 2^32 bases");
-            if (txr_pack_2bit(s.data(), s.size(), ch->words + ch->words_used) != TXR_OK)
-                throw std::runtime_error(std::string("read '") + id + "': " + txr_last_error());
-            ch->ids.push_back(id);
-            ch->len.push_back((uint32_t)s.size());
-            ch->word_off.push_back(ch->words_used);
-            ch->words_used += nw;
-            bases += s.size();
+            if (rb->refs.fetch_sub(1) == 1)
+                raw_free.push(rb);
         }
-        flush();
+        seal();
     }
     catch (std::exception const &e)
     {
-        parse_error = e.what();
+        std::lock_guard<std::mutex> l(err_m);
+        if (parse_error.empty())
+            parse_error = e.what();
+        failed = true;
     }
+    task_q.close();
+    for (auto &t : packers)
+        t.join();
     work_q.close();
     for (auto &t : workers)
         t.join();
     done_q.close();
     writer.join();
+    if (timing)
+    {
+        uint64_t fp_bytes = 0;
+        for (auto &x : idx.ixf)
+            fp_bytes += 3 * x.seg_len * x.tbins;
+        std::cerr << "[taxor timing] index load " << t_load << " s, upload to " << ctxs.size() << " GPU(s) " << t_upload << " s ("
+                  << fp_bytes / 1e9 << " GB), ingest+search+write " << since(t_search) << " s, " << seq << " chunks, " << n_pack
+                  << " pack threads\n";
+    }
     for (auto &ch : pool)
         txr_host_free(ch.words);
     for (txr_ctx *c : ctxs)

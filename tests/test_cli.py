@@ -109,3 +109,23 @@ def test_cli_kmer_mode_index(tmp_path, oracle, built_libs):
     assert r.returncode == 0 and "use kmer-model" in r.stdout, r.stderr
     assert open(out).read() == H.oracle_tsv(oracle, ds.arrays, species, records, k=20, s=0, t=0, use_syncmer=False, window_size=20,
                                             error_rate=0.02)
+
+
+@pytest.mark.gpu
+def test_cli_minimiser_index(tmp_path, oracle, built_libs):
+    """an index built with --window-size > --kmer-size: minimiser hashing, FracMinHash threshold banner and values"""
+    ds = H.make_dataset(oracle, n_genomes=12, genome_len=30_000, k=20, s=0, t=0, use_syncmer=False, t_max=4, window_size=28)
+    species = tools.default_species(ds.hixf.n_user_bins)
+    idx_path = tmp_path / "minimiser.hixf"
+    tools.write_hixf(idx_path, ds.hixf, k=20, s=0, t=0, use_syncmer=False, window_size=28, species=species)
+    reads = H.make_reads(ds, np.random.default_rng(6).integers(300, 6000, 80), err=0.01)
+    records = [(f"r{i}", "".join("ACGT"[c] for c in capi.unpack_codes(reads, i))) for i in range(reads.n)]
+    records += [("short", "ACGTACGT"), ("empty", "")]
+    open(tmp_path / "r.fa", "w").write(fasta_text(records, width=60))
+    out = tmp_path / "o.tsv"
+    r = run_cli("search", "--index-file", str(idx_path), "--query-file", str(tmp_path / "r.fa"), "--output-file", str(out),
+                "--error-rate", "0.02")
+    assert r.returncode == 0 and "use frac minhash" in r.stdout, r.stderr
+    got = open(out).read()
+    assert got == H.oracle_tsv(oracle, ds.arrays, species, records, k=20, s=0, t=0, use_syncmer=False, window_size=28, error_rate=0.02)
+    assert got.count("\t") > 6 * len(records)                   # reads really hit

@@ -1,0 +1,96 @@
+"""CPU: the CLI's parallel-ingest scanner (taxor_b200/csrc/ingest.cpp) against a plain Python statement of the record
+semantics of seqan3::sequence_file_input<fields<id, seq>> (taxor_search.cpp:181-182): FASTA and FASTQ, multi-line
+records, CRLF, blank lines, gzip, buffers far smaller than a record (carry-over between raw buffers)."""
+import ctypes as C
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from taxor_b200 import tools
+
+
+def _dump(path, target, tmp_path):
+    T = tools.tlib()
+    T.txs_ingest_dump.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p]
+    T.txs_ingest_dump.restype = C.c_int64
+    out = str(tmp_path / "dump.tsv")
+    n = T.txs_ingest_dump(str(path).encode(), target, out.encode())
+    if n < 0:
+        raise RuntimeError(T.txs_last_error().decode())
+    recs = []
+    with open(out, "rb") as f:
+        for line in f.read().split(b"\n")[:-1]:
+            i, s = line.split(b"\t")
+            recs.append((i, s))
+    assert len(recs) == n
+    return recs
+
+
+def _rand_seq(rng, n):
+    return bytes(rng.choice(np.frombuffer(b"ACGTNacgtRYKM", dtype=np.uint8), n).tobytes())
+
+
+def _wrap(seq, width, eol):
+    if width == 0 or len(seq) == 0:
+        return seq + eol
+    return b"".join(seq[i:i + width] + eol for i in range(0, len(seq), width))
+
+
+def _make(rng, fmt, n, eol=b"\n", width=0, final_eol=True, blank=False):
+    recs, blob = [], b""
+    for i in range(n):
+        L = int(rng.choice([0, 1, 5, 60, 61, 500, 4000, 20000]))
+        name = f"read_{i} len={L} some description".encode()
+        seq = _rand_seq(rng, L)
+        recs.append((name, seq))
+        if fmt == "fasta":
+            blob += b">" + name + eol + (_wrap(seq, width, eol) if L else b"")
+        else:
+            qual = bytes(rng.integers(33, 74, L, dtype=np.uint8).tobytes())      # may contain '@' and '+' and '>'
+            blob += b"@" + name + eol + _wrap(seq, width, eol) + b"+" + eol + _wrap(qual, width, eol)
+        if blank and i % 3 == 0:
+            blob += eol
+    if not final_eol and blob.endswith(eol):
+        blob = blob[:-len(eol)]
+    return recs, blob
+
+
+@pytest.mark.parametrize("fmt", ["fasta", "fastq"])
+@pytest.mark.parametrize("eol,width,final_eol,blank", [(b"\n", 0, True, False), (b"\r\n", 0, True, True), (b"\n", 60, False, False),
+                                                      (b"\r\n", 70, True, True)])
+def test_scanner_matches_record_semantics(tmp_path, fmt, eol, width, final_eol, blank):
+    rng = np.random.default_rng(hash((fmt, width, final_eol)) % 2**32)
+    if fmt == "fastq" and width and not final_eol:
+        final_eol = True
+    recs, blob = _make(rng, fmt, 120, eol, width, final_eol, blank)
+    if fmt == "fastq" and width:
+        # wrapped FASTQ: a quality line may start with '@' or '+'; the sequence lines never do
+        pass
+    p = tmp_path / f"x.{fmt}"
+    p.write_bytes(blob)
+    for target in (1 << 20, 4096, 64):              # 64 bytes: every record spans many refills
+        assert _dump(p, target, tmp_path) == recs
+    gz = tmp_path / f"x.{fmt}.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(blob)
+    assert _dump(gz, 5000, tmp_path) == recs
+
+
+def test_scanner_errors(tmp_path):
+    bad = tmp_path / "bad.fq"
+    bad.write_bytes(b"@r1\nACGT\n+\nIII\n")             # quality shorter than the sequence
+    with pytest.raises(RuntimeError, match="quality"):
+        _dump(bad, 4096, tmp_path)
+    bad.write_bytes(b"@r1\nACGT\n")                     # no '+' line
+    with pytest.raises(RuntimeError, match=r"\+"):
+        _dump(bad, 4096, tmp_path)
+    bad.write_bytes(b"ACGT\n")
+    with pytest.raises(RuntimeError, match="does not start"):
+        _dump(bad, 4096, tmp_path)
+    empty = tmp_path / "empty.fa"
+    empty.write_bytes(b"")
+    assert _dump(empty, 4096, tmp_path) == []
+    with pytest.raises(RuntimeError, match="cannot open"):
+        _dump(tmp_path / "missing.fa", 4096, tmp_path)
