@@ -271,7 +271,7 @@ struct txr_ctx
     cudaStream_t primary{nullptr};     // caller's stream: every search forks from it and joins back into it
     cudaStream_t compute{nullptr};     // the query kernels of all batches run here, in batch order; slot streams only carry copies
     cudaStream_t compute_hash{nullptr}; // overlap mode: hash + dedup (ALU bound) of batch i+1 beside the query (DRAM bound) of batch i
-    bool overlap{true};
+    bool overlap{false};               // TXR_OVERLAP=1: measured slower end to end, kept for experiments
     int query_ctas{0}, hash_ctas{0}, dedup_ctas{0}; // CTAs per SM (0: defaults for the mode)
     cudaEvent_t fork_ev{nullptr}, join_ev{nullptr};
 };

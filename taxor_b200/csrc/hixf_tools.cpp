@@ -4,7 +4,9 @@
 #include "ingest.hpp"
 
 #include <cstring>
+#include <stdexcept>
 #include <string>
+#include <vector>
 
 using namespace txr;
 
@@ -166,6 +168,80 @@ int64_t txs_ingest_dump(const char *path, uint64_t target, const char *out_path)
                 ++n;
             }
         fclose(f);
+        return n;
+    }
+    catch (std::exception const &e)
+    {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// The mapped-file path of the same ingest: byte ranges of `seg_bytes`, each guessed + scanned on its own, then
+// accepted or rescanned in order -- exactly what the driver's jobs and assembler do, single threaded.
+// `n_rescans` receives how many guesses were wrong.
+int64_t txs_ingest_dump_mapped(const char *path, uint64_t seg_bytes, const char *out_path, uint64_t *n_rescans)
+{
+    try
+    {
+        txr::MappedFile mf(path);
+        if (!mf.ok())
+        {
+            g_err = std::string("cannot open ") + path;
+            return -1;
+        }
+        FILE *f = fopen(out_path, "wb");
+        if (!f)
+        {
+            g_err = std::string("cannot write ") + out_path;
+            return -1;
+        }
+        const char *data = mf.data();
+        const size_t size = mf.size();
+        size_t first = 0;
+        while (first < size && (data[first] == '\n' || data[first] == '\r'))
+            ++first;
+        int64_t n = 0;
+        uint64_t rescans = 0;
+        if (first < size)
+        {
+            if (data[first] != '>' && data[first] != '@')
+                throw std::runtime_error("sequence file: record does not start with '>' or '@'");
+            const char marker = data[first];
+            const size_t n_seg = (size + seg_bytes - 1) / seg_bytes;
+            std::vector<txr::SegmentScan> segs(n_seg);
+            for (size_t k = 0; k < n_seg; ++k) // "parallel" phase
+                txr::scan_byte_range(data, size, first, marker, k * seg_bytes, std::min<size_t>(size, (k + 1) * seg_bytes), segs[k]);
+            size_t expected = first;
+            std::string joined;
+            for (size_t k = 0; k < n_seg; ++k)
+            {
+                const size_t hi = std::min<size_t>(size, (k + 1) * seg_bytes);
+                const bool inside = expected >= hi;
+                const bool agreed = segs[k].error.empty() && segs[k].begin == expected;
+                expected = txr::accept_byte_range(data, size, expected, hi, segs[k]);
+                if (!inside && !agreed)
+                    ++rescans;
+                const char *base = data + segs[k].begin;
+                for (const auto &r : segs[k].recs)
+                {
+                    fwrite(base + r.id_off, 1, r.id_len, f);
+                    fputc('\t', f);
+                    if (r.single_line)
+                        fwrite(base + r.seq_off, 1, r.seq_len, f);
+                    else
+                    {
+                        txr::join_record(base, r, joined);
+                        fwrite(joined.data(), 1, joined.size(), f);
+                    }
+                    fputc('\n', f);
+                    ++n;
+                }
+            }
+        }
+        fclose(f);
+        if (n_rescans)
+            *n_rescans = rescans;
         return n;
     }
     catch (std::exception const &e)

@@ -3,6 +3,8 @@
 #include <cstring>
 #include <fcntl.h>
 #include <stdexcept>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 namespace txr
@@ -196,6 +198,148 @@ bool RecordScanner::next(std::vector<char> &buf, std::vector<RecordRef> &recs, s
             throw std::runtime_error("sequence record larger than 4 GiB");
         buf.resize(std::min<size_t>(buf.size() * 2, 0xfffffff0ull));
     }
+}
+
+MappedFile::MappedFile(const std::string &path)
+{
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0)
+        return;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode))
+    {
+        ::close(fd);
+        return;
+    }
+    size_ = (size_t)st.st_size;
+    ok_ = true;
+    if (size_)
+    {
+        void *p = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (p == MAP_FAILED)
+        {
+            ok_ = false;
+            size_ = 0;
+        }
+        else
+        {
+            data_ = static_cast<const char *>(p);
+            madvise(p, size_, MADV_SEQUENTIAL);
+            gzip_ = size_ >= 2 && (unsigned char)data_[0] == 0x1f && (unsigned char)data_[1] == 0x8b;
+        }
+    }
+    ::close(fd);
+}
+
+MappedFile::~MappedFile()
+{
+    if (data_)
+        munmap(const_cast<char *>(data_), size_);
+}
+
+size_t guess_record_start(const char *data, size_t size, size_t from, char marker)
+{
+    size_t pos = from;
+    if (pos > 0) // move to the next line start unless `from` is one
+    {
+        if (data[pos - 1] != '\n')
+        {
+            const char *nl = static_cast<const char *>(memchr(data + pos, '\n', size - pos));
+            if (!nl)
+                return size;
+            pos = (size_t)(nl - data) + 1;
+        }
+    }
+    const char *end = data + size;
+    while (pos < size)
+    {
+        const char *l0 = data + pos;
+        const char *e0 = static_cast<const char *>(memchr(l0, '\n', (size_t)(end - l0)));
+        if (*l0 == marker)
+        {
+            if (marker == '>')
+                return pos;
+            // FASTQ, 4-line layout: header / bases / '+' / qualities of the same length
+            if (e0)
+            {
+                const char *l1 = e0 + 1;
+                const char *e1 = l1 < end ? static_cast<const char *>(memchr(l1, '\n', (size_t)(end - l1))) : nullptr;
+                if (e1 && e1 + 1 < end && e1[1] == '+')
+                {
+                    const char *e2 = static_cast<const char *>(memchr(e1 + 1, '\n', (size_t)(end - e1 - 1)));
+                    if (e2)
+                    {
+                        const char *l3 = e2 + 1;
+                        const char *e3 = l3 < end ? static_cast<const char *>(memchr(l3, '\n', (size_t)(end - l3))) : nullptr;
+                        const char *q_end = e3 ? e3 : end;
+                        if (line_len(l1, e1) == line_len(l3, q_end))
+                            return pos;
+                    }
+                }
+            }
+        }
+        if (!e0)
+            return size;
+        pos = (size_t)(e0 - data) + 1;
+    }
+    return size;
+}
+
+size_t scan_segment(const char *data, size_t size, size_t begin, size_t end_hint, std::vector<RecordRef> &recs)
+{
+    recs.clear();
+    const char *base = data + begin;
+    const size_t n = size - begin;
+    size_t pos = 0;
+    while (true)
+    {
+        while (pos < n && (base[pos] == '\n' || base[pos] == '\r'))
+            ++pos;
+        if (pos >= n || begin + pos >= end_hint)
+            break;
+        if (base[pos] != '>' && base[pos] != '@')
+            throw std::runtime_error("sequence file: record does not start with '>' or '@'");
+        if (pos > 0xf0000000ull)
+            throw std::runtime_error("sequence record larger than 4 GiB");
+        RecordRef r{};
+        size_t next_pos = pos;
+        scan_record(base, n, pos, true, r, next_pos); // the whole file is mapped: never incomplete
+        if (next_pos > 0xfffffff0ull)
+            throw std::runtime_error("sequence record larger than 4 GiB");
+        recs.push_back(r);
+        pos = next_pos;
+    }
+    return begin + pos;
+}
+
+void scan_byte_range(const char *data, size_t size, size_t first_record, char marker, size_t lo, size_t hi, SegmentScan &out)
+{
+    try
+    {
+        out.begin = lo == 0 ? first_record : guess_record_start(data, size, lo, marker);
+        out.end = out.begin < hi ? scan_segment(data, size, out.begin, hi, out.recs) : out.begin;
+    }
+    catch (std::exception const &e)
+    {
+        out.error = e.what();
+    }
+}
+
+size_t accept_byte_range(const char *data, size_t size, size_t expected, size_t hi, SegmentScan &sg)
+{
+    if (expected >= hi) // the record before spans this whole range
+    {
+        sg.recs.clear();
+        sg.begin = sg.end = expected;
+        return expected;
+    }
+    if (!sg.error.empty() || sg.begin != expected)
+    {
+        sg.error.clear();
+        sg.begin = expected;
+        sg.end = scan_segment(data, size, expected, hi, sg.recs);
+    }
+    return sg.end;
 }
 
 void join_record(const char *raw, const RecordRef &r, std::string &out)

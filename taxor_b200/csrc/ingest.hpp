@@ -46,6 +46,49 @@ private:
     std::vector<char> carry_;
 };
 
+// ---- plain (not gzip) files: mapped, cut into byte segments, segments scanned in parallel ----
+class MappedFile
+{
+public:
+    explicit MappedFile(const std::string &path);
+    ~MappedFile();
+    MappedFile(const MappedFile &) = delete;
+    MappedFile &operator=(const MappedFile &) = delete;
+    bool ok() const { return ok_; }
+    bool gzip() const { return gzip_; } // starts with the gzip magic: use RecordScanner instead
+    const char *data() const { return data_; }
+    size_t size() const { return size_; }
+
+private:
+    const char *data_{nullptr};
+    size_t size_{0};
+    bool ok_{false}, gzip_{false};
+};
+
+// A position >= from where a record PROBABLY starts (data[pos] == marker at a line start; for FASTQ also: the line
+// two below starts with '+' and lines 1 and 3 have equal lengths -- the 4-line layout).  `size` when there is none.
+// Only a guess: the caller checks it against the exact scan of the preceding segment and rescans on disagreement.
+size_t guess_record_start(const char *data, size_t size, size_t from, char marker);
+
+// Exact scan (scan semantics of RecordScanner) of the records that start in [begin, end_hint), where `begin` is a
+// record start (or blank lines before one).  Descriptors are relative to data + begin.  Returns the position after
+// the last scanned record; throws std::runtime_error on malformed input.
+size_t scan_segment(const char *data, size_t size, size_t begin, size_t end_hint, std::vector<RecordRef> &recs);
+
+// One byte range [lo, hi) of a mapped file, as the driver's scan jobs and its in-order consumer use it.
+struct SegmentScan
+{
+    size_t begin{0}, end{0};     // first record start (guessed unless lo == 0) / position after the last record scanned
+    std::vector<RecordRef> recs; // relative to data + begin
+    std::string error;
+};
+// the job: guess the first record start at or after lo, scan the records that start before hi (never throws)
+void scan_byte_range(const char *data, size_t size, size_t first_record, char marker, size_t lo, size_t hi, SegmentScan &out);
+// the consumer, called in range order with `expected` = where the next record must start according to the exact
+// scan of everything before: keeps `sg` if its guess agrees, rescans it exactly otherwise (throws on malformed input);
+// a range lying wholly inside the record before yields no records.  Returns the new `expected`.
+size_t accept_byte_range(const char *data, size_t size, size_t expected, size_t hi, SegmentScan &sg);
+
 // The sequence of `r` with its line breaks removed (multi-line records); single-line records need no copy.
 void join_record(const char *raw, const RecordRef &r, std::string &out);
 } // namespace txr

@@ -16,8 +16,10 @@
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <sstream>
 #include <stdexcept>
@@ -195,19 +197,15 @@ struct Chunk
     std::string text; // formatted result lines
 };
 
-struct RawBuf // a stretch of the input file that starts at a record boundary
+struct RawBuf // streaming path (gzip): a stretch of the input that starts at a record boundary
 {
     std::vector<char> data;
     std::vector<RecordRef> recs;
-    std::atomic<int> refs{0};
 };
 
-struct PackTask // records [rec_begin, rec_end) of raw -> reads first_read.. of chunk
+struct Segment : SegmentScan // mapped path: the records that start inside one byte range of the file
 {
-    RawBuf *raw{nullptr};
-    uint32_t rec_begin{0}, rec_end{0};
-    Chunk *chunk{nullptr};
-    uint32_t first_read{0};
+    bool done{false};
 };
 
 template <typename T> class Channel
@@ -331,8 +329,8 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     std::string load_error;
     std::thread loader([&] { load_error = load_index_file(index_path, cfg, idx); }); // the async cereal_worker (:162-180)
 
-    RecordScanner fin(query);
-    if (!fin.ok())
+    MappedFile mapped(query);
+    if (!mapped.ok())
     {
         loader.join();
         throw std::runtime_error("cannot open query file " + query);
@@ -385,15 +383,13 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
 
     const double t_upload = since(t_up);
     const auto t_search = std::chrono::steady_clock::now();
-    // chunk pool (pinned): scanner -> pack threads -> GPU workers -> ordered writer
+    // chunk pool (pinned): scan -> pack jobs -> GPU workers -> ordered writer
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const unsigned n_pack = cfg.threads_given ? cfg.threads : std::min(16u, hw);
     const size_t n_chunks = 2 * ctxs.size() + 2;
     std::vector<Chunk> pool(n_chunks);
-    std::vector<RawBuf> raw_pool(n_pack + 2);
     Channel<Chunk *> free_q, work_q, done_q;
-    Channel<RawBuf *> raw_free;
-    Channel<PackTask> task_q;
+    Channel<std::function<void()>> jobs;
     for (auto &ch : pool)
     {
         ch.words_cap = kChunkBases / 32 + 2 * kChunkReads + 64;
@@ -405,8 +401,6 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
         ch.word_off.resize(kChunkReads);
         free_q.push(&ch);
     }
-    for (auto &rb : raw_pool)
-        raw_free.push(&rb);
     std::string worker_error;
     std::mutex err_m;
     std::vector<std::thread> workers;
@@ -445,128 +439,185 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
         }
     });
 
-    // pack threads: IUPAC -> dna4 -> 2 bit straight into the chunk's pinned buffer, ids copied
+    // job threads: segment scans (mapped files) and packing (IUPAC -> dna4 -> 2 bit straight into the pinned chunk, ids)
     std::string parse_error;
     std::atomic<bool> failed{false};
-    std::vector<std::thread> packers;
+    auto fail = [&](const std::string &msg) {
+        std::lock_guard<std::mutex> l(err_m);
+        if (parse_error.empty())
+            parse_error = msg;
+        failed = true;
+    };
+    // state the jobs point into: declared before the threads so that it outlives them on every path
+    std::vector<RawBuf> raw_pool(n_pack + 2);
+    Channel<RawBuf *> raw_free;
+    std::mutex seg_m;
+    std::condition_variable seg_cv;
+    std::vector<std::thread> job_threads;
     for (unsigned t = 0; t < n_pack; ++t)
-        packers.emplace_back([&] {
-            PackTask task;
-            std::string scratch;
-            while (task_q.pop(task))
-            {
-                Chunk &ch = *task.chunk;
-                const char *raw = task.raw->data.data();
-                for (uint32_t k = task.rec_begin; k < task.rec_end && !failed.load(std::memory_order_relaxed); ++k)
-                {
-                    const RecordRef &r = task.raw->recs[k];
-                    const uint32_t idx = task.first_read + (k - task.rec_begin);
-                    ch.ids[idx].assign(raw + r.id_off, r.id_len);
-                    const char *bases = raw + r.seq_off;
-                    if (!r.single_line)
-                    {
-                        join_record(raw, r, scratch);
-                        bases = scratch.data();
-                    }
-                    if (txr_pack_2bit(bases, r.seq_len, ch.words + ch.word_off[idx]) != TXR_OK)
-                    {
-                        std::lock_guard<std::mutex> l(err_m);
-                        if (parse_error.empty())
-                            parse_error = "read '" + ch.ids[idx] + "': " + txr_last_error();
-                        failed = true;
-                    }
-                }
-                if (task.raw->refs.fetch_sub(1) == 1)
-                    raw_free.push(task.raw);
-                if (ch.pending.fetch_sub(1) == 1)
-                    work_q.push(&ch);
-            }
+        job_threads.emplace_back([&] {
+            std::function<void()> job;
+            while (jobs.pop(job))
+                job();
         });
-
-    // scanner (this thread): record boundaries only; chunks are taken and sealed in file order
-    size_t seq = 0;
-    try
-    {
-        Chunk *ch = nullptr;
-        size_t bases = 0;
-        auto seal = [&] {
-            if (!ch)
-                return;
-            ch->seq = seq++;
-            if (ch->pending.fetch_sub(1) == 1)
-                work_q.push(ch);
-            ch = nullptr;
-        };
-        while (!failed)
-        {
-            RawBuf *rb = nullptr;
-            raw_free.pop(rb);
-            if (!fin.next(rb->data, rb->recs, kRawTarget))
+    auto pack_job = [&](std::shared_ptr<const void> hold, const char *base, const RecordRef *recs, uint32_t count, Chunk *chp, uint32_t first_read) {
+        jobs.push([&, hold, base, recs, count, chp, first_read] {
+            Chunk &ch = *chp;
+            thread_local std::string scratch;
+            for (uint32_t k = 0; k < count && !failed.load(std::memory_order_relaxed); ++k)
             {
-                raw_free.push(rb);
-                break;
+                const RecordRef &r = recs[k];
+                const uint32_t idx = first_read + k;
+                ch.ids[idx].assign(base + r.id_off, r.id_len);
+                const char *bases = base + r.seq_off;
+                if (!r.single_line)
+                {
+                    join_record(base, r, scratch);
+                    bases = scratch.data();
+                }
+                if (txr_pack_2bit(bases, r.seq_len, ch.words + ch.word_off[idx]) != TXR_OK)
+                    fail("read '" + ch.ids[idx] + "': " + txr_last_error());
             }
-            rb->refs = 1;
-            size_t i = 0;
-            const size_t n_rec = rb->recs.size();
-            while (i < n_rec)
+            if (ch.pending.fetch_sub(1) == 1)
+                work_q.push(&ch);
+        });
+    };
+
+    // assembler (this thread): records -> chunk slots in file order; chunks are taken and sealed in order
+    size_t seq = 0;
+    Chunk *cur = nullptr;
+    size_t cur_bases = 0;
+    auto seal = [&] {
+        if (!cur)
+            return;
+        cur->seq = seq++;
+        if (cur->pending.fetch_sub(1) == 1)
+            work_q.push(cur);
+        cur = nullptr;
+    };
+    auto assemble = [&](const std::shared_ptr<const void> &hold, const char *base, const std::vector<RecordRef> &recs) {
+        size_t i = 0;
+        const size_t n_rec = recs.size();
+        while (i < n_rec)
+        {
+            if (!cur)
             {
-                if (!ch)
+                free_q.pop(cur);
+                cur->n = 0;
+                cur->words_used = 0;
+                cur->pending = 1;
+                cur_bases = 0;
+            }
+            size_t j = i;
+            while (j < n_rec)
+            {
+                const uint64_t L = recs[j].seq_len, nw = txr_packed_words(L);
+                if (cur->n >= kChunkReads || (cur->n && cur_bases + L > kChunkBases) || cur->words_used + nw > cur->words_cap)
+                    break;
+                cur->len[cur->n] = (uint32_t)L;
+                cur->word_off[cur->n] = cur->words_used;
+                cur->words_used += nw;
+                cur_bases += L;
+                ++cur->n;
+                ++j;
+            }
+            if (j == i)
+            {
+                if (cur->n) // full: hand it over and start the next one
                 {
-                    free_q.pop(ch);
-                    ch->n = 0;
-                    ch->words_used = 0;
-                    ch->pending = 1;
-                    bases = 0;
-                }
-                size_t j = i;
-                while (j < n_rec)
-                {
-                    const uint64_t L = rb->recs[j].seq_len, nw = txr_packed_words(L);
-                    if (ch->n >= kChunkReads || (ch->n && bases + L > kChunkBases) || ch->words_used + nw > ch->words_cap)
-                        break;
-                    ch->len[ch->n] = (uint32_t)L;
-                    ch->word_off[ch->n] = ch->words_used;
-                    ch->words_used += nw;
-                    bases += L;
-                    ++ch->n;
-                    ++j;
-                }
-                if (j == i)
-                {
-                    if (ch->n) // full: hand it over and start the next one
-                    {
-                        seal();
-                        continue;
-                    }
-                    // a single sequence larger than a chunk: grow this (empty, task-free) chunk's buffer
-                    const uint64_t nw = txr_packed_words(rb->recs[i].seq_len);
-                    txr_host_free(ch->words);
-                    ch->words_cap = nw + 64;
-                    ch->words = static_cast<uint64_t *>(txr_host_alloc(ch->words_cap * 8));
-                    if (!ch->words)
-                        throw std::runtime_error(txr_last_error());
+                    seal();
                     continue;
                 }
-                ch->pending.fetch_add(1);
-                rb->refs.fetch_add(1);
-                task_q.push(PackTask{rb, (uint32_t)i, (uint32_t)j, ch, (uint32_t)(ch->n - (j - i))});
-                i = j;
+                // a single sequence larger than a chunk: grow this (empty, job-free) chunk's buffer
+                const uint64_t nw = txr_packed_words(recs[i].seq_len);
+                txr_host_free(cur->words);
+                cur->words_cap = nw + 64;
+                cur->words = static_cast<uint64_t *>(txr_host_alloc(cur->words_cap * 8));
+                if (!cur->words)
+                    throw std::runtime_error(txr_last_error());
+                continue;
             }
-            if (rb->refs.fetch_sub(1) == 1)
-                raw_free.push(rb);
+            cur->pending.fetch_add(1);
+            pack_job(hold, base, recs.data() + i, (uint32_t)(j - i), cur, (uint32_t)(cur->n - (j - i)));
+            i = j;
+        }
+    };
+
+    try
+    {
+        if (mapped.ok() && !mapped.gzip())
+        {
+            // mapped file: byte segments scanned by the job threads; every guess of a segment's first record is checked
+            // against the exact end of the segment before it, and a wrong one is rescanned here
+            const char *data = mapped.data();
+            const size_t size = mapped.size();
+            size_t first = 0;
+            while (first < size && (data[first] == '\n' || data[first] == '\r'))
+                ++first;
+            if (first < size && data[first] != '>' && data[first] != '@')
+                throw std::runtime_error("sequence file: record does not start with '>' or '@'");
+            const char marker = first < size ? data[first] : '>';
+            const size_t n_seg = (size + kRawTarget - 1) / kRawTarget;
+            std::vector<std::shared_ptr<Segment>> segs(n_seg);
+            size_t dispatched = 0;
+            auto dispatch = [&](size_t upto) {
+                for (; dispatched < std::min(upto, n_seg); ++dispatched)
+                {
+                    auto sg = std::make_shared<Segment>();
+                    segs[dispatched] = sg;
+                    const size_t lo = dispatched * kRawTarget, hi = std::min(size, lo + kRawTarget);
+                    jobs.push([&seg_m, &seg_cv, sg, lo, hi, data, size, first, marker] {
+                        scan_byte_range(data, size, first, marker, lo, hi, *sg);
+                        {
+                            std::lock_guard<std::mutex> l(seg_m);
+                            sg->done = true;
+                        }
+                        seg_cv.notify_all();
+                    });
+                }
+            };
+            size_t expected = first;
+            for (size_t k = 0; k < n_seg && !failed; ++k)
+            {
+                dispatch(k + 2 * n_pack + 2);
+                std::shared_ptr<Segment> sg = segs[k];
+                {
+                    std::unique_lock<std::mutex> l(seg_m);
+                    seg_cv.wait(l, [&] { return sg->done; });
+                }
+                segs[k].reset();
+                const size_t hi = std::min(size, (k + 1) * kRawTarget);
+                expected = accept_byte_range(data, size, expected, hi, *sg); // a wrong guess is rescanned exactly here
+                assemble(sg, data + sg->begin, sg->recs);
+            }
+        }
+        else
+        {
+            // gzip (or unmappable) input: one streaming scanner, raw buffers recycled through a pool
+            RecordScanner fin(query);
+            if (!fin.ok())
+                throw std::runtime_error("cannot open query file " + query);
+            for (auto &rb : raw_pool)
+                raw_free.push(&rb);
+            while (!failed)
+            {
+                RawBuf *rb = nullptr;
+                raw_free.pop(rb);
+                if (!fin.next(rb->data, rb->recs, kRawTarget))
+                    break;
+                std::shared_ptr<RawBuf> hold(rb, [&raw_free](RawBuf *p) { raw_free.push(p); });
+                assemble(hold, rb->data.data(), rb->recs);
+            }
         }
         seal();
     }
     catch (std::exception const &e)
     {
-        std::lock_guard<std::mutex> l(err_m);
-        if (parse_error.empty())
-            parse_error = e.what();
-        failed = true;
+        fail(e.what());
+        seal();
     }
-    task_q.close();
-    for (auto &t : packers)
+    jobs.close();
+    for (auto &t : job_threads)
         t.join();
     work_q.close();
     for (auto &t : workers)
