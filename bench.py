@@ -357,6 +357,7 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = {"hash_ms": 0.0, "dedup_ms": 0.0, "query_ms": 0.0, "query_bytes": 0, "hash_bytes": 0, "launches": 0, "query_launches": 0,
+             "probe_launches": 0,
              "query_items": 0, "n_hashes": 0}
     with torch.cuda.stream(stream):
         ev0.record()
@@ -367,6 +368,7 @@ def main():
                 stage[kname] += tm[kname]
             stage["launches"] += tm["hash_launches"] + tm["dedup_launches"] + tm["query_launches"]
             stage["query_launches"] += tm["query_launches"]
+            stage["probe_launches"] += tm["probe_launches"]
         ev1.record()
     barrier()
     clocks = sampler.stop()
@@ -410,11 +412,23 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         q_gbs = stage["query_bytes"] / (stage["query_ms"] / 1e3) / 1e9 if stage["query_ms"] > 0 else 0.0
+        # DRAM traffic of kernel #2 per launch: measured once per round with `ncu --set full` on this workload and
+        # stored as a ratio to the algorithmic bytes (profiles/query_traffic.json, written from the capture)
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "query_traffic.json")) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_algorithmic_byte"] * stage["query_bytes"] / max(stage["probe_launches"], 1)
+            traffic_src = tj.get("source")
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "ixf_query_small_kernel (kernel #2, all HIXF levels of a batch)",
                 "achieved": q_gbs, "peak": peak, "unit": "GB/s", "frac": q_gbs / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": None,
-                "avg_launch_ms": stage["query_ms"] / max(stage["query_launches"], 1),
+                "traffic": traffic, "traffic_source": traffic_src,
+                "avg_launch_ms": stage["query_ms"] / max(stage["probe_launches"], 1),
+                "launches_per_step": stage["probe_launches"] / args.steps,
+                "algorithmic_bytes_per_launch": stage["query_bytes"] / max(stage["probe_launches"], 1),
                 "algorithmic_bytes_per_step": stage["query_bytes"] / args.steps,
                 "stage_ms_per_step": {"hash": stage["hash_ms"] / args.steps, "dedup": stage["dedup_ms"] / args.steps,
                                       "query": stage["query_ms"] / args.steps}}
@@ -432,7 +446,7 @@ def main():
                 "reads_per_s": n_reads * world * args.steps / (resident_ms / 1e3),
                 "e2e": {"value": e2e_value, "unit": UNIT,
                         "h2d_bytes_per_step": int(pin.nbytes + off_pin.nbytes + len_pin.nbytes + 8 * (n_reads + 1)),
-                        "d2h_bytes_per_step": int(4 * n_reads + 12 * n_hits + 576 * ((n_reads + 131071) // 131072)),
+                        "d2h_bytes_per_step": int(4 * n_reads + 12 * n_hits + 576 * (-(-n_reads // (args.batch_reads or 262144)) + 2)),
                         "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "hits_per_step": n_hits,
                         "stage_ms_per_step_overlapped": {kk: tm_e2e[kk] for kk in ("h2d_ms", "hash_ms", "dedup_ms", "query_ms", "d2h_ms")}},
                 "gpu_launches": int(stage["launches"]),

@@ -44,7 +44,8 @@ class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("hash_ms", C.c_float), ("dedup_ms", C.c_float), ("query_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("query_launches", C.c_uint64),
                 ("hash_launches", C.c_uint64), ("dedup_launches", C.c_uint64), ("query_items", C.c_uint64),
-                ("query_bytes", C.c_uint64), ("hash_bytes", C.c_uint64), ("n_hashes", C.c_uint64)]
+                ("query_bytes", C.c_uint64), ("hash_bytes", C.c_uint64), ("n_hashes", C.c_uint64),
+                ("probe_launches", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -234,7 +235,7 @@ class Context:
     def set_stream(self, cuda_stream: int) -> None:
         _check(self._L.txr_ctx_set_stream(self._h, C.c_void_p(cuda_stream)))
 
-    def configure(self, max_batch_reads=131072, max_batch_bases=1_500_000_000, n_slots=3):
+    def configure(self, max_batch_reads=262144, max_batch_bases=3_000_000_000, n_slots=3):
         _check(self._L.txr_ctx_configure(self._h, max_batch_reads, max_batch_bases, n_slots))
 
     def upload_index(self, seed, bins, tbins, seg_len, data, bin_off, next_ixf_id, bin_to_ub, n_user_bins):

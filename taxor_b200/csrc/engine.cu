@@ -247,8 +247,8 @@ struct txr_ctx
 {
     int device{0};
     int sm_count{148};
-    uint64_t max_batch_reads{131072};
-    uint64_t max_batch_bases{1500000000ull};
+    uint64_t max_batch_reads{262144};
+    uint64_t max_batch_bases{3000000000ull};
     int n_slots{3};
     std::vector<std::unique_ptr<Slot>> slots;
     DeviceIndex index;
@@ -634,16 +634,19 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
                 CU(cudaMemsetAsync(rp.counts, 0, (size_t)m.n_reads * ix.ixf[0].tbins * 2, cs));
                 CU(launch_root_partitioned(q, rp, c->sm_count, cs));
                 c->timing.query_launches += 5;
+                c->timing.probe_launches += 1;
             }
             else if (ix.ixf[0].tbins <= kSmallRowBytes)
             {
                 CU(launch_query_small(q, c->sm_count, cs));
                 c->timing.query_launches += 1;
+                c->timing.probe_launches += 1;
             }
             else
             {
                 CU(launch_query_large(q, c->sm_count, ix.max_tbins, cs));
                 c->timing.query_launches += 1;
+                c->timing.probe_launches += 1;
             }
         }
         else
@@ -661,6 +664,7 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
             q.cursor = lc + 2;
             CU(launch_query_small(q, c->sm_count, cs));
             c->timing.query_launches += c->sort_items ? 4 : 1;
+            c->timing.probe_launches += 1;
             if (ix.any_large)
             {
                 sorted += s.queue_cap;
@@ -672,6 +676,7 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
                 q.cursor = lc + 3;
                 CU(launch_query_large(q, c->sm_count, ix.max_tbins, cs));
                 c->timing.query_launches += c->sort_items ? 4 : 1;
+                c->timing.probe_launches += 1;
             }
         }
     }
