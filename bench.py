@@ -89,6 +89,8 @@ def make_genomes(args, rank=0, barrier=None):
         mm.flush()
         del mm
         open(done, "w").close()
+    while not os.path.exists(done):
+        time.sleep(0.5)
     if barrier is not None:
         barrier()
     mm = np.load(path, mmap_mode="r")
@@ -118,7 +120,8 @@ def build_index_arrays(args, genomes, lens, ctx):
         for i in range(len(part)):
             ub.append(h[int(o[i]):int(o[i + 1])])
     t1 = time.time()
-    hx = tools.BuiltHixf(ub, t_max=args.t_max, seed=1, inplace=True)
+    # explicit thread count: torchrun exports OMP_NUM_THREADS=1, which would make the CPU peeling take half an hour
+    hx = tools.BuiltHixf(ub, t_max=args.t_max, seed=1, inplace=True, threads=os.cpu_count() or 1)
     del ub
     t2 = time.time()
     info = dict(hash_s=round(t1 - t0, 2), build_s=round(t2 - t1, 2), n_ixf=hx.n_ixf, fp_bytes=hx.fp_bytes,
@@ -174,8 +177,10 @@ def make_reads(args, genomes, lens, rank):
     nw_per = tools.packed_words(args.read_len)
     pin = capi.PinnedArray(n * nw_per, np.uint64)
     pin.array[:] = 0
+    world = int(os.environ.get("WORLD_SIZE", 1))
     words, off, ln, src = tools.simulate_reads(genomes, lens, np.full(n, args.read_len, np.uint32), args.read_error,
-                                               seed=42 + 7919 * rank, out_words=pin.array)
+                                               seed=42 + 7919 * rank, out_words=pin.array,
+                                               threads=max(1, (os.cpu_count() or 1) // world))
     off_pin = capi.PinnedArray(n, np.uint64)
     off_pin.array[:] = off
     len_pin = capi.PinnedArray(n, np.uint32)
@@ -287,7 +292,8 @@ def main():
     dist = None
     if world > 1 and args.impl == "ours":
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=60))
 
     ctx = capi.Context(local_rank)
     genomes, lens = make_genomes(args, rank, dist.barrier if dist is not None else None)
@@ -298,6 +304,8 @@ def main():
         hx, info = build_index_arrays(args, genomes, lens, ctx)
         save_index(hx, d, info)
         hx.close()
+    while not os.path.exists(done):          # the other ranks sleep (no spinning collective) while rank 0 builds
+        time.sleep(1.0)
     if dist is not None:
         dist.barrier()
     ix = LoadedIndex(d)
@@ -357,7 +365,7 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = {"hash_ms": 0.0, "dedup_ms": 0.0, "query_ms": 0.0, "query_bytes": 0, "hash_bytes": 0, "launches": 0, "query_launches": 0,
-             "probe_launches": 0,
+             "probe_launches": 0, "skipped_hashes": 0,
              "query_items": 0, "n_hashes": 0}
     with torch.cuda.stream(stream):
         ev0.record()
@@ -369,6 +377,7 @@ def main():
             stage["launches"] += tm["hash_launches"] + tm["dedup_launches"] + tm["query_launches"]
             stage["query_launches"] += tm["query_launches"]
             stage["probe_launches"] += tm["probe_launches"]
+            stage["skipped_hashes"] += tm["skipped_hashes"]
         ev1.record()
     barrier()
     clocks = sampler.stop()
@@ -430,6 +439,9 @@ def main():
                 "launches_per_step": stage["probe_launches"] / args.steps,
                 "algorithmic_bytes_per_launch": stage["query_bytes"] / max(stage["probe_launches"], 1),
                 "algorithmic_bytes_per_step": stage["query_bytes"] / args.steps,
+                "bytes_note": "bytes of the probes actually issued (Hp*3*tbins + 8*Hp per visited IXF); probes saved by the exact "
+                              "early exit are NOT counted",
+                "early_exit_skipped_hashes_per_step": stage["skipped_hashes"] / args.steps,
                 "stage_ms_per_step": {"hash": stage["hash_ms"] / args.steps, "dedup": stage["dedup_ms"] / args.steps,
                                       "query": stage["query_ms"] / args.steps}}
         cpu = None

@@ -93,9 +93,11 @@ typedef struct
     float h2d_ms, hash_ms, dedup_ms, query_ms, d2h_ms, total_ms;
     uint64_t query_launches, hash_launches, dedup_launches;
     uint64_t query_items;              /* (read, IXF) work items processed                                  */
-    uint64_t query_bytes;              /* sum over items of H*3*tbins + 8*H   (SURVEY 8(d) algorithmic bytes) */
+    uint64_t query_bytes;              /* sum over items of Hp*3*tbins + 8*Hp, Hp = hashes actually probed (= H, SURVEY 8(d), without early exits) */
     uint64_t hash_bytes;               /* sum over reads of ceil(L/4) + 8*H_raw                              */
     uint64_t n_hashes;                 /* sum of hash_count                                                  */
+    uint64_t skipped_hashes;           /* probes the early exit of kernel #2 saved (an item stops once no user bin can
+                                          reach the read's threshold any more); their bytes are NOT in query_bytes   */
     uint64_t probe_launches;           /* launches of the probe kernels alone (query_launches also counts the
                                           small queue-grouping kernels between levels)                        */
 } txr_timing;

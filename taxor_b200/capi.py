@@ -45,7 +45,7 @@ class Timing(C.Structure):
                 ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("query_launches", C.c_uint64),
                 ("hash_launches", C.c_uint64), ("dedup_launches", C.c_uint64), ("query_items", C.c_uint64),
                 ("query_bytes", C.c_uint64), ("hash_bytes", C.c_uint64), ("n_hashes", C.c_uint64),
-                ("probe_launches", C.c_uint64)]
+                ("skipped_hashes", C.c_uint64), ("probe_launches", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

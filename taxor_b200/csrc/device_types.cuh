@@ -50,6 +50,7 @@ struct IxfDev
     uint32_t tbins;            // row stride in bytes
     uint32_t bins;             // counting-vector size
     uint32_t meta_off;         // first entry of this IXF in the per-bin metadata arrays
+    uint32_t max_run;          // longest run of technical bins that belong to one user bin (>= 1)
 };
 
 enum : uint8_t { kBinMid = 0, kBinRunEnd = 1, kBinMerged = 2 };
@@ -87,9 +88,11 @@ struct QueryArgs
     uint32_t *n_hits;
     uint32_t hit_cap;
 
+    uint32_t early_exit;            // 1: stop probing an item once no user bin can reach the threshold any more
     uint32_t l2_hints;              // 1: items are grouped by IXF, use the L2 eviction-priority plan (query_kernels.cu)
     unsigned long long *stat_bytes; // algorithmic bytes: sum H*3*tbins + 8*H
     unsigned long long *stat_items;
+    unsigned long long *stat_skipped; // hashes NOT probed thanks to the early exit (their bytes are not in stat_bytes)
 };
 
 // ---- kernel #2, root level of a batch, slot-partitioned (query_kernels.cu: "partitioned root") ----

@@ -189,8 +189,8 @@ enum CounterSlot : int
     C_LEVEL0 = 8, // per level: n_small, n_large, cursor_small, cursor_large
     C_PER_LEVEL = 4,
     C_MAX_LEVELS = 32,
-    C_STATS = C_LEVEL0 + C_PER_LEVEL * C_MAX_LEVELS, // two u64: bytes, items (8-byte aligned: index is even)
-    C_TOTAL = C_STATS + 4
+    C_STATS = C_LEVEL0 + C_PER_LEVEL * C_MAX_LEVELS, // three u64: bytes, items, skipped hashes (8-byte aligned: index is even)
+    C_TOTAL = C_STATS + 6
 };
 
 struct Slot
@@ -257,6 +257,7 @@ struct txr_ctx
     Thresholder thresholder;
     uint64_t kmer_seed{0};
     bool sort_items{true};     // group level queues by IXF (TXR_SORT_ITEMS=0 disables, for A/B measurements)
+    bool early_exit{true};     // exact early exit of kernel #2 (TXR_EARLY_EXIT=0 disables)
     bool l2_hints{true};       // L2 eviction-priority plan for small child IXFs (TXR_L2_HINTS=0 disables)
     int root_partition{0};     // root level grouped by segment-0 slot: 0 off (default: measured slower), 1 auto, 2 always (TXR_ROOT_PARTITION)
     bool per_read_thr{false};  // FracMinHash model: the threshold depends on hash_count AND the read length
@@ -594,6 +595,8 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
     q.next_cap = s.queue_cap;
     q.stat_bytes = reinterpret_cast<unsigned long long *>(cnt + C_STATS);
     q.stat_items = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 2);
+    q.stat_skipped = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 4);
+    q.early_exit = c->early_exit;
     uint2 *queues = s.queues.as<uint2>();
     const uint32_t levels = std::min<uint32_t>(ix.depth, C_MAX_LEVELS);
     for (uint32_t lv = 0; lv < levels; ++lv)
@@ -786,10 +789,11 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
     }
     const uint32_t *hc = s.h_counters.as<uint32_t>();
     const uint32_t n_hits = hc[C_NHITS];
-    uint64_t stats[2];
-    memcpy(stats, hc + C_STATS, 16);
+    uint64_t stats[3];
+    memcpy(stats, hc + C_STATS, 24);
     c->timing.query_bytes += stats[0];
     c->timing.query_items += stats[1];
+    c->timing.skipped_hashes += stats[2];
 
     float ms = 0;
     cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]);
@@ -978,6 +982,8 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->hash_ctas = atoi(e);
     if (const char *e = getenv("TXR_DEDUP_CTAS_PER_SM"))
         c->dedup_ctas = atoi(e);
+    if (const char *e = getenv("TXR_EARLY_EXIT"))
+        c->early_exit = atoi(e) != 0;
     if (const char *e = getenv("TXR_L2_HINTS"))
         c->l2_hints = atoi(e) != 0;
     if (const char *e = getenv("TXR_ROOT_PARTITION"))
@@ -1071,7 +1077,7 @@ int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
                              (unsigned long long)x.tbins);
         arena_off[i] = arena_bytes;
         arena_bytes += (3 * x.seg_len * dev_tbins + 255) / 256 * 256;
-        ix.ixf[i] = IxfDev{nullptr, x.seed, (uint32_t)x.seg_len, (uint32_t)dev_tbins, (uint32_t)x.bins, (uint32_t)v->bin_off[i]};
+        ix.ixf[i] = IxfDev{nullptr, x.seed, (uint32_t)x.seg_len, (uint32_t)dev_tbins, (uint32_t)x.bins, (uint32_t)v->bin_off[i], 1u};
         ix.max_tbins = std::max<uint32_t>(ix.max_tbins, (uint32_t)dev_tbins);
         ix.any_large = ix.any_large || dev_tbins > kSmallRowBytes;
         ix.fp_bytes += 3 * x.seg_len * dev_tbins;
@@ -1123,7 +1129,10 @@ int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
                 child[o + b] = -1;
                 run_begin[o + b] = run_start;
                 if (end)
+                {
+                    ix.ixf[i].max_run = std::max<uint32_t>(ix.ixf[i].max_run, (uint32_t)b + 1 - run_start);
                     run_start = (uint32_t)b + 1;
+                }
             }
         }
     }

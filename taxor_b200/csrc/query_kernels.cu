@@ -152,10 +152,29 @@ __device__ __forceinline__ void acc_flush(uint32_t (&acc)[4], uint32_t *cnt16)
 //   chunk_off : first byte (bin) of the chunk inside a row, multiple of 16
 //   lpr       : lanes per row for this chunk (chunk bytes / 16), 1..32
 //   cnt       : shared counters of the chunk's first bin
+// Early exit (exact).  A hit or a descent needs a run of technical bins (one user bin, or one merged bin) whose
+// counts sum to >= thr.  After h of H hashes a run of at most max_run bins holds at most
+// max_run * (largest bin count so far + (H - h)), because every remaining hash adds at most 1 to each of its bins.
+// Once that is below thr nothing of this item can be reported or descended into, so the remaining probes cannot
+// change the output and are skipped (the reference computes them, hixf.hpp:307-309, and throws the counts away).
+// Typical: a read of an organism that is not in the index stops after (1 - ratio) of its hashes.  The bound uses
+// the lane-local byte counters (times the G hash slots that share a bin) plus the flushed shared counters.
+__device__ __forceinline__ uint32_t max_byte4(const uint32_t (&acc)[4])
+{
+    const uint32_t t = __vmaxu4(__vmaxu4(acc[0], acc[1]), __vmaxu4(acc[2], acc[3]));
+    return max(max(t & 0xffu, (t >> 8) & 0xffu), max((t >> 16) & 0xffu, t >> 24));
+}
+
+// One warp probes all hashes of a read against a column chunk of an IXF.
+//   chunk_off : first byte (bin) of the chunk inside a row, multiple of 16
+//   lpr       : lanes per row for this chunk (chunk bytes / 16), 1..32
+//   cnt       : shared counters of the chunk's first bin
+//   exit_thr  : != 0: the chunk is the whole row and the item may stop early against this threshold
+// Returns the number of hashes probed.
 template <int UNROLL>
-__device__ __forceinline__ void probe_chunk(const IxfDev &d, const uint64_t *__restrict__ hp, uint32_t H,
-                                            uint32_t chunk_off, uint32_t lpr, uint32_t *cnt, int lane,
-                                            const L2Plan &l2 = L2Plan{false, 0, 0})
+__device__ __forceinline__ uint32_t probe_chunk(const IxfDev &d, const uint64_t *__restrict__ hp, uint32_t H,
+                                                uint32_t chunk_off, uint32_t lpr, uint32_t *cnt, int lane,
+                                                const L2Plan &l2 = L2Plan{false, 0, 0}, uint64_t exit_thr = 0)
 {
     const uint32_t G = 32u / lpr;         // hashes per step
     const uint32_t sub = (uint32_t)lane / lpr;
@@ -164,6 +183,13 @@ __device__ __forceinline__ void probe_chunk(const IxfDev &d, const uint64_t *__r
     const uint8_t *col_base = d.fp + chunk_off + 16u * col;
     uint32_t acc[4] = {0, 0, 0, 0};
     uint32_t steps = 0;
+    // first hash index at which even all-zero counts could rule the item out: max_run * (H - h) < thr
+    const uint64_t slack = exit_thr ? (exit_thr - 1) / d.max_run : 0;
+    if (exit_thr && slack >= H)
+        return 0; // max_run * H < thr: hopeless before the first probe (e.g. the k-mer model's wrapped thresholds)
+    uint32_t next_check = exit_thr ? H - (uint32_t)slack : 0xffffffffu;
+    bool flushed = false;
+    uint32_t probed = H;
     Probe pr[UNROLL];
     for (uint32_t h0 = 0; h0 < H; h0 += G * UNROLL)
     {
@@ -179,15 +205,36 @@ __device__ __forceinline__ void probe_chunk(const IxfDev &d, const uint64_t *__r
         for (int u = 0; u < UNROLL; ++u)
             probe_reduce(pr[u], acc);
         steps += UNROLL;
+        const uint32_t done = h0 + G * UNROLL;
+        if (done >= next_check && done < H)
+        {
+            uint32_t m = __reduce_max_sync(0xffffffffu, max_byte4(acc)) * G;
+            if (flushed)
+            {
+                uint32_t ms = 0;
+                for (uint32_t i = lane; i < lpr * 16u; i += 32)
+                    ms = max(ms, cnt[i]);
+                m += __reduce_max_sync(0xffffffffu, ms);
+            }
+            if ((uint64_t)d.max_run * ((uint64_t)m + (H - done)) < exit_thr)
+            {
+                probed = done;
+                break;
+            }
+            next_check = done + 4 * G * UNROLL;
+        }
         if (steps + UNROLL > 255)
         {
             if (active)
                 acc_flush(acc, cnt + 16u * col);
+            __syncwarp();
+            flushed = true;
             steps = 0;
         }
     }
     if (active)
         acc_flush(acc, cnt + 16u * col);
+    return probed;
 }
 
 // bin scan of hixf.hpp:311-339 for one (read, IXF) from the shared counters; warp- or block-wide
@@ -282,7 +329,7 @@ __global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(Query
         cnt[i] = 0;
     __syncwarp();
     const uint32_t n_items = a.items ? *a.n_items_ptr : a.n_items_direct;
-    unsigned long long bytes = 0, items = 0;
+    unsigned long long bytes = 0, items = 0, skipped = 0;
     while (true)
     {
         uint32_t it = 0;
@@ -302,20 +349,24 @@ __global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(Query
         const uint32_t H = a.hash_count[read];
         const uint64_t *hp = a.hashes + a.hash_off[read];
         const uint64_t thr = a.thr_read ? a.thr_read[read] : (H < a.lut_len ? a.thr_lut[H] : ~0ULL);
-        probe_chunk<kQueryUnroll>(d, hp, H, 0u, d.tbins >> 4, cnt, lane, l2_plan_for(d, a.l2_hints != 0));
+        const uint32_t Hp = probe_chunk<kQueryUnroll>(d, hp, H, 0u, d.tbins >> 4, cnt, lane, l2_plan_for(d, a.l2_hints != 0),
+                                                      a.early_exit ? thr : 0);
         __syncwarp();
         scan_bins(a, d, read, thr, cnt, (uint32_t)lane, 32u);
         __syncwarp();
         for (uint32_t i = lane; i < d.tbins; i += 32)
             cnt[i] = 0;
         __syncwarp();
-        bytes += (unsigned long long)H * 3ull * d.tbins + 8ull * H;
+        bytes += (unsigned long long)Hp * 3ull * d.tbins + 8ull * Hp;
+        skipped += H - Hp;
         ++items;
     }
     if (lane == 0 && items)
     {
         atomicAdd(a.stat_bytes, bytes);
         atomicAdd(a.stat_items, items);
+        if (skipped)
+            atomicAdd(a.stat_skipped, skipped);
     }
 }
 

@@ -161,6 +161,22 @@ def test_search_parity_syncmer(ctx, oracle, t_max, n_genomes):
     H.assert_same_search(res2, ora, reads.n)
 
 
+def test_early_exit_is_exact_and_taken(ctx, oracle):
+    """reads that match nothing stop probing once no bin can reach the threshold: same output, fewer probes"""
+    ds = H.make_dataset(oracle, n_genomes=60, genome_len=40_000, t_max=64)
+    rng = np.random.default_rng(31)
+    foreign = [rng.integers(0, 4, int(n), dtype=np.uint8) for n in rng.integers(2000, 12000, 150)]   # not in the index
+    own = H.make_reads(ds, rng.integers(2000, 12000, 150), err=0.03)
+    seqs = foreign + [capi.unpack_codes(own, i) for i in range(own.n)]
+    order = rng.permutation(len(seqs))
+    reads = capi.pack_codes([seqs[i] for i in order])
+    for er in (0.05, 0.1):
+        res, ora = _search_case(ctx, oracle, ds, reads, error_rate=er)
+        tm = ctx.timing()
+        assert int(res.hit_begin[-1]) > 50
+        assert tm["skipped_hashes"] > 0.2 * sum(len(x) for x in foreign) / 11 * 0.5, tm
+
+
 def test_search_threshold_zero_flood(ctx, oracle):
     """H5: reads shorter than k have hash_count 0 -> threshold 0 -> every user bin reported, every merged bin descended."""
     ds = H.make_dataset(oracle, n_genomes=30, genome_len=30_000, t_max=4)
