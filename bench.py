@@ -32,6 +32,18 @@ METRIC = "taxor search Mbases/s (syncmer hash+HIXF query)"
 UNIT = "Mbases/s"
 K, S, T = 22, 12, 5
 
+# The headline workload is configs[1].  The other BASELINE configs can be run at full size with --workload (extra
+# evidence lines under profiles/, not the driver's bench line): their parameters override the defaults below.
+WORKLOADS = {
+    "configs1": dict(label="configs[1]"),
+    # configs[3]: plain canonical 20-mers (no syncmers, duplicates kept, k-mer-model threshold), viral-scale index,
+    # read lengths log-uniform in [1 kb, 50 kb]
+    "kmer": dict(label="configs[3]", k=20, s=0, t=0, use_syncmer=False, genomes=5000, genome_len=150_000, min_genome_len=60_000,
+                 t_max=128, read_len_range=(1000, 50_000), read_error=0.03, error_rate=0.05),
+    # configs[4] shape at 1/10 of its size: 20,000 genomes under t_max=64 give a three-level hierarchy
+    "deep": dict(label="configs[4] shape (three-level hierarchy, 10 GB)", genomes=20000, genome_len=2_000_000, t_max=64),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -39,6 +51,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="configs1", choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=int(os.environ.get("TAXOR_BENCH_READS", 1_000_000)), help="reads per GPU per step")
     ap.add_argument("--read-len", type=int, default=10_000)
     ap.add_argument("--genomes", type=int, default=int(os.environ.get("TAXOR_BENCH_GENOMES", 1000)))
@@ -52,29 +65,40 @@ def parse_args():
     ap.add_argument("--batch-reads", type=int, default=int(os.environ.get("TAXOR_BENCH_BATCH_READS", 0)),
                     help="reads per internal batch (0: library default)")
     ap.add_argument("--cache", default=os.environ.get("TAXOR_BENCH_CACHE", "/dev/shm/taxor_b200_bench"))
-    return ap.parse_args()
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    args.k, args.s, args.t, args.use_syncmer = w.get("k", K), w.get("s", S), w.get("t", T), w.get("use_syncmer", True)
+    args.window = 20 if args.use_syncmer else args.k
+    args.min_genome_len = w.get("min_genome_len", 20_000)
+    args.read_len_range = w.get("read_len_range")
+    args.label = w["label"]
+    explicit = {a.split("=")[0] for a in sys.argv[1:] if a.startswith("--")}
+    for key in ("genomes", "genome_len", "t_max", "read_error", "error_rate"):
+        if key in w and "--" + key.replace("_", "-") not in explicit:
+            setattr(args, key, w[key])
+    return args
 
 
 # ----------------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------------
-def genome_lengths(n, mean, seed=7):
+def genome_lengths(n, mean, seed=7, min_len=20_000):
     """RefSeq-ABFV-like size mix: log-uniform over a 16x range around the mean (small 'viral' to large genomes)."""
     rng = np.random.default_rng(seed)
     x = np.exp(rng.uniform(np.log(0.25), np.log(4.0), n))
     x = x / x.mean() * mean
-    return np.maximum(x.astype(np.int64), 20_000)
+    return np.maximum(x.astype(np.int64), min_len)
 
 
 def make_genomes(args, rank=0, barrier=None):
     """Packed synthetic genomes, generated once (rank 0) into a /dev/shm file that every rank maps: at the default
     size they are 10 GB, too much to hold once per rank."""
     from taxor_b200 import tools
-    lens = genome_lengths(args.genomes, args.genome_len)
+    lens = genome_lengths(args.genomes, args.genome_len, min_len=getattr(args, "min_genome_len", 20_000))
     nw = np.array([tools.packed_words(int(x)) for x in lens], dtype=np.uint64)
     off = np.zeros(args.genomes + 1, dtype=np.uint64)
     off[1:] = np.cumsum(nw)
-    d = os.path.join(args.cache, f"genomes_g{args.genomes}_l{args.genome_len}")
+    d = os.path.join(args.cache, f"genomes_g{args.genomes}_l{args.genome_len}_m{getattr(args, 'min_genome_len', 20_000)}")
     path, done = os.path.join(d, "words.bin"), os.path.join(d, "DONE")
     if rank == 0 and not os.path.exists(done):
         os.makedirs(d, exist_ok=True)
@@ -98,7 +122,7 @@ def make_genomes(args, rank=0, barrier=None):
 
 
 def index_cache_paths(args):
-    tag = f"g{args.genomes}_l{args.genome_len}_t{args.t_max}_k{K}s{S}"
+    tag = f"g{args.genomes}_l{args.genome_len}_m{getattr(args, 'min_genome_len', 20_000)}_t{args.t_max}_k{getattr(args, 'k', K)}s{getattr(args, 's', S)}"
     d = os.path.join(args.cache, tag)
     return d, os.path.join(d, "DONE")
 
@@ -108,7 +132,7 @@ def build_index_arrays(args, genomes, lens, ctx):
     from taxor_b200 import capi, tools
     t0 = time.time()
     ub = []
-    ctx.set_params(k=K, s=S, t=T, use_syncmer=True, window_size=20, error_rate=args.error_rate)
+    ctx.set_params(k=args.k, s=args.s, t=args.t, use_syncmer=args.use_syncmer, window_size=args.window, error_rate=args.error_rate)
     chunk = 64
     for a in range(0, len(genomes), chunk):
         part = genomes[a:a + chunk]
@@ -162,6 +186,13 @@ class LoadedIndex:
             self.info = json.load(f)
         self.n_user_bins = self.info["n_user_bins"]
         self.n_ixf = len(self.seed)
+        # tree depth: children are created after their parent, so one forward pass over the merged bins is enough
+        level = np.ones(self.n_ixf, dtype=np.int64)
+        for i in range(self.n_ixf):
+            a, b = int(self.bin_off[i]), int(self.bin_off[i + 1])
+            ch = self.next_ixf_id[a:b][self.bin_to_ub[a:b] < 0]
+            level[ch] = level[i] + 1
+        self.depth = int(level.max())
         self.fp_bytes = int(sizes.sum())
 
 
@@ -174,11 +205,15 @@ def make_reads(args, genomes, lens, rank):
     """This rank's shard of the read set, simulated straight into pinned host memory."""
     from taxor_b200 import capi, tools
     n = args.reads
-    nw_per = tools.packed_words(args.read_len)
-    pin = capi.PinnedArray(n * nw_per, np.uint64)
+    if args.read_len_range:
+        lo, hi = args.read_len_range
+        rl = np.exp(np.random.default_rng(1234 + rank).uniform(np.log(lo), np.log(hi), n)).astype(np.uint32)
+    else:
+        rl = np.full(n, args.read_len, np.uint32)
+    pin = capi.PinnedArray(int(((rl.astype(np.uint64) + 31) // 32 + 1).sum()), np.uint64)
     pin.array[:] = 0
     world = int(os.environ.get("WORLD_SIZE", 1))
-    words, off, ln, src = tools.simulate_reads(genomes, lens, np.full(n, args.read_len, np.uint32), args.read_error,
+    words, off, ln, src = tools.simulate_reads(genomes, lens, rl, args.read_error,
                                                seed=42 + 7919 * rank, out_words=pin.array,
                                                threads=max(1, (os.cpu_count() or 1) // world))
     off_pin = capi.PinnedArray(n, np.uint64)
@@ -263,7 +298,8 @@ def cpu_run(args, ix, pin_words, off, ln, n_sample, threads):
         at += len(c)
         coff[i + 1] = at
     t0 = time.perf_counter()
-    res = o.search_batch(h, codes, coff, k=K, s=S, t=T, use_syncmer=True, window_size=20, error_rate=args.error_rate,
+    res = o.search_batch(h, codes, coff, k=args.k, s=args.s, t=args.t, use_syncmer=args.use_syncmer, window_size=args.window,
+                         error_rate=args.error_rate,
                          threads=threads, want_raw=False)
     dt = time.perf_counter() - t0
     return at / dt / 1e6, dt, res
@@ -310,16 +346,19 @@ def main():
         dist.barrier()
     ix = LoadedIndex(d)
     upload_index(ctx, ix)
-    ctx.set_params(k=K, s=S, t=T, use_syncmer=True, window_size=20, error_rate=args.error_rate)
+    ctx.set_params(k=args.k, s=args.s, t=args.t, use_syncmer=args.use_syncmer, window_size=args.window, error_rate=args.error_rate)
 
     pin, off_pin, len_pin = make_reads(args, genomes, lens, rank)
     n_reads = args.reads
     bases_per_step = int(len_pin.array.astype(np.uint64).sum())
     reads = capi.PackedReads(pin.array, off_pin.array, len_pin.array)
 
-    workload = {"workload": f"configs[1]: {args.genomes} synthetic genomes (mean {args.genome_len} bp, 16x log-uniform size mix), "
-                            f"k={K} s={S} t={T} syncmers, HIXF t_max={args.t_max} ({ix.n_ixf} IXFs, {ix.fp_bytes / 1e9:.2f} GB fingerprints); "
-                            f"{n_reads} reads x {args.read_len} bp per GPU, {args.read_error:.0%} error, --error-rate {args.error_rate}",
+    mode = f"k={args.k} s={args.s} t={args.t} syncmers" if args.use_syncmer else f"canonical {args.k}-mers (no syncmers, duplicates kept)"
+    rl_txt = (f"{args.read_len_range[0]}-{args.read_len_range[1]} bp (log-uniform, mean {bases_per_step // n_reads})" if args.read_len_range
+              else f"{args.read_len} bp")
+    workload = {"workload": f"{args.label}: {args.genomes} synthetic genomes (mean {args.genome_len} bp, 16x log-uniform size mix), "
+                            f"{mode}, HIXF t_max={args.t_max} ({ix.n_ixf} IXFs, {ix.depth} levels, {ix.fp_bytes / 1e9:.2f} GB fingerprints); "
+                            f"{n_reads} reads x {rl_txt} per GPU, {args.read_error:.0%} error, --error-rate {args.error_rate}",
                 "reads_per_gpu": n_reads, "read_len": args.read_len, "index_bytes": ix.fp_bytes,
                 "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective",
                 "l2": "inputs larger than L2 (packed reads and index each exceed 126 MB); no flush needed"}
@@ -355,7 +394,8 @@ def main():
         torch.cuda.synchronize()
 
     # (1) device-resident: kernels only.  One pipeline slot so that the per-stage CUDA events are not overlapped
-    batch_kw = dict(max_batch_reads=args.batch_reads, max_batch_bases=int(args.batch_reads * args.read_len * 1.1)) if args.batch_reads else {}
+    mean_len = max(1, bases_per_step // max(n_reads, 1))
+    batch_kw = dict(max_batch_reads=args.batch_reads, max_batch_bases=int(args.batch_reads * mean_len * 1.1)) if args.batch_reads else {}
     ctx.configure(n_slots=int(os.environ.get("TAXOR_BENCH_RESIDENT_SLOTS", 1)), **batch_kw)
     h = ctx.upload_reads(reads)
     for _ in range(args.warmup):
@@ -452,7 +492,7 @@ def main():
             v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"first {n_s} of the {n_reads} reads, {dt:.1f} s (restated CPU path with OpenMP over reads; not the reference binary)"}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": METRIC if args.use_syncmer else METRIC.replace("syncmer hash", "k-mer hash"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": workload,
                 "reads_per_s": n_reads * world * args.steps / (resident_ms / 1e3),

@@ -163,7 +163,7 @@ def test_search_parity_syncmer(ctx, oracle, t_max, n_genomes):
 
 def test_early_exit_is_exact_and_taken(ctx, oracle):
     """reads that match nothing stop probing once no bin can reach the threshold: same output, fewer probes"""
-    ds = H.make_dataset(oracle, n_genomes=60, genome_len=40_000, t_max=64)
+    ds = H.make_dataset(oracle, n_genomes=100, genome_len=30_000, t_max=64)   # > t_max genomes: no split bins in the root
     rng = np.random.default_rng(31)
     foreign = [rng.integers(0, 4, int(n), dtype=np.uint8) for n in rng.integers(2000, 12000, 150)]   # not in the index
     own = H.make_reads(ds, rng.integers(2000, 12000, 150), err=0.03)
@@ -174,7 +174,8 @@ def test_early_exit_is_exact_and_taken(ctx, oracle):
         res, ora = _search_case(ctx, oracle, ds, reads, error_rate=er)
         tm = ctx.timing()
         assert int(res.hit_begin[-1]) > 50
-        assert tm["skipped_hashes"] > 0.2 * sum(len(x) for x in foreign) / 11 * 0.5, tm
+        # a foreign read stops after about (1 - ratio) of its ~L/11 hashes: ratio 0.44 / 0.23 for these error rates
+        assert tm["skipped_hashes"] > 0.1 * sum(len(x) for x in foreign) / 11, tm
 
 
 def test_search_threshold_zero_flood(ctx, oracle):
