@@ -396,7 +396,7 @@ def main():
     # (1) device-resident: kernels only.  One pipeline slot so that the per-stage CUDA events are not overlapped
     mean_len = max(1, bases_per_step // max(n_reads, 1))
     batch_kw = dict(max_batch_reads=args.batch_reads, max_batch_bases=int(args.batch_reads * mean_len * 1.1)) if args.batch_reads else {}
-    ctx.configure(n_slots=int(os.environ.get("TAXOR_BENCH_RESIDENT_SLOTS", 1)), **batch_kw)
+    ctx.configure(n_slots=int(os.environ.get("TAXOR_BENCH_RESIDENT_SLOTS", 2)), **batch_kw)
     h = ctx.upload_reads(reads)
     for _ in range(args.warmup):
         ctx.search_resident(h, fetch=False)
@@ -447,6 +447,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms.item())
     tm_e2e = ctx.timing()
+    gpu_result = capi.SearchResult(r) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None  # copy: the view dies with the next call
 
     total_bases = bases_per_step * world
     value = total_bases * args.steps / (resident_ms / 1e3) / 1e6
@@ -484,14 +485,28 @@ def main():
                 "early_exit_skipped_hashes_per_step": stage["skipped_hashes"] / args.steps,
                 "stage_ms_per_step": {"hash": stage["hash_ms"] / args.steps, "dedup": stage["dedup_ms"] / args.steps,
                                       "query": stage["query_ms"] / args.steps}}
-        cpu = None
+        cpu, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
             n_s = min(n_reads, 1000)
             v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
             n_s = int(min(n_reads, max(200, n_s * args.cpu_seconds / max(dt, 1e-3))))
-            v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
+            v, dt, ora = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"first {n_s} of the {n_reads} reads, {dt:.1f} s (restated CPU path with OpenMP over reads; not the reference binary)"}
+            # parity at full size, for free: the oracle's answers for the CPU sample against the GPU's answers for the same reads
+            g = gpu_result
+            nh = int(g.hit_begin[n_s])
+            keep = g.keep[:nh]
+            kept_per_read = np.concatenate([[0], np.cumsum(keep)])[g.hit_begin[: n_s + 1].astype(np.int64)]
+            parity = {"reads": n_s,
+                      "hash_count_mismatches": int(np.count_nonzero(g.hash_count[:n_s] != ora["hash_count"])),
+                      "threshold_mismatches": int(np.count_nonzero(g.threshold[:n_s] != ora["threshold"])),
+                      "hit_offsets_equal": bool(np.array_equal(kept_per_read.astype(np.uint64), ora["hit_off"])),
+                      "hit_user_bins_equal": bool(np.array_equal(g.user_bin[:nh][keep], ora["ub"])),
+                      "hit_counts_equal": bool(np.array_equal(g.count[:nh][keep], ora["cnt"])),
+                      "reported_hits": int(len(ora["ub"]))}
+            parity["ok"] = (parity["hash_count_mismatches"] == 0 and parity["threshold_mismatches"] == 0 and parity["hit_offsets_equal"]
+                            and parity["hit_user_bins_equal"] and parity["hit_counts_equal"])
         line = {"metric": METRIC if args.use_syncmer else METRIC.replace("syncmer hash", "k-mer hash"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": workload,
@@ -502,9 +517,12 @@ def main():
                         "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "hits_per_step": n_hits,
                         "stage_ms_per_step_overlapped": {kk: tm_e2e[kk] for kk in ("h2d_ms", "hash_ms", "dedup_ms", "query_ms", "d2h_ms")}},
                 "gpu_launches": int(stage["launches"]),
-                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                "roofline": roof, "cpu_baseline": cpu, "parity_at_scale": parity, "clocks": clocks,
                 "index_build": ix.info, "host_cores": cores}
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            print("PARITY FAILURE at full size: " + json.dumps(parity), file=sys.stderr)
+            sys.exit(3)
     pin.free()
     off_pin.free()
     len_pin.free()

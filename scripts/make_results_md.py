@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Prints the measured-results block of DESIGN.md section 6 from the JSON lines kept under profiles/ (so the numbers in the
+text are the numbers in the files).  Usage: python scripts/make_results_md.py > /tmp/results.md"""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+
+
+def load(name):
+    path = os.path.join(P, name)
+    if not os.path.exists(path):
+        return None
+    txt = open(path).read().strip()
+    return json.loads(txt.splitlines()[-1]) if txt else None
+
+
+def bench_row(tag, d):
+    r, e = d["roofline"], d["e2e"]
+    st = r["stage_ms_per_step"]
+    cpu = d.get("cpu_baseline") or {}
+    return (f"| {tag} | {d['value'] / 1e3:.1f} | {d['ms_per_step']:.1f} | {st['hash']:.1f} / {st['dedup']:.1f} / {st['query']:.1f} | "
+            f"{e['value'] / 1e3:.1f} | {e['ms_per_step']:.1f} | {r['achieved']:.0f} | {r['frac']:.3f} | "
+            f"{(cpu.get('value') or 0) / 1e3:.2f} ({cpu.get('cores', '-')} cores) |")
+
+
+def main():
+    out = []
+    final = load("r1_final_bench.json")
+    if final:
+        out.append("| workload (1 × B200) | value Gbases/s | ms/step | hash / dedup / query ms | e2e Gbases/s | e2e ms/step | kernel #2 GB/s | frac of measured HBM | CPU port Gbases/s |")
+        out.append("|---|---|---|---|---|---|---|---|---|")
+        out.append(bench_row("configs[1], 10.15 GB index, 1 M × 10 kb (`r1_final_bench.json`)", final))
+        for name, tag in (("r1_bench_kmer.json", "configs[3] k-mer mode, 1 M reads 1–50 kb (`r1_bench_kmer.json`)"),
+                          ("r1_bench_deep.json", "three-level hierarchy, 20,000 genomes (`r1_bench_deep.json`)")):
+            d = load(name)
+            if d:
+                out.append(bench_row(tag, d))
+        r = final["roofline"]
+        out.append("")
+        out.append(f"configs[1]: {final['reads_per_s'] / 1e6:.2f} M reads/s device-resident; e2e moves {final['e2e']['h2d_bytes_per_step'] / 1e9:.2f} GB "
+                   f"H2D and {final['e2e']['d2h_bytes_per_step'] / 1e6:.1f} MB D2H per step; {final['gpu_launches']} kernel launches in the timed region; "
+                   f"clocks {final['clocks']['sm_mhz']:.0f}/{final['clocks']['sm_max_mhz']:.0f} MHz, reasons {final['clocks']['reasons'] or 'none'}; "
+                   f"early exit skips {r.get('early_exit_skipped_hashes_per_step', 0) / 1e6:.0f} M of "
+                   f"{(r.get('early_exit_skipped_hashes_per_step', 0) + r['algorithmic_bytes_per_step'] / 200) / 1e6:.0f} M probes per step; "
+                   f"`traffic` {(r.get('traffic') or 0) / 1e9:.1f} GB per probe launch for {r.get('algorithmic_bytes_per_launch', 0) / 1e9:.1f} GB of probe bytes.")
+    ref = load("r1_final_bench_reference_arm.json")
+    if ref and final:
+        out.append(f"Reference arm (`bench.py --impl reference`, the restated CPU path on {ref['cpu_baseline']['cores']} host cores): "
+                   f"{ref['value'] / 1e3:.2f} Gbases/s ⇒ e2e ≈ {final['e2e']['value'] / ref['value']:.0f}× (reported baseline, not the target).")
+    n2 = load("r1_bench_n2.json")
+    if n2:
+        out.append(f"2 × B200 (torchrun, weak scaling, `r1_bench_n2.json`): value {n2['value'] / 1e3:.1f} Gbases/s, e2e {n2['e2e']['value'] / 1e3:.1f} Gbases/s.")
+    cli = load("r1_cli_bench.json")
+    if cli:
+        out.append("")
+        out.append("CLI, file → file (`scripts/cli_bench.py`, `r1_cli_bench.json`; 10.15 GB `.hixf` and reads in /dev/shm, 1 GPU):")
+        out.append("")
+        out.append("| input | pack threads | index load (mmap) s | upload s | ingest+search+write s | Gbases/s in that phase | wall s |")
+        out.append("|---|---|---|---|---|---|---|")
+        for k, v in cli["runs"].items():
+            tag, th = k.rsplit("_threads", 1)
+            out.append(f"| {tag} {v['file_GB']} GB | {th} | {v['index_load_s']:.3f} | {v['index_upload_s']:.2f} | {v['ingest_search_write_s']:.2f} | "
+                       f"{v['Mbases_per_s_search_phase'] / 1e3:.2f} | {v['wall_s']:.1f} |")
+    print("\n".join(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,25 @@ constexpr uint64_t kEmptyKey = ~0ULL;      // sentinel of the dedup tables
 constexpr int kMaxMinimiserValues = 96;    // taxor build --window-size <= 96 (taxor_build.cpp:78-80)
 constexpr uint32_t kSmallRowBytes = 512;   // IXFs with tbins <= this are probed by one warp per (read, IXF)
 
+// SM partition for the persistent (work-stealing) kernels: a CTA keeps running iff mod == 0 or (its SM id % mod) lies
+// in [lo, hi); otherwise it returns before taking any work.  With complementary filters the ALU-bound hash / dedup
+// kernels of batch i+1 and the DRAM-bound probe kernels of batch i run side by side on disjoint SMs (engine.cu).
+struct SmFilter
+{
+    uint32_t mod, lo, hi;
+};
+#if defined(__CUDACC__)
+__device__ __forceinline__ bool sm_filter_keep(const SmFilter &f)
+{
+    if (f.mod == 0)
+        return true;
+    uint32_t id;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(id));
+    const uint32_t r = id % f.mod;
+    return r >= f.lo && r < f.hi;
+}
+#endif
+
 // ---- kernel #1 (hashing) ----
 struct HashArgs
 {
@@ -24,6 +43,7 @@ struct HashArgs
     uint32_t *overflow;        // set to 1 when a read needed more than its capacity
     uint64_t kmer_seed;        // k-mer mode: adjust_seed(k)
     int k, s, t;               // generic kernel only
+    SmFilter smf;
     int window;                // minimiser mode: k-mer values per window, window_size - k + 1 (2..kMaxMinimiserValues)
 };
 
@@ -39,6 +59,7 @@ struct DedupArgs
     const uint64_t *gtable_off;
     uint32_t scaling;          // 1 = off
     double scaling_limit;      // double(UINT64_MAX) / double(scaling)
+    SmFilter smf;
 };
 
 // ---- kernel #2 (IXF probe / count / threshold / compaction) ----
@@ -88,6 +109,7 @@ struct QueryArgs
     uint32_t *n_hits;
     uint32_t hit_cap;
 
+    SmFilter smf;
     uint32_t early_exit;            // 1: stop probing an item once no user bin can reach the threshold any more
     uint32_t l2_hints;              // 1: items are grouped by IXF, use the L2 eviction-priority plan (query_kernels.cu)
     unsigned long long *stat_bytes; // algorithmic bytes: sum H*3*tbins + 8*H

@@ -215,6 +215,7 @@ struct Slot
     const BatchDev *bd{nullptr};
     const uint64_t *d_words{nullptr};
     bool busy{false};
+    bool split_used{false}, ran_query{true};
 };
 
 struct ResultStore
@@ -274,6 +275,10 @@ struct txr_ctx
     cudaStream_t compute_hash{nullptr}; // overlap mode: hash + dedup (ALU bound) of batch i+1 beside the query (DRAM bound) of batch i
     bool overlap{false};               // TXR_OVERLAP=1: measured slower end to end, kept for experiments
     int query_ctas{0}, hash_ctas{0}, dedup_ctas{0}; // CTAs per SM (0: defaults for the mode)
+    // overlap by SM partition: of every `sm_mod` consecutive SM ids the first `sm_hash` run hash + dedup, the rest the
+    // probe kernels (0: share the SMs with small grids instead)
+    uint32_t sm_mod{0}, sm_hash{0};
+    SmFilter smf_hash{0, 0, 0}, smf_query{0, 0, 0}; // filters of the batch being enqueued
     cudaEvent_t fork_ev{nullptr}, join_ev{nullptr};
 };
 
@@ -510,6 +515,7 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     h.s = c->params.syncmer_size;
     h.t = c->params.t_syncmer;
     h.window = (int)c->params.window_size - (int)c->params.kmer_size + 1;
+    h.smf = c->smf_hash;
     if (c->params.use_syncmer)
         CU(launch_syncmer(h, c->sm_count, cs));
     else if (h.window > 1)
@@ -531,6 +537,7 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     dd.hash_count = s.hash_count.as<uint32_t>();
     dd.scaling = c->params.scaling;
     dd.scaling_limit = double(UINT64_MAX) / double(c->params.scaling ? c->params.scaling : 1);
+    dd.smf = c->smf_hash;
     if (c->params.use_syncmer)
     {
         if (!m.ids_small.empty())
@@ -597,6 +604,7 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
     q.stat_items = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 2);
     q.stat_skipped = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 4);
     q.early_exit = c->early_exit;
+    q.smf = c->smf_query;
     uint2 *queues = s.queues.as<uint2>();
     const uint32_t levels = std::min<uint32_t>(ix.depth, C_MAX_LEVELS);
     for (uint32_t lv = 0; lv < levels; ++lv)
@@ -706,6 +714,65 @@ static int per_read_thresholds(txr_ctx *c, Slot &s, const BatchMeta &m, cudaStre
     return TXR_OK;
 }
 
+// All kernels of one batch (after its reads are on the device) + the D2H of its counters.
+// Default: the kernels of all slots share ONE compute stream in batch order -- copies overlap compute, kernels never
+// compete with each other.  Overlap mode (TXR_OVERLAP=1, several slots): hash + dedup of batch i+1 run on a second
+// stream beside the probe kernels of batch i, either on the same SMs with small grids or, with TXR_SM_SPLIT=mod:n,
+// on disjoint SMs (SmFilter).
+static int enqueue_kernels(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev &bd, const uint64_t *d_words, bool run_query)
+{
+    const bool overlap = c->overlap && c->n_slots > 1;
+    const bool split = overlap && c->sm_mod > 1 && c->sm_hash > 0 && c->sm_hash < c->sm_mod;
+    set_query_launch_shape(c->query_ctas ? c->query_ctas : overlap && !split ? 5 : 8);
+    set_hash_launch_shape(c->hash_ctas ? c->hash_ctas : overlap && !split ? 1 : 8, c->dedup_ctas ? c->dedup_ctas : overlap && !split ? 2 : 6);
+    c->smf_hash = split ? SmFilter{c->sm_mod, 0, c->sm_hash} : SmFilter{0, 0, 0};
+    c->smf_query = split ? SmFilter{c->sm_mod, c->sm_hash, c->sm_mod} : SmFilter{0, 0, 0};
+    cudaStream_t cs = c->compute, hs = overlap ? c->compute_hash : c->compute;
+    CU(cudaStreamWaitEvent(hs, s.ev[1], 0));
+    CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, hs));
+    CU(cudaEventRecord(s.ev[6], hs));
+    TRY(launch_hash_stage(c, s, m, bd, d_words, true, hs));
+    if (run_query && c->per_read_thr)
+        TRY(per_read_thresholds(c, s, m, hs));
+    CU(cudaEventRecord(s.ev[9], hs));
+    CU(cudaStreamWaitEvent(cs, s.ev[9], 0));
+    CU(cudaEventRecord(s.ev[8], cs));
+    if (run_query)
+        TRY(launch_query_stage(c, s, m, bd, cs));
+    else
+        CU(cudaEventRecord(s.ev[4], cs));
+    CU(cudaEventRecord(s.ev[7], cs));
+    CU(cudaStreamWaitEvent(s.stream, s.ev[7], 0));
+    CU(cudaMemcpyAsync(s.h_counters.p, s.counters.p, C_TOTAL * 4, cudaMemcpyDeviceToHost, s.stream));
+    s.split_used = split;
+    s.ran_query = run_query;
+    return TXR_OK;
+}
+
+// With an SM partition a kernel only makes progress on the SMs its filter keeps.  The block scheduler has always put
+// CTAs there, but nothing in the programming model promises it, so every work-stealing cursor is checked: a cursor
+// below its item count means some kernel ran without a single kept CTA.
+static bool split_left_work_undone(const txr_ctx *c, const Slot &s, const BatchMeta &m)
+{
+    const uint32_t *hc = s.h_counters.as<uint32_t>();
+    if (hc[C_HASH_WORK] < m.n_reads)
+        return true;
+    if (c->params.use_syncmer && !m.ids_small.empty() && hc[C_DEDUP_WORK] < m.ids_small.size())
+        return true;
+    if (!s.ran_query)
+        return false;
+    const uint32_t levels = std::min<uint32_t>(c->index.depth, C_MAX_LEVELS);
+    for (uint32_t lv = 0; lv < levels; ++lv)
+    {
+        const uint32_t *lc = hc + C_LEVEL0 + C_PER_LEVEL * lv;
+        const uint32_t n_small = lv == 0 ? (c->index.ixf[0].tbins <= kSmallRowBytes ? m.n_reads : 0) : std::min(lc[0], s.queue_cap);
+        const uint32_t n_large = lv == 0 ? (c->index.ixf[0].tbins <= kSmallRowBytes ? 0 : m.n_reads) : std::min(lc[1], s.queue_cap);
+        if (lv == 0 ? lc[2] < n_small + n_large : (lc[2] < n_small || lc[3] < n_large))
+            return true;
+    }
+    return false;
+}
+
 // enqueue everything for one batch; `h_words` != nullptr: copy the packed reads from the host first
 static int submit_batch(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev *resident_meta,
                         const uint64_t *d_words_resident, const uint64_t *h_words, bool run_query)
@@ -725,30 +792,7 @@ static int submit_batch(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev 
         d_words = s.words.as<uint64_t>();
     }
     CU(cudaEventRecord(s.ev[1], s.stream));
-    // kernels of all slots share ONE compute stream (in batch order): copies overlap compute, kernels never
-    // compete with each other for SMs / DRAM
-    // Overlap mode (several slots): hash + dedup run on their own stream with small grids, so that these ALU-bound
-    // kernels of batch i+1 share the SMs with the DRAM-bound query kernels of batch i.
-    const bool overlap = c->overlap && c->n_slots > 1;
-    set_query_launch_shape(c->query_ctas ? c->query_ctas : overlap ? 5 : 8);
-    set_hash_launch_shape(c->hash_ctas ? c->hash_ctas : overlap ? 1 : 8, c->dedup_ctas ? c->dedup_ctas : overlap ? 2 : 6);
-    cudaStream_t cs = c->compute, hs = overlap ? c->compute_hash : c->compute;
-    CU(cudaStreamWaitEvent(hs, s.ev[1], 0));
-    CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, hs));
-    CU(cudaEventRecord(s.ev[6], hs));
-    TRY(launch_hash_stage(c, s, m, *bd, d_words, true, hs));
-    if (run_query && c->per_read_thr)
-        TRY(per_read_thresholds(c, s, m, hs));
-    CU(cudaEventRecord(s.ev[9], hs));
-    CU(cudaStreamWaitEvent(cs, s.ev[9], 0));
-    CU(cudaEventRecord(s.ev[8], cs));
-    if (run_query)
-        TRY(launch_query_stage(c, s, m, *bd, cs));
-    else
-        CU(cudaEventRecord(s.ev[4], cs));
-    CU(cudaEventRecord(s.ev[7], cs));
-    CU(cudaStreamWaitEvent(s.stream, s.ev[7], 0));
-    CU(cudaMemcpyAsync(s.h_counters.p, s.counters.p, C_TOTAL * 4, cudaMemcpyDeviceToHost, s.stream));
+    TRY(enqueue_kernels(c, s, m, *bd, d_words, run_query));
     s.bm = &m;
     s.bd = bd;
     s.d_words = d_words;
@@ -764,6 +808,16 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
     for (int attempt = 0;; ++attempt)
     {
         CU(cudaStreamSynchronize(s.stream));
+        if (s.split_used && split_left_work_undone(c, s, m))
+        {
+            // never observed; keeps the result exact if the block scheduler ever behaves differently
+            fprintf(stderr, "taxor_b200: SM partition left work undone, disabling it and re-running the batch\n");
+            c->sm_mod = 0;
+            CU(cudaDeviceSynchronize());
+            CU(cudaEventRecord(s.ev[1], s.stream));
+            TRY(enqueue_kernels(c, s, m, *s.bd, s.d_words, s.ran_query));
+            continue;
+        }
         const uint32_t *hc = s.h_counters.as<uint32_t>();
         if (hc[C_HASH_OVERFLOW])
             return set_error(TXR_ERR_OVERFLOW, "hash capacity bound violated (k=%d s=%d t=%d)", c->params.kmer_size,
@@ -976,6 +1030,15 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->sort_items = atoi(e) != 0;
     if (const char *e = getenv("TXR_OVERLAP"))
         c->overlap = atoi(e) != 0;
+    if (const char *e = getenv("TXR_SM_SPLIT")) // "mod:n": of every mod SM ids, n run hash + dedup
+    {
+        unsigned mod = 0, n = 0;
+        if (sscanf(e, "%u:%u", &mod, &n) == 2)
+        {
+            c->sm_mod = mod;
+            c->sm_hash = n;
+        }
+    }
     if (const char *e = getenv("TXR_QUERY_CTAS_PER_SM"))
         c->query_ctas = atoi(e);
     if (const char *e = getenv("TXR_HASH_CTAS_PER_SM"))
@@ -1475,7 +1538,8 @@ int txr_hash_batch(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, 
     TRY(validate_reads(word_off, len, n_reads));
     c->hb_off.assign(1, 0);
     c->hb_hashes.clear();
-    set_hash_launch_shape(8, 6); // this entry point runs the hash stage alone: full grids
+    set_hash_launch_shape(8, 6); // this entry point runs the hash stage alone: full grids, every SM
+    c->smf_hash = SmFilter{0, 0, 0};
     std::vector<std::pair<uint64_t, uint32_t>> plan;
     plan_batches(c, len, n_reads, plan);
     Slot &s = *c->slots[0];

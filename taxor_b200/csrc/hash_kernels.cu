@@ -272,6 +272,8 @@ __device__ bool resolve_tie_local(const uint64_t *w, const uint32_t *sv, uint64_
 template <int K, int S, int T>
 __global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
 {
+    if (!sm_filter_keep(a.smf))
+        return;
     constexpr int WN = K - S + 1;    // s-mers per k-mer window
     constexpr int QN = 32 + WN - 1;  // s-mers a lane needs for its 32 windows
     constexpr int NL = T - 1;        // neighbourhood left of the candidate s-mer
@@ -499,6 +501,8 @@ __global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
 __global__ void __launch_bounds__(128) syncmer_generic_kernel(HashArgs a)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0)
+        atomicAdd(a.work_counter, a.n_reads); // not work-stealing, but the engine checks this counter after a batch
     if (r >= a.n_reads)
         return;
     const int K = a.k, S = a.s, T = a.t, WN = K - S + 1;
@@ -537,6 +541,8 @@ __global__ void __launch_bounds__(128) syncmer_generic_kernel(HashArgs a)
 // -----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kmer_kernel(HashArgs a)
 {
+    if (!sm_filter_keep(a.smf))
+        return;
     const int lane = threadIdx.x & 31;
     const int K = a.k;
     while (true)
@@ -659,6 +665,8 @@ __device__ __forceinline__ int minimiser_run(const uint64_t *sv, int a, int b, i
 
 __global__ void __launch_bounds__(32 * kMinWarps) minimiser_kernel(HashArgs a)
 {
+    if (!sm_filter_keep(a.smf))
+        return;
     __shared__ uint64_t s_val[kMinWarps][kMinValsPadded];
     __shared__ uint16_t s_ev[kMinWarps][32][34]; // 34: lanes land on different banks
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -839,6 +847,8 @@ constexpr uint32_t kWarpMaxKeys = kWarpSlots * 3 / 4; // 1536 < 2^11: an index +
 __global__ void __launch_bounds__(32 * kDedupWarps) dedup_warp_kernel(DedupArgs a, uint32_t *work_counter, uint32_t *deferred,
                                                                       uint32_t *n_deferred)
 {
+    if (!sm_filter_keep(a.smf))
+        return;
     __shared__ uint32_t s_tab[kDedupWarps][kWarpSlots];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     volatile uint32_t *tab = s_tab[wib];
@@ -1109,7 +1119,8 @@ cudaError_t launch_dedup_warp(const DedupArgs &a, int sm_count, uint32_t *work_c
 {
     if (a.n_ids == 0)
         return cudaSuccess;
-    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sm_count * g_dedup_ctas_per_sm, ((uint64_t)a.n_ids + kDedupWarps - 1) / kDedupWarps);
+    const unsigned grid = a.smf.mod ? (unsigned)(sm_count * g_dedup_ctas_per_sm)
+                                     : (unsigned)std::min<uint64_t>((uint64_t)sm_count * g_dedup_ctas_per_sm, ((uint64_t)a.n_ids + kDedupWarps - 1) / kDedupWarps);
     dedup_warp_kernel<<<grid, 32 * kDedupWarps, 0, st>>>(a, work_counter, deferred, n_deferred);
     return cudaGetLastError();
 }

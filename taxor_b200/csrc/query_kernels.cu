@@ -322,6 +322,8 @@ __device__ __forceinline__ void scan_bins(const QueryArgs &a, const IxfDev &d, u
 // ---- IXFs with tbins <= 512: one warp per (read, IXF) ----
 __global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(QueryArgs a)
 {
+    if (!sm_filter_keep(a.smf))
+        return;
     __shared__ uint32_t s_cnt[kQueryWarps][kSmallRowBytes];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t *cnt = s_cnt[wib];
@@ -615,6 +617,8 @@ __global__ void __launch_bounds__(32 * kQueryWarps) root_part_scan_kernel2(Query
 // ---- IXFs with tbins > 512: one CTA per (read, IXF); warps take 512-byte column chunks of the rows ----
 __global__ void __launch_bounds__(256) ixf_query_large_kernel(QueryArgs a)
 {
+    if (!sm_filter_keep(a.smf))
+        return;
     extern __shared__ uint32_t s_cnt_dyn[]; // tbins counters
     __shared__ uint32_t s_item;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;

@@ -285,6 +285,27 @@ def test_search_parity_partitioned_root(ctx_partitioned, oracle, t_max, n_genome
     _search_case(ctx_partitioned, oracle, ds, reads, percentage=0.1)
 
 
+@pytest.mark.parametrize("env", [{"TXR_OVERLAP": "1"}, {"TXR_OVERLAP": "1", "TXR_SM_SPLIT": "4:1"}, {"TXR_OVERLAP": "1", "TXR_SM_SPLIT": "2:1"}])
+def test_search_parity_overlap_modes(monkeypatch, oracle, env):
+    """hash/dedup of batch i+1 beside the probes of batch i (shared SMs, or disjoint SMs through the SM filter):
+    many small batches through 3 slots, same answers; k-mer mode too (kmer_kernel is filtered as well)"""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    c = capi.Context(0)
+    try:
+        ds = H.make_dataset(oracle, n_genomes=80, genome_len=40_000, t_max=16)
+        rng = np.random.default_rng(41)
+        reads = H.make_reads(ds, rng.integers(300, 9000, 600), err=0.04)
+        c.configure(max_batch_reads=50, max_batch_bases=300_000, n_slots=3)
+        res, ora = _search_case(c, oracle, ds, reads, error_rate=0.1)
+        assert int(res.hit_begin[-1]) > 100
+        ds2 = H.make_dataset(oracle, n_genomes=24, genome_len=60_000, k=20, s=0, t=0, use_syncmer=False, t_max=8)
+        reads2 = H.make_reads(ds2, rng.integers(500, 6000, 120), err=0.02)
+        _search_case(c, oracle, ds2, reads2, window_size=20, error_rate=0.02)
+    finally:
+        c.close()
+
+
 def test_errors_are_loud(ctx):
     with pytest.raises(capi.TaxorError):
         ctx.set_params(k=20, use_syncmer=False, window_size=19)       # window smaller than k
