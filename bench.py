@@ -472,10 +472,23 @@ def main():
             traffic_src = tj.get("source")
         except Exception:
             pass
+        # the north star's yardstick: random-gather throughput of this GPU for rows of this width, measured by
+        # taxor_b200/csrc/microbench/gather_bench2.cu (useful GB/s; every random row costs a whole 128-byte DRAM line)
+        gather = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_gather_bench2.json")) as f:
+                gb = json.load(f)
+            row = int(ix.tbins[0])
+            for e in gb["qualifiers_GBps"]:
+                if e["row_bytes"] == row:
+                    gather = {"row_bytes": row, "useful_GBps": e["nc_noalloc"], "frac": q_gbs / e["nc_noalloc"],
+                              "source": "profiles/r1_gather_bench2.json (random rows of the root IXF's width, 8 GiB table)"}
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "ixf_query_small_kernel (kernel #2, all HIXF levels of a batch)",
                 "achieved": q_gbs, "peak": peak, "unit": "GB/s", "frac": q_gbs / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": traffic, "traffic_source": traffic_src,
+                "traffic": traffic, "traffic_source": traffic_src, "random_gather_ceiling": gather,
                 "avg_launch_ms": stage["query_ms"] / max(stage["probe_launches"], 1),
                 "launches_per_step": stage["probe_launches"] / args.steps,
                 "algorithmic_bytes_per_launch": stage["query_bytes"] / max(stage["probe_launches"], 1),

@@ -49,9 +49,11 @@ def main():
     if ref and final:
         out.append(f"Reference arm (`bench.py --impl reference`, the restated CPU path on {ref['cpu_baseline']['cores']} host cores): "
                    f"{ref['value'] / 1e3:.2f} Gbases/s ⇒ e2e ≈ {final['e2e']['value'] / ref['value']:.0f}× (reported baseline, not the target).")
-    n2 = load("r1_bench_n2.json")
-    if n2:
-        out.append(f"2 × B200 (torchrun, weak scaling, `r1_bench_n2.json`): value {n2['value'] / 1e3:.1f} Gbases/s, e2e {n2['e2e']['value'] / 1e3:.1f} Gbases/s.")
+    n2, n1 = load("r1_bench_n2_1GBindex.json"), load("r1_bench_n1_1GBindex.json")
+    if n2 and n1:
+        out.append(f"2 × B200 under torchrun (weak scaling, plumbing check on a 1 GB index, `r1_bench_n2_1GBindex.json`): value "
+                   f"{n2['value'] / 1e3:.1f} Gbases/s, e2e {n2['e2e']['value'] / 1e3:.1f} Gbases/s against {n1['value'] / 1e3:.1f} / "
+                   f"{n1['e2e']['value'] / 1e3:.1f} on one GPU of the same box ({n2['ms_per_step']:.1f} vs {n1['ms_per_step']:.1f} ms per step).")
     cli = load("r1_cli_bench.json")
     if cli:
         out.append("")
