@@ -62,6 +62,26 @@ struct DedupArgs
     SmFilter smf;
 };
 
+// ---- build side: distinct hash set of a user bin from the raw hash lists of its sequence segments ----
+struct BinSetArgs
+{
+    const uint64_t *hashes;      // raw hash lists of the segments (kernel #1 output, capacity layout)
+    const uint64_t *out_off;     // [n_segments+1] capacity offsets
+    const uint32_t *n_raw;       // [n_segments]
+    const uint32_t *seg_bin;     // [n_segments] user bin (batch-local) of a segment
+    uint32_t n_segments;
+    uint64_t *tables;            // open-addressing tables of all bins, filled with kEmptyKey
+    const uint64_t *table_off;   // [n_bins+1] first slot of a bin's table (sizes are powers of two)
+    uint32_t n_bins;
+    uint32_t *bin_has_empty_key; // [n_bins] the key equal to the sentinel was seen
+    uint64_t *out;               // distinct hashes, bin b at out[out_bin_off[b] ..)
+    const uint64_t *out_bin_off; // [n_bins+1] (capacity: raw count of the bin)
+    uint32_t *bin_count;         // [n_bins] distinct hashes written
+    uint32_t *work;              // work-stealing cursor (segments)
+    uint32_t scaling;
+    double scaling_limit;
+};
+
 // ---- kernel #2 (IXF probe / count / threshold / compaction) ----
 struct IxfDev
 {

@@ -1059,6 +1059,82 @@ __global__ void filter_kernel(DedupArgs a)
 }
 
 // -----------------------------------------------------------------------------------------------------------
+// build side: the std::set / ankerl set that compute_hashes fills per user bin
+// (src/hixf/build/compute_hashes.cpp:76-142), for genomes cut into segments that kernel #1 hashed independently.
+// A user bin's raw hashes are spread over many segments, so the set is a global-memory open-addressing table per bin
+// that all CTAs insert into (atomicCAS); a second pass compacts the tables.  The FracMin scaling filter is applied
+// on insertion.  Order inside a bin is arbitrary: the consumer is XOR-filter construction, a set operation.
+// -----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) binset_insert_kernel(BinSetArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    while (true)
+    {
+        uint32_t sg = 0;
+        if (lane == 0)
+            sg = atomicAdd(a.work, 1u);
+        sg = __shfl_sync(0xffffffffu, sg, 0);
+        if (sg >= a.n_segments)
+            break;
+        const uint32_t b = a.seg_bin[sg];
+        uint64_t *tab = a.tables + a.table_off[b];
+        const uint32_t mask = (uint32_t)(a.table_off[b + 1] - a.table_off[b]) - 1u;
+        const uint64_t *hp = a.hashes + a.out_off[sg];
+        const uint32_t n = a.n_raw[sg];
+        for (uint32_t i = lane; i < n; i += 32)
+        {
+            const uint64_t h = hp[i];
+            if (!scaling_keep(h, a.scaling, a.scaling_limit))
+                continue;
+            if (h == kEmptyKey)
+                a.bin_has_empty_key[b] = 1u;
+            else
+                table_insert(tab, mask, h);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) binset_compact_kernel(BinSetArgs a)
+{
+    const uint64_t total = a.table_off[a.n_bins];
+    const int lane = threadIdx.x & 31;
+    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base < total; base += (uint64_t)gridDim.x * blockDim.x)
+    {
+        // a warp looks at 32 consecutive slots; tables are powers of two >= 32 slots, so they belong to one bin
+        uint32_t lo = 0, hi = a.n_bins;
+        while (hi - lo > 1)
+        {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (a.table_off[mid] <= base)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const uint32_t b = lo;
+        const uint64_t key = a.tables[base + lane];
+        const bool keep = key != kEmptyKey;
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (bal)
+        {
+            uint32_t at = 0;
+            if (lane == 0)
+                at = atomicAdd(&a.bin_count[b], (uint32_t)__popc(bal));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (keep)
+                a.out[a.out_bin_off[b] + at + __popc(bal & ((1u << lane) - 1u))] = key;
+        }
+    }
+}
+
+// the sentinel key itself, if a bin saw it (one thread per bin)
+__global__ void binset_sentinel_kernel(BinSetArgs a)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < a.n_bins && a.bin_has_empty_key[b])
+        a.out[a.out_bin_off[b] + atomicAdd(&a.bin_count[b], 1u)] = kEmptyKey;
+}
+
+// -----------------------------------------------------------------------------------------------------------
 // host-side launchers
 // -----------------------------------------------------------------------------------------------------------
 template <int K, int S, int T>
@@ -1186,6 +1262,13 @@ cudaError_t launch_filter(const DedupArgs &a, cudaStream_t st)
     if (a.n_ids == 0)
         return cudaSuccess;
     filter_kernel<<<a.n_ids, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_binset(const BinSetArgs &a, int sm_count, cudaStream_t st)
+{
+    binset_insert_kernel<<<sm_count * 8, 256, 0, st>>>(a);
+    binset_compact_kernel<<<sm_count * 8, 256, 0, st>>>(a);
+    binset_sentinel_kernel<<<(a.n_bins + 127) / 128, 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 } // namespace txr
