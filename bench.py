@@ -133,22 +133,29 @@ def build_index_arrays(args, genomes, lens, ctx):
     t0 = time.time()
     ub = []
     ctx.set_params(k=args.k, s=args.s, t=args.t, use_syncmer=args.use_syncmer, window_size=args.window, error_rate=args.error_rate)
-    chunk = 64
-    for a in range(0, len(genomes), chunk):
-        part = genomes[a:a + chunk]
+    # build-side hashing on the GPU (txr_hash_user_bins: genomes cut into independent segments, per-genome distinct sets)
+    a, n_seg = 0, 0
+    while a < len(genomes):
+        b, bases = a, 0
+        while b < len(genomes) and (b == a or bases + int(lens[b]) <= 2_500_000_000):
+            bases += int(lens[b])
+            b += 1
+        part = genomes[a:b]
         nw = np.array([len(w) for w in part], dtype=np.uint64)
         off = np.zeros(len(part), dtype=np.uint64)
         off[1:] = np.cumsum(nw)[:-1]
-        reads = capi.PackedReads(np.concatenate(part), off, np.asarray(lens[a:a + chunk], dtype=np.uint32))
-        o, h = ctx.hash_batch(reads, dedup=False)
+        seqs = capi.PackedReads(np.concatenate(part), off, np.asarray(lens[a:b], dtype=np.uint32))
+        o, h, ns = ctx.hash_user_bins(seqs, np.arange(len(part), dtype=np.uint32), len(part))
+        n_seg += ns
         for i in range(len(part)):
             ub.append(h[int(o[i]):int(o[i + 1])])
+        a = b
     t1 = time.time()
     # explicit thread count: torchrun exports OMP_NUM_THREADS=1, which would make the CPU peeling take half an hour
     hx = tools.BuiltHixf(ub, t_max=args.t_max, seed=1, inplace=True, threads=os.cpu_count() or 1)
     del ub
     t2 = time.time()
-    info = dict(hash_s=round(t1 - t0, 2), build_s=round(t2 - t1, 2), n_ixf=hx.n_ixf, fp_bytes=hx.fp_bytes,
+    info = dict(hash_s=round(t1 - t0, 2), hash_segments=n_seg, build_s=round(t2 - t1, 2), n_ixf=hx.n_ixf, fp_bytes=hx.fp_bytes,
                 n_hashes=int(hx.n_keys), reseeds=hx.reseeds)
     return hx, info
 

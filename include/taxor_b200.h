@@ -141,6 +141,23 @@ void txr_reads_free(txr_ctx *ctx, txr_reads *reads);
 int txr_search_resident(txr_ctx *ctx, txr_reads *reads, int fetch, txr_result *out);
 int txr_get_timing(txr_ctx *ctx, txr_timing *out);
 
+/* ---- build side: hash generation of `taxor build` on the GPU ----
+ * Replaces the per-user-bin loop of compute_hashes (src/hixf/build/compute_hashes.cpp:76-142): every sequence of a user
+ * bin is hashed with the context's parameters (syncmers / k-mers / minimisers, FracMin scaling filter) and the DISTINCT
+ * hashes of the bin are returned (order unspecified: the consumer builds a set / an XOR filter).  Long sequences are cut
+ * into segments at windows whose state does not depend on what came before (unique window minimum), so the result is
+ * bit-identical to the sequential scan.  seq_bin[] must be non-decreasing; sequences use the packed layout above.
+ * The XOR-filter construction itself stays on the CPU (as in the reference).  Buffers are owned by the context. */
+typedef struct
+{
+    uint64_t n_bins;
+    const uint64_t *bin_off;           /* [n_bins+1] offsets into hashes                                      */
+    const uint64_t *hashes;
+    uint64_t n_segments;               /* how many independent pieces the sequences were hashed in            */
+} txr_bin_hashes;
+int txr_hash_user_bins(txr_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len,
+                       uint64_t n_seqs, const uint32_t *seq_bin, uint64_t n_bins, txr_bin_hashes *out);
+
 /* ---- kernel-level entry points for parity tests ---- */
 /* kernel #1 alone: seq_to_syncmers / minimiser_hash for a batch.  hash_off[n_reads+1]; hashes of read r are
  * hashes[hash_off[r] .. hash_off[r+1]) (distinct, unordered, in syncmer mode; position order in k-mer mode).

@@ -40,6 +40,11 @@ class Result(C.Structure):
                 ("count", C.POINTER(C.c_uint32)), ("keep", C.POINTER(C.c_uint8))]
 
 
+class BinHashes(C.Structure):
+    _fields_ = [("n_bins", C.c_uint64), ("bin_off", C.POINTER(C.c_uint64)), ("hashes", C.POINTER(C.c_uint64)),
+                ("n_segments", C.c_uint64)]
+
+
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("hash_ms", C.c_float), ("dedup_ms", C.c_float), ("query_ms", C.c_float),
                 ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("query_launches", C.c_uint64),
@@ -90,6 +95,7 @@ def lib():
     L.txr_search_resident.argtypes = [vp, vp, C.c_int, C.POINTER(Result)]
     L.txr_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.txr_hash_batch.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+    L.txr_hash_user_bins.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(BinHashes)]
     L.txr_ixf_bulk_count.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp]
     _LIB = L
     return L
@@ -99,7 +105,7 @@ EXPORTED = ["txr_last_error", "txr_version", "txr_ctx_create", "txr_ctx_destroy"
             "txr_index_upload", "txr_params_set", "txr_threshold_get", "txr_threshold_eval", "txr_packed_words", "txr_pack_2bit",
             "txr_pack_codes", "txr_unpack_codes", "txr_host_alloc", "txr_host_free", "txr_search",
             "txr_reads_upload", "txr_reads_free", "txr_search_resident", "txr_get_timing", "txr_hash_batch",
-            "txr_ixf_bulk_count"]
+            "txr_hash_user_bins", "txr_ixf_bulk_count"]
 
 
 def _check(rc: int) -> None:
@@ -290,6 +296,18 @@ class Context:
         t = Timing()
         _check(self._L.txr_get_timing(self._h, C.byref(t)))
         return t.as_dict()
+
+    def hash_user_bins(self, seqs: PackedReads, seq_bin, n_bins: int):
+        """txr_hash_user_bins: distinct hashes per user bin (compute_hashes of `taxor build`).  Returns (bin_off, hashes,
+        n_segments); the arrays are copies."""
+        seq_bin = np.ascontiguousarray(seq_bin, dtype=np.uint32)
+        r = BinHashes()
+        _check(self._L.txr_hash_user_bins(self._h, seqs.words.ctypes.data, seqs.word_off.ctypes.data, seqs.length.ctypes.data,
+                                          seqs.n, seq_bin.ctypes.data, n_bins, C.byref(r)))
+        off = np.ctypeslib.as_array(r.bin_off, (n_bins + 1,)).copy()
+        total = int(off[-1])
+        hashes = np.ctypeslib.as_array(r.hashes, (total,)).copy() if total else np.zeros(0, np.uint64)
+        return off, hashes, int(r.n_segments)
 
     def hash_batch(self, reads: PackedReads, dedup: bool = True):
         off, hs = C.c_void_p(), C.c_void_p()

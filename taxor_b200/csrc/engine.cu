@@ -39,6 +39,7 @@ cudaError_t launch_query_large(const QueryArgs &a, int sm_count, uint32_t max_tb
 cudaError_t launch_sort_items(const uint2 *items, const uint32_t *n_ptr, uint32_t cap, uint32_t *hist, uint32_t n_ixf, uint2 *out,
                               int sm_count, cudaStream_t st);
 cudaError_t launch_root_partitioned(const QueryArgs &q, const RootPartArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_binset(const BinSetArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_bulk_count(const IxfDev &d, const uint64_t *values, uint32_t n, uint32_t *counts, cudaStream_t st);
 } // namespace txr
 
@@ -269,7 +270,9 @@ struct txr_ctx
     txr_timing timing{};
     // scratch for the parity entry points
     std::vector<uint64_t> hb_off, hb_hashes;
+    std::vector<uint64_t> ub_off, ub_hashes; // txr_hash_user_bins result
     DevBuf scratch_a, scratch_b;
+    DevBuf binset[8]; // txr_hash_user_bins: segment bins, tables, table offsets, flags, output, output offsets, counts, cursor
     cudaStream_t primary{nullptr};     // caller's stream: every search forks from it and joins back into it
     cudaStream_t compute{nullptr};     // the query kernels of all batches run here, in batch order; slot streams only carry copies
     cudaStream_t compute_hash{nullptr}; // overlap mode: hash + dedup (ALU bound) of batch i+1 beside the query (DRAM bound) of batch i
@@ -1088,6 +1091,8 @@ void txr_ctx_destroy(txr_ctx *c)
     c->d_lut.release();
     c->scratch_a.release();
     c->scratch_b.release();
+    for (auto &b : c->binset)
+        b.release();
     delete c;
 }
 
@@ -1575,6 +1580,254 @@ int txr_hash_batch(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, 
     }
     *hash_off = c->hb_off.data();
     *hashes = c->hb_hashes.data();
+    return TXR_OK;
+}
+
+// ---- build side: per-user-bin distinct hashes ----
+namespace
+{
+inline uint64_t host_mer(const uint64_t *w, uint64_t pos, int n)
+{
+    const uint64_t wi = pos >> 5;
+    const int off = (int)(pos & 31) * 2;
+    uint64_t x = w[wi];
+    if (off)
+        x = (x << off) | (w[wi + 1] >> (64 - off));
+    return x >> (64 - 2 * n);
+}
+inline uint64_t host_revcomp(uint64_t fwd, int n)
+{
+    uint64_t y = ~fwd, r = 0;
+    for (int i = 0; i < n; ++i, y >>= 2)
+        r = (r << 2) | (y & 3);
+    return r;
+}
+// Is the scan state at k-mer window j independent of everything before it?  Syncmers: the k-s+1 canonical s-mers of the
+// window have ONE minimum (syncmer.cpp:113-141 then tracks exactly that position, whatever happened earlier, and a scan
+// that starts here picks the same one).  Minimisers: the W values starting at j have one minimum.  k-mers: stateless.
+bool state_is_history_free(const txr_params &p, uint64_t kmer_seed, const uint64_t *w, uint64_t j)
+{
+    int n_vals, mer;
+    if (p.use_syncmer)
+    {
+        n_vals = p.kmer_size - p.syncmer_size + 1;
+        mer = p.syncmer_size;
+    }
+    else
+    {
+        n_vals = (int)p.window_size - p.kmer_size + 1;
+        mer = p.kmer_size;
+        if (n_vals <= 1)
+            return true;
+    }
+    uint64_t best = ~0ULL;
+    int count = 0;
+    for (int i = 0; i < n_vals; ++i)
+    {
+        const uint64_t f = host_mer(w, j + i, mer), r = host_revcomp(f, mer);
+        const uint64_t v = p.use_syncmer ? std::min(f, r) : std::min(f ^ kmer_seed, r ^ kmer_seed);
+        if (v < best)
+        {
+            best = v;
+            count = 1;
+        }
+        else if (v == best)
+            ++count;
+    }
+    return count == 1;
+}
+// target k-mer windows per segment (TXR_SEGMENT_WINDOWS overrides it: the tests cut every few thousand windows)
+uint64_t segment_windows()
+{
+    const char *e = getenv("TXR_SEGMENT_WINDOWS");
+    const long long v = e ? atoll(e) : 0;
+    return v >= 64 ? (uint64_t)v : (1u << 18);
+}
+} // namespace
+
+int txr_hash_user_bins(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_seqs,
+                       const uint32_t *seq_bin, uint64_t n_bins, txr_bin_hashes *out)
+{
+    if (!c || !c->have_params)
+        return set_error(TXR_ERR_STATE, "txr_params_set not called");
+    if (!words || !word_off || !len || !seq_bin || !out || n_bins == 0 || n_bins > 0xffffffffull)
+        return set_error(TXR_ERR_ARG, "null or empty argument");
+    CU(cudaSetDevice(c->device));
+    TRY(ensure_slots(c));
+    for (uint64_t i = 0; i < n_seqs; ++i)
+    {
+        if (seq_bin[i] >= n_bins || (i && seq_bin[i] < seq_bin[i - 1]))
+            return set_error(TXR_ERR_ARG, "seq_bin must be non-decreasing and below n_bins (sequence %llu)", (unsigned long long)i);
+        if (i + 1 < n_seqs && word_off[i + 1] < word_off[i] + txr_packed_words(len[i]))
+            return set_error(TXR_ERR_ARG, "sequences must be packed in ascending, non-overlapping order (sequence %llu)", (unsigned long long)i);
+    }
+    const txr_params &p = c->params;
+    const int k = p.kmer_size;
+    // 1. segments: cut long sequences at history-free windows that start on a word boundary
+    std::vector<uint64_t> seg_off;
+    std::vector<uint32_t> seg_len, seg_bin, seg_seq;
+    const int span = p.use_syncmer ? k : std::max<int>(k, (int)p.window_size); // bases a window's state test reads
+    const uint64_t kSegmentWindows = segment_windows();
+    for (uint64_t q = 0; q < n_seqs; ++q)
+    {
+        const uint64_t L = len[q], n_win = L >= (uint64_t)k ? L - k + 1 : 0;
+        const uint64_t *w = words + word_off[q];
+        uint64_t start = 0;
+        while (true)
+        {
+            uint64_t cut = n_win; // no cut: the segment runs to the end of the sequence
+            if (n_win > start + kSegmentWindows + kSegmentWindows / 2)
+            {
+                uint64_t cand = (start + kSegmentWindows + 31) & ~31ull;
+                for (int tries = 0; tries < 256 && cand + span <= L && cand + kSegmentWindows / 4 < n_win; ++tries, cand += 32)
+                    if (state_is_history_free(p, c->kmer_seed, w, cand))
+                    {
+                        cut = cand;
+                        break;
+                    }
+            }
+            seg_off.push_back(word_off[q] + start / 32);
+            seg_len.push_back((uint32_t)(cut == n_win ? L - start : cut - start + span - 1));
+            seg_bin.push_back(seq_bin[q]);
+            seg_seq.push_back((uint32_t)q);
+            if (cut == n_win)
+                break;
+            start = cut;
+        }
+    }
+    const uint64_t n_seg = seg_off.size();
+    c->ub_off.assign(n_bins + 1, 0);
+    c->ub_hashes.clear();
+    set_hash_launch_shape(8, 6);
+    c->smf_hash = SmFilter{0, 0, 0};
+    Slot &s = *c->slots[0];
+    cudaStream_t st = s.stream;
+    DevBuf &d_seg_bin = c->binset[0], &d_tables = c->binset[1], &d_table_off = c->binset[2], &d_flags = c->binset[3],
+           &d_out = c->binset[4], &d_out_off = c->binset[5], &d_count = c->binset[6], &d_work = c->binset[7];
+    auto release_all = [&] {
+        for (auto &b : c->binset)
+            b.release();
+    };
+    std::vector<uint64_t> bin_total(n_bins, 0);
+    // 2. batches of whole user bins
+    uint64_t a = 0;
+    while (a < n_seg)
+    {
+        uint64_t b = a, bases = 0;
+        while (b < n_seg && (b == a || seg_bin[b] == seg_bin[b - 1] || bases + seg_len[b] <= c->max_batch_bases))
+            bases += seg_len[b++]; // a bin is never split over two batches
+        const uint32_t n = (uint32_t)(b - a);
+        const uint32_t bin_lo = seg_bin[a], bin_hi = seg_bin[b - 1], nb = bin_hi - bin_lo + 1;
+        BatchMeta m;
+        build_batch_meta(c, seg_off.data(), seg_len.data(), a, n, m);
+        // segments overlap by k-1 bases, so their word ranges do too: the batch's words run to the end of the last one
+        uint64_t last_word = 0;
+        for (uint64_t i = a; i < b; ++i)
+            last_word = std::max(last_word, seg_off[i] + txr_packed_words(seg_len[i]));
+        m.n_words = last_word - m.first_word;
+        int rc = slot_reserve(c, s, m);
+        if (rc == TXR_OK)
+            rc = s.words.ensure(m.n_words * 8);
+        if (rc != TXR_OK)
+        {
+            release_all();
+            return rc;
+        }
+        CU(cudaMemcpyAsync(s.words.p, words + m.first_word, m.n_words * 8, cudaMemcpyHostToDevice, st));
+        TRY(upload_batch_meta(m, s.meta, st, nullptr));
+        CU(cudaMemsetAsync(s.counters.p, 0, C_TOTAL * 4, st));
+        TRY(launch_hash_stage(c, s, m, s.meta, s.words.as<uint64_t>(), false, st));
+        // raw counts -> table sizes
+        std::vector<uint32_t> n_raw(n);
+        const bool raw_in_nraw = p.use_syncmer || p.scaling > 1;
+        CU(cudaMemcpyAsync(n_raw.data(), raw_in_nraw ? s.n_raw.p : s.hash_count.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        uint32_t ovf = 0;
+        CU(cudaMemcpyAsync(&ovf, s.counters.as<uint32_t>() + C_HASH_OVERFLOW, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (ovf)
+        {
+            release_all();
+            return set_error(TXR_ERR_OVERFLOW, "hash capacity bound violated");
+        }
+        std::vector<uint64_t> raw_per_bin(nb, 0), table_off(nb + 1, 0), out_off(nb + 1, 0);
+        std::vector<uint32_t> local_bin(n);
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            local_bin[i] = seg_bin[a + i] - bin_lo;
+            raw_per_bin[local_bin[i]] += n_raw[i];
+        }
+        for (uint32_t q = 0; q < nb; ++q)
+        {
+            table_off[q + 1] = table_off[q] + std::max<uint64_t>(32, next_pow2(2 * raw_per_bin[q]));
+            out_off[q + 1] = out_off[q] + raw_per_bin[q] + 1;
+            if (table_off[q + 1] - table_off[q] > (1ull << 32))
+            {
+                release_all();
+                return set_error(TXR_ERR_UNSUPPORTED, "user bin %u: more than 2^31 raw hashes", bin_lo + q);
+            }
+        }
+        rc = d_seg_bin.ensure((size_t)n * 4);
+        rc = rc ? rc : d_tables.ensure(table_off[nb] * 8);
+        rc = rc ? rc : d_table_off.ensure((nb + 1) * 8);
+        rc = rc ? rc : d_flags.ensure((size_t)nb * 4);
+        rc = rc ? rc : d_out.ensure(out_off[nb] * 8);
+        rc = rc ? rc : d_out_off.ensure((nb + 1) * 8);
+        rc = rc ? rc : d_count.ensure((size_t)nb * 4);
+        rc = rc ? rc : d_work.ensure(4);
+        if (rc != TXR_OK)
+        {
+            release_all();
+            return rc;
+        }
+        CU(cudaMemcpyAsync(d_seg_bin.p, local_bin.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_table_off.p, table_off.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_out_off.p, out_off.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(d_tables.p, 0xff, table_off[nb] * 8, st));
+        CU(cudaMemsetAsync(d_flags.p, 0, (size_t)nb * 4, st));
+        CU(cudaMemsetAsync(d_count.p, 0, (size_t)nb * 4, st));
+        CU(cudaMemsetAsync(d_work.p, 0, 4, st));
+        BinSetArgs ba{};
+        ba.hashes = s.hashes.as<uint64_t>();
+        ba.out_off = s.meta.out_off.as<uint64_t>();
+        ba.n_raw = raw_in_nraw ? s.n_raw.as<uint32_t>() : s.hash_count.as<uint32_t>();
+        ba.seg_bin = d_seg_bin.as<uint32_t>();
+        ba.n_segments = n;
+        ba.tables = d_tables.as<uint64_t>();
+        ba.table_off = d_table_off.as<uint64_t>();
+        ba.n_bins = nb;
+        ba.bin_has_empty_key = d_flags.as<uint32_t>();
+        ba.out = d_out.as<uint64_t>();
+        ba.out_bin_off = d_out_off.as<uint64_t>();
+        ba.bin_count = d_count.as<uint32_t>();
+        ba.work = d_work.as<uint32_t>();
+        ba.scaling = p.scaling;
+        ba.scaling_limit = double(UINT64_MAX) / double(p.scaling ? p.scaling : 1);
+        CU(launch_binset(ba, c->sm_count, st));
+        std::vector<uint32_t> counts(nb);
+        CU(cudaMemcpyAsync(counts.data(), d_count.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        // bins ascend with the segments and a bin never spans two batches: appending keeps the result in bin order
+        uint64_t at = c->ub_hashes.size(), add = 0;
+        for (uint32_t q = 0; q < nb; ++q)
+            add += counts[q];
+        c->ub_hashes.resize(at + add);
+        for (uint32_t q = 0; q < nb; ++q)
+        {
+            bin_total[bin_lo + q] = counts[q];
+            if (counts[q])
+                CU(cudaMemcpyAsync(c->ub_hashes.data() + at, d_out.as<uint64_t>() + out_off[q], (size_t)counts[q] * 8, cudaMemcpyDeviceToHost, st));
+            at += counts[q];
+        }
+        CU(cudaStreamSynchronize(st));
+        a = b;
+    }
+    for (uint64_t q = 0; q < n_bins; ++q)
+        c->ub_off[q + 1] = c->ub_off[q] + bin_total[q];
+    release_all();
+    out->n_bins = n_bins;
+    out->bin_off = c->ub_off.data();
+    out->hashes = c->ub_hashes.data();
+    out->n_segments = n_seg;
     return TXR_OK;
 }
 

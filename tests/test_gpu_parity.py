@@ -306,6 +306,67 @@ def test_search_parity_overlap_modes(monkeypatch, oracle, env):
         c.close()
 
 
+@pytest.mark.parametrize("mode", ["syncmer", "syncmer_generic", "kmer", "minimiser", "syncmer_scaled"])
+def test_hash_user_bins_build_side(monkeypatch, oracle, mode):
+    """compute_hashes of `taxor build` on the GPU: per-user-bin distinct hashes == union of the oracle's per-sequence
+    sets, with the sequences cut into many independently hashed segments (every ~1-2 k windows here).  The low-complexity
+    inserts put tie runs (homopolymers, tandem repeats, palindromes) right where cuts are attempted: a cut may only be
+    taken at a window whose state does not depend on history."""
+    monkeypatch.setenv("TXR_SEGMENT_WINDOWS", "1024")
+    c = capi.Context(0)
+    try:
+        par = dict(syncmer=dict(k=22, s=12, t=5, use_syncmer=True, window_size=20),
+                   syncmer_generic=dict(k=21, s=11, t=oracle.t_syncmer(21, 11), use_syncmer=True, window_size=20),
+                   kmer=dict(k=20, use_syncmer=False, window_size=20),
+                   minimiser=dict(k=20, use_syncmer=False, window_size=31),
+                   syncmer_scaled=dict(k=22, s=12, t=5, use_syncmer=True, window_size=20, scaling=10))[mode]
+        c.set_params(**par)
+        rng = np.random.default_rng(sum(mode.encode()))
+        seqs, seq_bin = [], []
+        n_bins = 9
+        for b in range(n_bins):
+            if b == 4:
+                continue                                               # a user bin without sequences
+            for _ in range(int(rng.integers(1, 4))):
+                x = rng.integers(0, 4, int(rng.integers(3000, 60000)), dtype=np.uint8)
+                for _ in range(int(rng.integers(0, 12))):              # low-complexity inserts at random places
+                    at, ln = int(rng.integers(0, len(x) - 2500)), int(rng.integers(30, 2500))
+                    kind = rng.integers(0, 3)
+                    if kind == 0:
+                        x[at:at + ln] = rng.integers(0, 4)
+                    elif kind == 1:
+                        x[at:at + ln] = np.resize(rng.integers(0, 4, int(rng.integers(2, 7)), dtype=np.uint8), ln)
+                    else:
+                        half = x[at:at + ln // 2]
+                        x[at + ln // 2:at + 2 * (ln // 2)] = (3 - half)[::-1]
+                seqs.append(x)
+                seq_bin.append(b)
+        seqs += [rng.integers(0, 4, n, dtype=np.uint8) for n in (0, 5, 21, 22, 40)]   # short tails in the last bin
+        seq_bin += [n_bins - 1] * 5
+        packed = capi.pack_codes(seqs)
+        off, h, n_seg = c.hash_user_bins(packed, seq_bin, n_bins)
+        assert n_seg > 3 * len(seqs)                                    # the sequences really were cut
+        k = par["k"]
+        for b in range(n_bins):
+            exp = set()
+            for x, sb in zip(seqs, seq_bin):
+                if sb != b:
+                    continue
+                if par["use_syncmer"]:
+                    v = oracle.syncmer_hashes(x, k, par["s"], par["t"])
+                elif par["window_size"] > k:
+                    v = oracle.minimiser_hashes(x, k, par["window_size"])
+                else:
+                    v = oracle.kmer_hashes(x, k)
+                exp.update(int(t) for t in v.tolist() if oracle.scaling_keep(int(t), par.get("scaling", 1)))
+            got = h[int(off[b]):int(off[b + 1])]
+            assert len(got) == len(set(got.tolist())), b               # distinct
+            assert set(got.tolist()) == exp, (mode, b, len(got), len(exp))
+        assert off[4] == off[5]
+    finally:
+        c.close()
+
+
 def test_errors_are_loud(ctx):
     with pytest.raises(capi.TaxorError):
         ctx.set_params(k=20, use_syncmer=False, window_size=19)       # window smaller than k
