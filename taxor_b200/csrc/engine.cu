@@ -278,6 +278,8 @@ struct txr_ctx
     cudaStream_t compute_hash{nullptr}; // overlap mode: hash + dedup (ALU bound) of batch i+1 beside the query (DRAM bound) of batch i
     bool overlap{false};               // TXR_OVERLAP=1: measured slower end to end, kept for experiments
     int query_ctas{0}, hash_ctas{0}, dedup_ctas{0}; // CTAs per SM (0: defaults for the mode)
+    int level_ctas{0};                              // probe kernels of the levels below the root (0: same as query_ctas)
+    bool ramp_tail{true};                           // TXR_RAMP_TAIL=0: no short last batch
     // overlap by SM partition: of every `sm_mod` consecutive SM ids the first `sm_hash` run hash + dedup, the rest the
     // probe kernels (0: share the SMs with small grids instead)
     uint32_t sm_mod{0}, sm_hash{0};
@@ -667,6 +669,8 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
         {
             q.items_cap = s.queue_cap;
             q.n_items_direct = 0;
+            if (c->level_ctas)
+                set_query_launch_shape(c->level_ctas);
             // group the level's items by IXF first (L2 reuse of the child IXFs, see query_kernels.cu)
             uint2 *sorted = queues + (size_t)(2 * levels) * s.queue_cap;
             const uint2 *raw = queues + (size_t)(2 * lv) * s.queue_cap;
@@ -694,6 +698,8 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
             }
         }
     }
+    if (c->level_ctas)
+        set_query_launch_shape(c->query_ctas ? c->query_ctas : 8);
     CU(cudaEventRecord(s.ev[4], cs));
     return TXR_OK;
 }
@@ -964,6 +970,17 @@ static void plan_batches(const txr_ctx *c, const uint32_t *len, uint64_t n, std:
         out.emplace_back(i, (uint32_t)(j - i));
         i = j;
     }
+    // ... and the last batch is short as well: its result copy and host pass are what nothing overlaps at the end
+    if (ramp && c->ramp_tail && out.size() >= 2)
+    {
+        const uint32_t tail = (uint32_t)std::max<uint64_t>(c->max_batch_reads / 8, 1);
+        auto last = out.back();
+        if (last.second > 2 * tail)
+        {
+            out.back().second = last.second - tail;
+            out.emplace_back(last.first + last.second - tail, tail);
+        }
+    }
 }
 
 // make the slot streams wait for work already queued on the caller's stream ...
@@ -1044,6 +1061,10 @@ int txr_ctx_create(int device, txr_ctx **out)
     }
     if (const char *e = getenv("TXR_QUERY_CTAS_PER_SM"))
         c->query_ctas = atoi(e);
+    if (const char *e = getenv("TXR_LEVEL_CTAS_PER_SM"))
+        c->level_ctas = atoi(e);
+    if (const char *e = getenv("TXR_RAMP_TAIL"))
+        c->ramp_tail = atoi(e) != 0;
     if (const char *e = getenv("TXR_HASH_CTAS_PER_SM"))
         c->hash_ctas = atoi(e);
     if (const char *e = getenv("TXR_DEDUP_CTAS_PER_SM"))
