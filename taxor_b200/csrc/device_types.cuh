@@ -44,6 +44,7 @@ struct HashArgs
     uint64_t kmer_seed;        // k-mer mode: adjust_seed(k)
     int k, s, t;               // generic kernel only
     SmFilter smf;
+    int ctas_per_sm;           // host side: CTAs per SM of the persistent grid (0: fill the SM)
     int window;                // minimiser mode: k-mer values per window, window_size - k + 1 (2..kMaxMinimiserValues)
 };
 
@@ -60,6 +61,7 @@ struct DedupArgs
     uint32_t scaling;          // 1 = off
     double scaling_limit;      // double(UINT64_MAX) / double(scaling)
     SmFilter smf;
+    int ctas_per_sm;           // host side: CTAs per SM of the warp-per-read grid (0: default)
 };
 
 // ---- build side: distinct hash set of a user bin from the raw hash lists of its sequence segments ----
@@ -130,6 +132,7 @@ struct QueryArgs
     uint32_t hit_cap;
 
     SmFilter smf;
+    int ctas_per_sm;                // host side: CTAs per SM of the persistent probe grid (0: fill the SM)
     uint32_t early_exit;            // 1: stop probing an item once no user bin can reach the threshold any more
     uint32_t l2_hints;              // 1: items are grouped by IXF, use the L2 eviction-priority plan (query_kernels.cu)
     unsigned long long *stat_bytes; // algorithmic bytes: sum H*3*tbins + 8*H

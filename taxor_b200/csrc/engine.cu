@@ -26,8 +26,6 @@ namespace txr
 cudaError_t launch_syncmer(const HashArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_kmer(const HashArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_minimiser(const HashArgs &a, int sm_count, cudaStream_t st);
-void set_hash_launch_shape(int hash_ctas_per_sm, int dedup_ctas_per_sm);
-void set_query_launch_shape(int ctas_per_sm);
 cudaError_t launch_dedup_warp(const DedupArgs &a, int sm_count, uint32_t *work_counter, uint32_t *deferred, uint32_t *n_deferred,
                               cudaStream_t st);
 cudaError_t launch_dedup_deferred(const DedupArgs &a, int sm_count, const uint32_t *n_deferred, cudaStream_t st);
@@ -279,11 +277,11 @@ struct txr_ctx
     bool overlap{false};               // TXR_OVERLAP=1: measured slower end to end, kept for experiments
     int query_ctas{0}, hash_ctas{0}, dedup_ctas{0}; // CTAs per SM (0: defaults for the mode)
     int level_ctas{0};                              // probe kernels of the levels below the root (0: same as query_ctas)
-    bool ramp_tail{true};                           // TXR_RAMP_TAIL=0: no short last batch
     // overlap by SM partition: of every `sm_mod` consecutive SM ids the first `sm_hash` run hash + dedup, the rest the
     // probe kernels (0: share the SMs with small grids instead)
     uint32_t sm_mod{0}, sm_hash{0};
-    SmFilter smf_hash{0, 0, 0}, smf_query{0, 0, 0}; // filters of the batch being enqueued
+    SmFilter smf_hash{0, 0, 0}, smf_query{0, 0, 0}; // filters of the batch being enqueued ...
+    int shape_query{0}, shape_level{0}, shape_hash{0}, shape_dedup{0}; // ... and its CTAs per SM (0: fill the SM)
     cudaEvent_t fork_ev{nullptr}, join_ev{nullptr};
 };
 
@@ -521,6 +519,7 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     h.t = c->params.t_syncmer;
     h.window = (int)c->params.window_size - (int)c->params.kmer_size + 1;
     h.smf = c->smf_hash;
+    h.ctas_per_sm = c->shape_hash;
     if (c->params.use_syncmer)
         CU(launch_syncmer(h, c->sm_count, cs));
     else if (h.window > 1)
@@ -543,6 +542,7 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     dd.scaling = c->params.scaling;
     dd.scaling_limit = double(UINT64_MAX) / double(c->params.scaling ? c->params.scaling : 1);
     dd.smf = c->smf_hash;
+    dd.ctas_per_sm = c->shape_dedup;
     if (c->params.use_syncmer)
     {
         if (!m.ids_small.empty())
@@ -610,6 +610,7 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
     q.stat_skipped = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 4);
     q.early_exit = c->early_exit;
     q.smf = c->smf_query;
+    q.ctas_per_sm = c->shape_query;
     uint2 *queues = s.queues.as<uint2>();
     const uint32_t levels = std::min<uint32_t>(ix.depth, C_MAX_LEVELS);
     for (uint32_t lv = 0; lv < levels; ++lv)
@@ -669,8 +670,7 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
         {
             q.items_cap = s.queue_cap;
             q.n_items_direct = 0;
-            if (c->level_ctas)
-                set_query_launch_shape(c->level_ctas);
+            q.ctas_per_sm = c->shape_level;
             // group the level's items by IXF first (L2 reuse of the child IXFs, see query_kernels.cu)
             uint2 *sorted = queues + (size_t)(2 * levels) * s.queue_cap;
             const uint2 *raw = queues + (size_t)(2 * lv) * s.queue_cap;
@@ -698,8 +698,6 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
             }
         }
     }
-    if (c->level_ctas)
-        set_query_launch_shape(c->query_ctas ? c->query_ctas : 8);
     CU(cudaEventRecord(s.ev[4], cs));
     return TXR_OK;
 }
@@ -732,8 +730,10 @@ static int enqueue_kernels(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchD
 {
     const bool overlap = c->overlap && c->n_slots > 1;
     const bool split = overlap && c->sm_mod > 1 && c->sm_hash > 0 && c->sm_hash < c->sm_mod;
-    set_query_launch_shape(c->query_ctas ? c->query_ctas : overlap && !split ? 5 : 8);
-    set_hash_launch_shape(c->hash_ctas ? c->hash_ctas : overlap && !split ? 1 : 8, c->dedup_ctas ? c->dedup_ctas : overlap && !split ? 2 : 6);
+    c->shape_query = c->query_ctas ? c->query_ctas : overlap && !split ? 5 : 8;
+    c->shape_level = c->level_ctas ? c->level_ctas : c->shape_query;
+    c->shape_hash = c->hash_ctas ? c->hash_ctas : overlap && !split ? 1 : 8;
+    c->shape_dedup = c->dedup_ctas ? c->dedup_ctas : overlap && !split ? 2 : 6;
     c->smf_hash = split ? SmFilter{c->sm_mod, 0, c->sm_hash} : SmFilter{0, 0, 0};
     c->smf_query = split ? SmFilter{c->sm_mod, c->sm_hash, c->sm_mod} : SmFilter{0, 0, 0};
     cudaStream_t cs = c->compute, hs = overlap ? c->compute_hash : c->compute;
@@ -970,17 +970,6 @@ static void plan_batches(const txr_ctx *c, const uint32_t *len, uint64_t n, std:
         out.emplace_back(i, (uint32_t)(j - i));
         i = j;
     }
-    // ... and the last batch is short as well: its result copy and host pass are what nothing overlaps at the end
-    if (ramp && c->ramp_tail && out.size() >= 2)
-    {
-        const uint32_t tail = (uint32_t)std::max<uint64_t>(c->max_batch_reads / 8, 1);
-        auto last = out.back();
-        if (last.second > 2 * tail)
-        {
-            out.back().second = last.second - tail;
-            out.emplace_back(last.first + last.second - tail, tail);
-        }
-    }
 }
 
 // make the slot streams wait for work already queued on the caller's stream ...
@@ -1063,8 +1052,6 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->query_ctas = atoi(e);
     if (const char *e = getenv("TXR_LEVEL_CTAS_PER_SM"))
         c->level_ctas = atoi(e);
-    if (const char *e = getenv("TXR_RAMP_TAIL"))
-        c->ramp_tail = atoi(e) != 0;
     if (const char *e = getenv("TXR_HASH_CTAS_PER_SM"))
         c->hash_ctas = atoi(e);
     if (const char *e = getenv("TXR_DEDUP_CTAS_PER_SM"))
@@ -1564,7 +1551,7 @@ int txr_hash_batch(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, 
     TRY(validate_reads(word_off, len, n_reads));
     c->hb_off.assign(1, 0);
     c->hb_hashes.clear();
-    set_hash_launch_shape(8, 6); // this entry point runs the hash stage alone: full grids, every SM
+    c->shape_hash = c->shape_dedup = 0; // this entry point runs the hash stage alone: full grids, every SM
     c->smf_hash = SmFilter{0, 0, 0};
     std::vector<std::pair<uint64_t, uint32_t>> plan;
     plan_batches(c, len, n_reads, plan);
@@ -1719,7 +1706,7 @@ int txr_hash_user_bins(txr_ctx *c, const uint64_t *words, const uint64_t *word_o
     const uint64_t n_seg = seg_off.size();
     c->ub_off.assign(n_bins + 1, 0);
     c->ub_hashes.clear();
-    set_hash_launch_shape(8, 6);
+    c->shape_hash = c->shape_dedup = 0;
     c->smf_hash = SmFilter{0, 0, 0};
     Slot &s = *c->slots[0];
     cudaStream_t st = s.stream;

@@ -1146,18 +1146,13 @@ static bool try_launch_syncmer(const HashArgs &a, int k, int s, int t, int grid,
     return true;
 }
 
-// CTAs per SM of the persistent hash / dedup grids.  Defaults fill the SM; the engine lowers them when these
-// ALU-bound kernels run beside the DRAM-bound query kernel of the previous batch (engine.cu, "overlap").
-static int g_hash_ctas_per_sm = 8, g_dedup_ctas_per_sm = 6;
-void set_hash_launch_shape(int hash_ctas_per_sm, int dedup_ctas_per_sm)
-{
-    g_hash_ctas_per_sm = std::max(1, std::min(16, hash_ctas_per_sm));
-    g_dedup_ctas_per_sm = std::max(1, std::min(16, dedup_ctas_per_sm));
-}
+// CTAs per SM of the persistent hash / dedup grids come with the arguments (HashArgs / DedupArgs::ctas_per_sm): the
+// defaults fill the SM; the engine lowers them when these ALU-bound kernels share SMs with the probe kernels ("overlap").
+static int clamp_ctas(int v, int dflt) { return v <= 0 ? dflt : v > 16 ? 16 : v; }
 
 cudaError_t launch_syncmer(const HashArgs &a, int sm_count, cudaStream_t st)
 {
-    const int grid = sm_count * g_hash_ctas_per_sm;
+    const int grid = sm_count * clamp_ctas(a.ctas_per_sm, 8);
     bool ok = try_launch_syncmer<22, 12, 5>(a, a.k, a.s, a.t, grid, st)      // Taxor's published indexes
               || try_launch_syncmer<20, 10, 5>(a, a.k, a.s, a.t, grid, st)   // taxor build defaults
               || try_launch_syncmer<24, 12, 6>(a, a.k, a.s, a.t, grid, st)
@@ -1195,8 +1190,9 @@ cudaError_t launch_dedup_warp(const DedupArgs &a, int sm_count, uint32_t *work_c
 {
     if (a.n_ids == 0)
         return cudaSuccess;
-    const unsigned grid = a.smf.mod ? (unsigned)(sm_count * g_dedup_ctas_per_sm)
-                                     : (unsigned)std::min<uint64_t>((uint64_t)sm_count * g_dedup_ctas_per_sm, ((uint64_t)a.n_ids + kDedupWarps - 1) / kDedupWarps);
+    const int ctas = clamp_ctas(a.ctas_per_sm, 6);
+    const unsigned grid = a.smf.mod ? (unsigned)(sm_count * ctas)
+                                     : (unsigned)std::min<uint64_t>((uint64_t)sm_count * ctas, ((uint64_t)a.n_ids + kDedupWarps - 1) / kDedupWarps);
     dedup_warp_kernel<<<grid, 32 * kDedupWarps, 0, st>>>(a, work_counter, deferred, n_deferred);
     return cudaGetLastError();
 }

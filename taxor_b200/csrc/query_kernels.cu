@@ -769,16 +769,14 @@ cudaError_t launch_sort_items(const uint2 *items, const uint32_t *n_ptr, uint32_
 }
 
 // ---- launchers ----
-// CTAs per SM of the persistent query grids: 8 = all 32 warps an SM can hold at 56 registers.  The random-line rate
-// of HBM is already saturated by 16 warps per SM (profiles/r1_gather_bench2.json), so the engine lowers this when
-// the hash / dedup kernels of the next batch run beside it.
-static int g_query_ctas_per_sm = 8;
-void set_query_launch_shape(int ctas_per_sm) { g_query_ctas_per_sm = ctas_per_sm < 1 ? 1 : ctas_per_sm > 16 ? 16 : ctas_per_sm; }
-static int query_ctas_per_sm() { return g_query_ctas_per_sm; }
+// CTAs per SM of the persistent probe grids (QueryArgs::ctas_per_sm): 8 = all 32 warps an SM can hold at 56 registers.
+// The random-line rate of HBM is already saturated by 16 warps per SM (profiles/r1_gather_bench2.json); the engine
+// lowers the value when the hash / dedup kernels of the next batch run beside the probes.
+static int query_ctas(const QueryArgs &a) { return a.ctas_per_sm <= 0 ? 8 : a.ctas_per_sm > 16 ? 16 : a.ctas_per_sm; }
 
 cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st)
 {
-    ixf_query_small_kernel<<<sm_count * query_ctas_per_sm(), 32 * kQueryWarps, 0, st>>>(a);
+    ixf_query_small_kernel<<<sm_count * query_ctas(a), 32 * kQueryWarps, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -788,7 +786,7 @@ cudaError_t launch_root_partitioned(const QueryArgs &q, const RootPartArgs &a, i
     root_part_hist_kernel<<<sm_count * 4, 256, 0, st>>>(a);
     root_part_scan_kernel<<<1, 1024, 0, st>>>(a);
     root_part_scatter_kernel<<<sm_count * 4, 256, 0, st>>>(a);
-    root_part_probe_kernel<<<sm_count * query_ctas_per_sm(), 32 * kQueryWarps, 0, st>>>(a);
+    root_part_probe_kernel<<<sm_count * query_ctas(q), 32 * kQueryWarps, 0, st>>>(a);
     root_part_scan_kernel2<<<sm_count * 8, 32 * kQueryWarps, 0, st>>>(q, a);
     return cudaGetLastError();
 }
