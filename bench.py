@@ -127,13 +127,33 @@ def index_cache_paths(args):
     return d, os.path.join(d, "DONE")
 
 
-def build_index_arrays(args, genomes, lens, ctx):
-    """Hashes every genome with kernel #1 on the GPU, then lays out + peels the HIXF on the CPU (tooling)."""
-    from taxor_b200 import capi, tools
-    t0 = time.time()
+def unpack_2bit(words, n):
+    """2-bit packed bases (first base most significant) -> codes 0..3, pure numpy (the reference arm loads no CUDA library)."""
+    w = np.asarray(words[: (int(n) + 31) // 32], dtype=np.uint64)
+    shifts = np.arange(62, -2, -2, dtype=np.uint64)
+    return ((w[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8).reshape(-1)[: int(n)]
+
+
+def hash_genomes_cpu(args, genomes, lens):
+    """compute_hashes on the host through the oracle (reference arm: no GPU code anywhere on its path)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle import Oracle
+    o = Oracle()
+
+    def one(g):
+        c = unpack_2bit(genomes[g], lens[g])
+        if args.use_syncmer:
+            return o.syncmer_hashes(c, args.k, args.s, args.t)
+        return np.unique(o.kmer_hashes(c, args.k))
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        return list(ex.map(one, range(len(genomes)))), 0
+
+
+def hash_genomes_gpu(args, genomes, lens, ctx):
+    """build-side hashing on the GPU (txr_hash_user_bins: genomes cut into independent segments, per-genome distinct sets)"""
+    from taxor_b200 import capi
     ub = []
     ctx.set_params(k=args.k, s=args.s, t=args.t, use_syncmer=args.use_syncmer, window_size=args.window, error_rate=args.error_rate)
-    # build-side hashing on the GPU (txr_hash_user_bins: genomes cut into independent segments, per-genome distinct sets)
     a, n_seg = 0, 0
     while a < len(genomes):
         b, bases = a, 0
@@ -150,6 +170,15 @@ def build_index_arrays(args, genomes, lens, ctx):
         for i in range(len(part)):
             ub.append(h[int(o[i]):int(o[i + 1])])
         a = b
+    return ub, n_seg
+
+
+def build_index_arrays(args, genomes, lens, ctx):
+    """Hashes every genome (GPU: txr_hash_user_bins; reference arm: the CPU oracle -- same sets), then lays out + peels the
+    HIXF on the CPU (tooling)."""
+    from taxor_b200 import tools
+    t0 = time.time()
+    ub, n_seg = hash_genomes_gpu(args, genomes, lens, ctx) if ctx is not None else hash_genomes_cpu(args, genomes, lens)
     t1 = time.time()
     # explicit thread count: torchrun exports OMP_NUM_THREADS=1, which would make the CPU peeling take half an hour
     hx = tools.BuiltHixf(ub, t_max=args.t_max, seed=1, inplace=True, threads=os.cpu_count() or 1)
@@ -208,24 +237,41 @@ def upload_index(ctx, ix):
     ctx.upload_index(ix.seed, ix.bins, ix.tbins, ix.seg_len, data, ix.bin_off, ix.next_ixf_id, ix.bin_to_ub, ix.n_user_bins)
 
 
-def make_reads(args, genomes, lens, rank):
+class HostArray:
+    """plain numpy stand-in for capi.PinnedArray (reference arm)"""
+
+    def __init__(self, n, dtype):
+        self.array = np.zeros(int(n), dtype=dtype)
+        self.nbytes = self.array.nbytes
+        self.ptr = self.array.ctypes.data
+
+    def free(self):
+        self.array = None
+
+
+def make_reads(args, genomes, lens, rank, pinned=True):
     """This rank's shard of the read set, simulated straight into pinned host memory."""
-    from taxor_b200 import capi, tools
+    from taxor_b200 import tools
+    if pinned:
+        from taxor_b200 import capi
+        Arr = capi.PinnedArray
+    else:
+        Arr = HostArray
     n = args.reads
     if args.read_len_range:
         lo, hi = args.read_len_range
         rl = np.exp(np.random.default_rng(1234 + rank).uniform(np.log(lo), np.log(hi), n)).astype(np.uint32)
     else:
         rl = np.full(n, args.read_len, np.uint32)
-    pin = capi.PinnedArray(int(((rl.astype(np.uint64) + 31) // 32 + 1).sum()), np.uint64)
+    pin = Arr(int(((rl.astype(np.uint64) + 31) // 32 + 1).sum()), np.uint64)
     pin.array[:] = 0
     world = int(os.environ.get("WORLD_SIZE", 1))
     words, off, ln, src = tools.simulate_reads(genomes, lens, rl, args.read_error,
                                                seed=42 + 7919 * rank, out_words=pin.array,
                                                threads=max(1, (os.cpu_count() or 1) // world))
-    off_pin = capi.PinnedArray(n, np.uint64)
+    off_pin = Arr(n, np.uint64)
     off_pin.array[:] = off
-    len_pin = capi.PinnedArray(n, np.uint32)
+    len_pin = Arr(n, np.uint32)
     len_pin.array[:] = ln
     return pin, off_pin, len_pin
 
@@ -289,18 +335,16 @@ class ClockSampler:
 def cpu_run(args, ix, pin_words, off, ln, n_sample, threads):
     """Times oracle.search_batch (restated CPU path, OpenMP over reads) on the first n_sample reads."""
     from oracle.oracle import HixfArrays, Oracle
-    from taxor_b200 import capi
     o = Oracle()
     arrays = HixfArrays(np.ascontiguousarray(ix.seed), np.ascontiguousarray(ix.bins), np.ascontiguousarray(ix.tbins),
                         np.ascontiguousarray(ix.seg_len), [np.ascontiguousarray(x) for x in ix.data],
                         np.ascontiguousarray(ix.bin_off), np.ascontiguousarray(ix.next_ixf_id), np.ascontiguousarray(ix.bin_to_ub))
     h = o.make_hixf(arrays)
-    reads = capi.PackedReads(pin_words, off, ln)
     codes = np.empty(int(ln[:n_sample].astype(np.uint64).sum()), dtype=np.uint8)
     coff = np.zeros(n_sample + 1, dtype=np.uint64)
     at = 0
     for i in range(n_sample):
-        c = capi.unpack_codes(reads, i)
+        c = unpack_2bit(pin_words[int(off[i]):], ln[i])
         codes[at:at + len(c)] = c
         at += len(c)
         coff[i + 1] = at
@@ -323,25 +367,26 @@ def main():
         return 0
 
     import __graft_entry__ as ge
-    from taxor_b200 import capi
     import taxor_b200
     if not (os.path.exists(taxor_b200.LIB_PATH) and os.path.exists(taxor_b200.TOOLS_PATH)):
         ge.build()
+    reference = args.impl == "reference"   # CPU only: no CUDA context, no CUDA library, no torch.cuda on this arm
 
-    import torch
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1 and args.impl == "ours":
-        import torch.distributed as dist
-        import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=60))
-
-    ctx = capi.Context(local_rank)
+    dist, ctx, capi = None, None, None
+    if not reference:
+        from taxor_b200 import capi
+        import torch
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            import torch.distributed as dist
+            import datetime
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=60))
+        ctx = capi.Context(local_rank)
     genomes, lens = make_genomes(args, rank, dist.barrier if dist is not None else None)
 
-    # ---- index: rank 0 builds (GPU hashing + CPU peeling), everybody loads it from /dev/shm ----
+    # ---- index: rank 0 builds (hashing on the GPU -- on the CPU for the reference arm -- then CPU peeling), cached in /dev/shm ----
     d, done = index_cache_paths(args)
     if rank == 0 and not os.path.exists(done):
         hx, info = build_index_arrays(args, genomes, lens, ctx)
@@ -352,13 +397,14 @@ def main():
     if dist is not None:
         dist.barrier()
     ix = LoadedIndex(d)
-    upload_index(ctx, ix)
-    ctx.set_params(k=args.k, s=args.s, t=args.t, use_syncmer=args.use_syncmer, window_size=args.window, error_rate=args.error_rate)
+    if not reference:
+        upload_index(ctx, ix)
+        ctx.set_params(k=args.k, s=args.s, t=args.t, use_syncmer=args.use_syncmer, window_size=args.window, error_rate=args.error_rate)
 
-    pin, off_pin, len_pin = make_reads(args, genomes, lens, rank)
+    pin, off_pin, len_pin = make_reads(args, genomes, lens, rank, pinned=not reference)
     n_reads = args.reads
     bases_per_step = int(len_pin.array.astype(np.uint64).sum())
-    reads = capi.PackedReads(pin.array, off_pin.array, len_pin.array)
+    reads = capi.PackedReads(pin.array, off_pin.array, len_pin.array) if not reference else None
 
     mode = f"k={args.k} s={args.s} t={args.t} syncmers" if args.use_syncmer else f"canonical {args.k}-mers (no syncmers, duplicates kept)"
     rl_txt = (f"{args.read_len_range[0]}-{args.read_len_range[1]} bp (log-uniform, mean {bases_per_step // n_reads})" if args.read_len_range
@@ -371,7 +417,7 @@ def main():
                 "l2": "inputs larger than L2 (packed reads and index each exceed 126 MB); no flush needed"}
 
     # ---------------------------------------------------------------- reference arm (CPU)
-    if args.impl == "reference":
+    if reference:
         n_s = min(n_reads, 2000)
         v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
         n_s = int(min(n_reads, max(200, n_s * args.cpu_seconds / max(dt, 1e-3))))
