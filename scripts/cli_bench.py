@@ -21,6 +21,27 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
+def write_bgzf(src, dst, block=65280):
+    """bgzip-style blocked gzip (BGZF): one gzip member per 64 KiB block, block size in the 'BC' extra field"""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    def member(c):
+        co = zlib.compressobj(1, zlib.DEFLATED, -15)
+        data = co.compress(c) + co.flush()
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", 18 + len(data) + 8 - 1) + data
+                + struct.pack("<II", zlib.crc32(c) & 0xffffffff, len(c)))
+    with open(src, "rb") as f, open(dst, "wb") as out, ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        while True:
+            big = f.read(block * 4096)
+            if not big:
+                break
+            for m in ex.map(member, [big[i:i + block] for i in range(0, len(big), block)]):
+                out.write(m)
+        out.write(member(b""))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=200_000)
@@ -32,6 +53,7 @@ def main():
     ap.add_argument("--work", default="/dev/shm/taxor_b200_cli")
     ap.add_argument("--threads", type=int, default=16)
     ap.add_argument("--gz", action="store_true", help="also time a gzip-compressed copy of the reads")
+    ap.add_argument("--bgzf", action="store_true", help="also time a BGZF (bgzip-style blocked gzip) copy of the reads")
     args = ap.parse_args()
     from taxor_b200 import capi, tools
     import taxor_b200
@@ -68,6 +90,11 @@ def main():
         if not os.path.exists(gz):
             subprocess.run(f"gzip -1 -c {fq} > {gz}", shell=True, check=True)
         files.append(("fastq.gz", gz))
+    if args.bgzf:
+        bg = fq + ".bgzf.gz"
+        if not os.path.exists(bg):
+            write_bgzf(fq, bg)
+        files.append(("fastq.bgzf", bg))
     for tag, path in files:
         for th in sorted({1, args.threads}):
             out = os.path.join(args.work, "out.tsv")

@@ -9,14 +9,62 @@
 
 namespace txr
 {
+namespace
+{
+// BGZF block at p (n bytes left): gzip member with FEXTRA whose 'B','C' subfield holds the block size - 1.
+// Returns the block size, 0 if this is not a BGZF block header.
+size_t bgzf_block_size(const unsigned char *p, size_t n)
+{
+    if (n < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4))
+        return 0;
+    const size_t xlen = p[10] | (size_t)p[11] << 8;
+    if (12 + xlen > n)
+        return 0;
+    for (size_t q = 12; q + 4 <= 12 + xlen;)
+    {
+        const size_t slen = p[q + 2] | (size_t)p[q + 3] << 8;
+        if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen)
+        {
+            const size_t bsize = (p[q + 4] | (size_t)p[q + 5] << 8) + 1;
+            return bsize >= 12 + xlen + 8 && bsize <= n ? bsize : 0;
+        }
+        q += 4 + slen;
+    }
+    return 0;
+}
+} // namespace
+
 RecordScanner::RecordScanner(const std::string &path)
 {
     fd_ = ::open(path.c_str(), O_RDONLY);
     if (fd_ < 0)
         return;
-    unsigned char magic[2] = {0, 0};
-    const ssize_t n = ::pread(fd_, magic, 2, 0);
-    if (n == 2 && magic[0] == 0x1f && magic[1] == 0x8b) // gzip: inflate through zlib, everything else is read() directly
+    unsigned char magic[18] = {0};
+    const ssize_t n = ::pread(fd_, magic, sizeof magic, 0);
+    struct stat st;
+    if (n == 18 && fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && st.st_size >= 28)
+    {
+        // blocked gzip: look at the first header only (BSIZE must fit the file), then map the whole file
+        unsigned char probe[18];
+        memcpy(probe, magic, 18);
+        const size_t xlen = probe[10] | (size_t)probe[11] << 8;
+        if (probe[0] == 0x1f && probe[1] == 0x8b && probe[2] == 8 && (probe[3] & 4) && xlen >= 6 && probe[12] == 'B' && probe[13] == 'C')
+        {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd_, 0);
+            if (m != MAP_FAILED && bgzf_block_size(static_cast<const unsigned char *>(m), (size_t)st.st_size))
+            {
+                bgzf_data_ = static_cast<const unsigned char *>(m);
+                bgzf_size_ = (size_t)st.st_size;
+                madvise(m, bgzf_size_, MADV_SEQUENTIAL);
+                ::close(fd_);
+                fd_ = -1;
+                return;
+            }
+            if (m != MAP_FAILED)
+                munmap(m, (size_t)st.st_size);
+        }
+    }
+    if (n >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) // gzip: inflate through zlib, everything else is read() directly
     {
         gz_ = gzdopen(fd_, "rb");
         if (!gz_)
@@ -36,14 +84,122 @@ RecordScanner::RecordScanner(const std::string &path)
 
 RecordScanner::~RecordScanner()
 {
+    if (bgzf_data_)
+        munmap(const_cast<unsigned char *>(bgzf_data_), bgzf_size_);
     if (gz_)
         gzclose(gz_);
     if (fd_ >= 0)
         ::close(fd_);
 }
 
+// Inflates as many whole BGZF blocks as fit into [dst, dst+cap) in parallel; a block that does not fit is inflated into
+// bgzf_rest_ and handed out piecewise.
+size_t RecordScanner::fill_bgzf(char *dst, size_t cap)
+{
+    size_t got = 0;
+    while (got < cap)
+    {
+        if (bgzf_rest_pos_ < bgzf_rest_.size())
+        {
+            const size_t n = std::min(cap - got, bgzf_rest_.size() - bgzf_rest_pos_);
+            memcpy(dst + got, bgzf_rest_.data() + bgzf_rest_pos_, n);
+            bgzf_rest_pos_ += n;
+            got += n;
+            continue;
+        }
+        if (bgzf_pos_ >= bgzf_size_)
+        {
+            eof_ = true;
+            break;
+        }
+        struct Block
+        {
+            size_t in, in_len, out, out_len;
+            uint32_t crc;
+        };
+        std::vector<Block> blocks;
+        size_t pos = bgzf_pos_, out = got;
+        while (pos < bgzf_size_)
+        {
+            const unsigned char *p = bgzf_data_ + pos;
+            const size_t bsize = bgzf_block_size(p, bgzf_size_ - pos);
+            if (!bsize)
+                throw std::runtime_error("read error (corrupt BGZF block header)");
+            const size_t xlen = p[10] | (size_t)p[11] << 8, hdr = 12 + xlen;
+            const unsigned char *t = p + bsize - 8;
+            const uint32_t crc = t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+            const size_t isize = t[4] | (size_t)t[5] << 8 | (size_t)t[6] << 16 | (size_t)t[7] << 24;
+            if (isize > cap - out)
+                break;
+            blocks.push_back(Block{pos + hdr, bsize - hdr - 8, out, isize, crc});
+            out += isize;
+            pos += bsize;
+        }
+        if (blocks.empty())
+        {
+            // the next block is larger than what is left of the caller's buffer: inflate it aside
+            const unsigned char *p = bgzf_data_ + pos;
+            const size_t bsize = bgzf_block_size(p, bgzf_size_ - pos);
+            const size_t xlen = p[10] | (size_t)p[11] << 8, hdr = 12 + xlen;
+            const unsigned char *t = p + bsize - 8;
+            const size_t isize = t[4] | (size_t)t[5] << 8 | (size_t)t[6] << 16 | (size_t)t[7] << 24;
+            bgzf_rest_.resize(isize);
+            bgzf_rest_pos_ = 0;
+            z_stream zs{};
+            if (inflateInit2(&zs, -15) != Z_OK)
+                throw std::runtime_error("zlib initialisation failed");
+            zs.next_in = const_cast<unsigned char *>(p + hdr);
+            zs.avail_in = (unsigned)(bsize - hdr - 8);
+            zs.next_out = reinterpret_cast<unsigned char *>(bgzf_rest_.data());
+            zs.avail_out = (unsigned)isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            const uint32_t crc = t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+            if (rc != Z_STREAM_END || zs.total_out != isize ||
+                crc32(0, reinterpret_cast<const unsigned char *>(bgzf_rest_.data()), (unsigned)isize) != crc)
+                throw std::runtime_error("read error (corrupt BGZF block)");
+            bgzf_pos_ = pos + bsize;
+            continue;
+        }
+        int bad = 0;
+#pragma omp parallel for schedule(dynamic, 4) if (blocks.size() > 8)
+        for (long i = 0; i < (long)blocks.size(); ++i)
+        {
+            const Block &b = blocks[(size_t)i];
+            z_stream zs{};
+            if (inflateInit2(&zs, -15) != Z_OK)
+            {
+#pragma omp atomic write
+                bad = 1;
+                continue;
+            }
+            zs.next_in = const_cast<unsigned char *>(bgzf_data_ + b.in);
+            zs.avail_in = (unsigned)b.in_len;
+            zs.next_out = reinterpret_cast<unsigned char *>(dst + b.out);
+            zs.avail_out = (unsigned)b.out_len;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END || zs.total_out != b.out_len ||
+                crc32(0, reinterpret_cast<const unsigned char *>(dst + b.out), (unsigned)b.out_len) != b.crc)
+            {
+#pragma omp atomic write
+                bad = 1;
+            }
+        }
+        if (bad)
+            throw std::runtime_error("read error (corrupt BGZF block)");
+        bgzf_pos_ = pos;
+        got = out;
+        if (pos < bgzf_size_)
+            break; // buffer (nearly) full: the next block does not fit
+    }
+    return got;
+}
+
 size_t RecordScanner::fill(char *dst, size_t cap)
 {
+    if (bgzf_data_)
+        return fill_bgzf(dst, cap);
     size_t got = 0;
     while (got < cap && !eof_)
     {

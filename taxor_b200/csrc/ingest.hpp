@@ -4,8 +4,8 @@
 // (src/main/taxor_search.cpp:181-184, 315-321), which parses serially while the workers idle.  Here ONE thread
 // streams the file (inflating if it is gzip) and only finds record boundaries (memchr per line, no copying);
 // the byte work -- IUPAC -> dna4 collapse and 2-bit packing straight into the pinned batch buffer, id strings --
-// is done by a pool of threads on disjoint record ranges.  Record semantics are those of seqio.cpp (the serial
-// reader kept for tests): id = header line without '>' / '@', sequence = all sequence lines joined, one trailing
+// is done by a pool of threads on disjoint record ranges.  Record semantics (those of seqan3's FASTA/FASTQ formats as
+// the search uses them): id = header line without '>' / '@', sequence = all sequence lines joined, one trailing
 // '\r' stripped per line, blank lines between records skipped, FASTQ quality length checked.
 #pragma once
 #include <cstddef>
@@ -32,18 +32,27 @@ public:
     ~RecordScanner();
     RecordScanner(const RecordScanner &) = delete;
     RecordScanner &operator=(const RecordScanner &) = delete;
-    bool ok() const { return fd_ >= 0 || gz_ != nullptr; }
+    bool ok() const { return fd_ >= 0 || gz_ != nullptr || bgzf_data_ != nullptr; }
     // Fills `buf` (resized as needed; `target` bytes unless one record needs more) and appends the descriptors of
     // the complete records it holds to `recs` (cleared first).  The incomplete tail is kept for the next call.
     // Returns false when the file is exhausted and nothing was produced; throws std::runtime_error on malformed input.
     bool next(std::vector<char> &buf, std::vector<RecordRef> &recs, size_t target);
 
+    bool bgzf() const { return bgzf_data_ != nullptr; } // blocked gzip (bgzip): blocks are inflated in parallel
+
 private:
     size_t fill(char *dst, size_t cap);
+    size_t fill_bgzf(char *dst, size_t cap);
     int fd_{-1};
     gzFile gz_{nullptr};
     bool eof_{false};
     std::vector<char> carry_;
+    // BGZF: the compressed file is mapped; every block states its compressed size in the 'BC' extra field and its
+    // inflated size in its trailer, so a run of blocks can be inflated by all cores straight into the caller's buffer
+    const unsigned char *bgzf_data_{nullptr};
+    size_t bgzf_size_{0}, bgzf_pos_{0};
+    std::vector<char> bgzf_rest_; // tail of a block that did not fit the caller's buffer
+    size_t bgzf_rest_pos_{0};
 };
 
 // ---- plain (not gzip) files: mapped, cut into byte segments, segments scanned in parallel ----

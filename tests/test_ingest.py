@@ -138,3 +138,38 @@ def test_mapped_guess_is_not_fooled_by_quality_lines(tmp_path):
         got, rescans = _dump_mapped(p, seg, tmp_path)
         assert got == recs and rescans == 0, (seg, rescans)
     assert _dump(p, 4096, tmp_path) == recs
+
+
+def _write_bgzf(path, blob, block=60000, eof_marker=True):
+    """BGZF as bgzip writes it: gzip members of <= 64 KiB with the 'BC' extra field holding the block size - 1"""
+    import struct
+    import zlib
+    with open(path, "wb") as f:
+        chunks = [blob[i:i + block] for i in range(0, len(blob), block)] + ([b""] if eof_marker else [])
+        for c in chunks:
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            data = co.compress(c) + co.flush()
+            bsize = 18 + len(data) + 8
+            f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize - 1))
+            f.write(data)
+            f.write(struct.pack("<II", zlib.crc32(c) & 0xffffffff, len(c)))
+
+
+@pytest.mark.parametrize("fmt", ["fasta", "fastq"])
+def test_bgzf_blocks_are_inflated_in_parallel_and_in_order(tmp_path, fmt):
+    rng = np.random.default_rng(77 if fmt == "fasta" else 78)
+    recs, blob = _make(rng, fmt, 400, b"\n", 0 if fmt == "fastq" else 70)
+    p = tmp_path / f"x.{fmt}.gz"
+    _write_bgzf(p, blob)
+    assert gzip.open(p, "rb").read() == blob             # it is a valid multi-member gzip file
+    for target in (1 << 22, 1 << 16, 70_000, 1000, 64):  # buffers larger / smaller than one 60 kB block
+        assert _dump(p, target, tmp_path) == recs, target
+    _write_bgzf(p, blob, block=4096, eof_marker=False)    # many small blocks, no EOF marker block
+    assert _dump(p, 1 << 20, tmp_path) == recs
+    # a flipped payload byte is caught by the block CRC (or by inflate)
+    raw = bytearray(p.read_bytes())
+    raw[len(raw) // 2] ^= 0x5A
+    bad = tmp_path / "bad.gz"
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(RuntimeError, match="corrupt|start"):
+        _dump(bad, 1 << 20, tmp_path)
