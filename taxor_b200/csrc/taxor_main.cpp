@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <atomic>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -386,6 +389,9 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     // chunk pool (pinned): scan -> pack jobs -> GPU workers -> ordered writer
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const unsigned n_pack = cfg.threads_given ? cfg.threads : std::min(16u, hw);
+#ifdef _OPENMP
+    omp_set_num_threads((int)n_pack); // block-parallel BGZF inflation inside the scanner obeys --threads as well
+#endif
     const size_t n_chunks = 2 * ctxs.size() + 2;
     std::vector<Chunk> pool(n_chunks);
     Channel<Chunk *> free_q, work_q, done_q;

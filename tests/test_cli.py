@@ -69,9 +69,12 @@ def test_cli_end_to_end_result_file(tmp_path, oracle, built_libs):
     open(fa, "w").write(fasta_text(records))
     with gzip.open(fqgz, "wt") as f:
         f.write(fastq_text(records))
+    from tests.test_ingest import _write_bgzf
+    fqbgzf = tmp_path / "r.bgzf.fastq.gz"
+    _write_bgzf(fqbgzf, fastq_text(records).encode(), block=20000)      # blocked gzip: inflated block-parallel
     expect = H.oracle_tsv(oracle, ds.arrays, species, records, k=22, s=12, t=5, use_syncmer=True, error_rate=0.1)
     assert expect.count("\n") > len(records)                   # several reads report more than one reference
-    for q in (fq, fa, fqgz):
+    for q in (fq, fa, fqgz, fqbgzf):
         out = tmp_path / (q.name + ".tsv")
         r = run_cli("search", "--index-file", str(idx_path), "--query-file", str(q), "--output-file", str(out), "--error-rate", "0.1",
                     "--threads", "4")
