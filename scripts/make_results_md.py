@@ -65,6 +65,16 @@ def main():
             tag, th = k.rsplit("_threads", 1)
             out.append(f"| {tag} {v['file_GB']} GB | {th} | {v['index_load_s']:.3f} | {v['index_upload_s']:.2f} | {v['ingest_search_write_s']:.2f} | "
                        f"{v['Mbases_per_s_search_phase'] / 1e3:.2f} | {v['wall_s']:.1f} |")
+    cli2 = load("r1_cli_bench_1GBindex_bgzf.json")
+    if cli2:
+        out.append("")
+        out.append("Same script on a 1 GB index with a BGZF copy of the reads (`r1_cli_bench_1GBindex_bgzf.json`):")
+        out.append("")
+        out.append("| input | pack threads | ingest+search+write s | Gbases/s in that phase |")
+        out.append("|---|---|---|---|")
+        for k, v in cli2["runs"].items():
+            tag, th = k.rsplit("_threads", 1)
+            out.append(f"| {tag} {v['file_GB']} GB | {th} | {v['ingest_search_write_s']:.2f} | {v['Mbases_per_s_search_phase'] / 1e3:.2f} |")
     print("\n".join(out))
 
 
