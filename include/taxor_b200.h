@@ -155,6 +155,11 @@ typedef struct
     const uint64_t *hashes;
     uint64_t n_segments;               /* how many independent pieces the sequences were hashed in            */
 } txr_bin_hashes;
+/* The cutting alone (pure host code, no GPU): k-mer window indices at which a sequence of `len` bases may be cut into
+ * independently hashed pieces of about target_windows windows (>= 64).  cuts[0] is 0; piece i covers the windows
+ * [cuts[i], cuts[i+1]), i.e. the bases [cuts[i], cuts[i+1] + span - 1) with span = k (syncmers, k-mers) or window_size. */
+int txr_plan_segments(const txr_params *params, const uint64_t *words, uint64_t len, uint64_t target_windows,
+                      uint64_t *cuts, uint64_t cap, uint64_t *n_cuts);
 int txr_hash_user_bins(txr_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len,
                        uint64_t n_seqs, const uint32_t *seq_bin, uint64_t n_bins, txr_bin_hashes *out);
 

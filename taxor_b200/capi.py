@@ -96,6 +96,7 @@ def lib():
     L.txr_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.txr_hash_batch.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int, C.POINTER(vp), C.POINTER(vp)]
     L.txr_hash_user_bins.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(BinHashes)]
+    L.txr_plan_segments.argtypes = [C.POINTER(Params), vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.txr_ixf_bulk_count.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp]
     _LIB = L
     return L
@@ -105,7 +106,7 @@ EXPORTED = ["txr_last_error", "txr_version", "txr_ctx_create", "txr_ctx_destroy"
             "txr_index_upload", "txr_params_set", "txr_threshold_get", "txr_threshold_eval", "txr_packed_words", "txr_pack_2bit",
             "txr_pack_codes", "txr_unpack_codes", "txr_host_alloc", "txr_host_free", "txr_search",
             "txr_reads_upload", "txr_reads_free", "txr_search_resident", "txr_get_timing", "txr_hash_batch",
-            "txr_hash_user_bins", "txr_ixf_bulk_count"]
+            "txr_hash_user_bins", "txr_plan_segments", "txr_ixf_bulk_count"]
 
 
 def _check(rc: int) -> None:
@@ -207,6 +208,16 @@ class SearchResult:
             k = self.keep[a:b]
             return ub[k], cnt[k]
         return ub, cnt
+
+
+def plan_segments(words: np.ndarray, length: int, target_windows: int, *, k, s=0, use_syncmer=True, window_size=None) -> np.ndarray:
+    """txr_plan_segments (host only): the window indices at which a sequence may be cut into independently hashed pieces."""
+    p = Params(k, s, 0, int(use_syncmer), k if window_size is None else window_size, 1, -1.0, 0.04)
+    cap = int(length) // max(int(target_windows), 1) + 2
+    cuts = np.zeros(cap, dtype=np.uint64)
+    n = C.c_uint64()
+    _check(lib().txr_plan_segments(C.byref(p), words.ctypes.data, int(length), int(target_windows), cuts.ctypes.data, cap, C.byref(n)))
+    return cuts[: n.value].copy()
 
 
 def threshold_eval(count: int, scaling_factor: float = 1.0, *, k, use_syncmer=True, window_size=None, percentage=-1.0,

@@ -1653,6 +1653,47 @@ uint64_t segment_windows()
 }
 } // namespace
 
+// Cut points (k-mer window indices, multiples of 32, ascending, first = 0) of one sequence: a cut is only placed at a
+// window whose scan state is history free, so the pieces [cut_i, cut_{i+1}) can be hashed as independent reads.
+static void plan_cuts(const txr_params &p, uint64_t kmer_seed, const uint64_t *w, uint64_t L, uint64_t target, std::vector<uint64_t> &cuts)
+{
+    const int k = p.kmer_size;
+    const int span = p.use_syncmer ? k : std::max<int>(k, (int)p.window_size); // bases a window's state test reads
+    const uint64_t n_win = L >= (uint64_t)k ? L - k + 1 : 0;
+    cuts.assign(1, 0);
+    uint64_t start = 0;
+    while (n_win > start + target + target / 2)
+    {
+        uint64_t cand = (start + target + 31) & ~31ull, cut = 0;
+        for (int tries = 0; tries < 256 && cand + span <= L && cand + target / 4 < n_win; ++tries, cand += 32)
+            if (state_is_history_free(p, kmer_seed, w, cand))
+            {
+                cut = cand;
+                break;
+            }
+        if (!cut)
+            break; // no history-free window nearby (a long repeat): the rest of the sequence stays one piece
+        cuts.push_back(cut);
+        start = cut;
+    }
+}
+
+int txr_plan_segments(const txr_params *p, const uint64_t *words, uint64_t len, uint64_t target_windows, uint64_t *cuts,
+                      uint64_t cap, uint64_t *n_cuts)
+{
+    if (!p || !words || !n_cuts || (!cuts && cap) || target_windows < 64)
+        return set_error(TXR_ERR_ARG, "bad argument");
+    if (p->kmer_size < 1 || p->kmer_size > 32 || (p->use_syncmer && (p->syncmer_size < 1 || p->syncmer_size >= p->kmer_size)) ||
+        (!p->use_syncmer && (p->window_size < p->kmer_size || p->window_size - p->kmer_size + 1 > (uint32_t)kMaxMinimiserValues)))
+        return set_error(TXR_ERR_ARG, "parameters out of range");
+    std::vector<uint64_t> v;
+    plan_cuts(*p, 0x8F3F73B5CF1C9ADEULL >> (64u - 2u * p->kmer_size), words, len, target_windows, v);
+    *n_cuts = v.size();
+    for (size_t i = 0; i < v.size() && i < cap; ++i)
+        cuts[i] = v[i];
+    return v.size() <= cap ? TXR_OK : set_error(TXR_ERR_OVERFLOW, "%zu cuts, room for %llu", v.size(), (unsigned long long)cap);
+}
+
 int txr_hash_user_bins(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_seqs,
                        const uint32_t *seq_bin, uint64_t n_bins, txr_bin_hashes *out)
 {
@@ -1673,34 +1714,20 @@ int txr_hash_user_bins(txr_ctx *c, const uint64_t *words, const uint64_t *word_o
     const int k = p.kmer_size;
     // 1. segments: cut long sequences at history-free windows that start on a word boundary
     std::vector<uint64_t> seg_off;
-    std::vector<uint32_t> seg_len, seg_bin, seg_seq;
-    const int span = p.use_syncmer ? k : std::max<int>(k, (int)p.window_size); // bases a window's state test reads
-    const uint64_t kSegmentWindows = segment_windows();
+    std::vector<uint32_t> seg_len, seg_bin;
+    const int span = p.use_syncmer ? k : std::max<int>(k, (int)p.window_size);
+    const uint64_t target = segment_windows();
+    std::vector<uint64_t> cuts;
     for (uint64_t q = 0; q < n_seqs; ++q)
     {
-        const uint64_t L = len[q], n_win = L >= (uint64_t)k ? L - k + 1 : 0;
-        const uint64_t *w = words + word_off[q];
-        uint64_t start = 0;
-        while (true)
+        const uint64_t L = len[q];
+        plan_cuts(p, c->kmer_seed, words + word_off[q], L, target, cuts);
+        for (size_t i = 0; i < cuts.size(); ++i)
         {
-            uint64_t cut = n_win; // no cut: the segment runs to the end of the sequence
-            if (n_win > start + kSegmentWindows + kSegmentWindows / 2)
-            {
-                uint64_t cand = (start + kSegmentWindows + 31) & ~31ull;
-                for (int tries = 0; tries < 256 && cand + span <= L && cand + kSegmentWindows / 4 < n_win; ++tries, cand += 32)
-                    if (state_is_history_free(p, c->kmer_seed, w, cand))
-                    {
-                        cut = cand;
-                        break;
-                    }
-            }
-            seg_off.push_back(word_off[q] + start / 32);
-            seg_len.push_back((uint32_t)(cut == n_win ? L - start : cut - start + span - 1));
+            const bool last = i + 1 == cuts.size();
+            seg_off.push_back(word_off[q] + cuts[i] / 32);
+            seg_len.push_back((uint32_t)(last ? L - cuts[i] : cuts[i + 1] - cuts[i] + span - 1));
             seg_bin.push_back(seq_bin[q]);
-            seg_seq.push_back((uint32_t)q);
-            if (cut == n_win)
-                break;
-            start = cut;
         }
     }
     const uint64_t n_seg = seg_off.size();

@@ -87,3 +87,50 @@ def test_threshold_mirror_matches_oracle(built_libs, oracle):
                 got = capi.threshold_eval(c, sf, k=k, use_syncmer=syn, window_size=w, percentage=p, error_rate=e)
                 assert got == oracle.threshold_get(ot, c, sf), (w, k, p, e, syn, c, sf)
     assert capi.threshold_eval(0, 1.0, k=22, use_syncmer=True, window_size=20, error_rate=0.05) == 0
+
+
+def _tie_heavy_sequences(rng, n):
+    out = []
+    for _ in range(n):
+        x = rng.integers(0, 4, int(rng.integers(2000, 30000)), dtype=np.uint8)
+        for _ in range(int(rng.integers(0, 10))):
+            at, ln = int(rng.integers(0, len(x) - 1500)), int(rng.integers(20, 1500))
+            kind = rng.integers(0, 3)
+            if kind == 0:
+                x[at:at + ln] = rng.integers(0, 4)                                        # homopolymer
+            elif kind == 1:
+                x[at:at + ln] = np.resize(rng.integers(0, 4, int(rng.integers(2, 7)), dtype=np.uint8), ln)   # tandem repeat
+            else:
+                half = x[at:at + ln // 2].copy()
+                x[at + ln // 2:at + 2 * (ln // 2)] = (3 - half)[::-1]                     # reverse-complement palindrome
+        out.append(x)
+    return out
+
+
+@pytest.mark.parametrize("mode", ["syncmer", "syncmer_t1", "kmer", "minimiser"])
+def test_segment_cuts_are_history_free(oracle, built_libs, mode):
+    """txr_plan_segments (host only): hashing the pieces independently gives exactly what one scan of the whole sequence
+    gives -- the property txr_hash_user_bins rests on -- checked with the ORACLE's scan on tie-heavy sequences."""
+    from taxor_b200 import capi
+    rng = np.random.default_rng({"syncmer": 1, "syncmer_t1": 2, "kmer": 3, "minimiser": 4}[mode])
+    k, s, t, w = {"syncmer": (22, 12, 5, 20), "syncmer_t1": (16, 8, 1, 20), "kmer": (20, 0, 0, 20), "minimiser": (20, 0, 0, 33)}[mode]
+    syn = mode.startswith("syncmer")
+    span = k if syn else w
+    n_cut = 0
+    for x in _tie_heavy_sequences(rng, 40):
+        words = capi.pack_codes([x]).words
+        cuts = capi.plan_segments(words, len(x), 96, k=k, s=s, use_syncmer=syn, window_size=w)
+        assert cuts[0] == 0 and np.all(cuts % 32 == 0) and np.all(np.diff(cuts.astype(np.int64)) > 0)
+        n_cut += len(cuts) - 1
+        pieces = [x[int(cuts[i]):(int(cuts[i + 1]) + span - 1 if i + 1 < len(cuts) else len(x))] for i in range(len(cuts))]
+        if syn:
+            whole = oracle.syncmer_hashes_raw(x, k, s, t)
+            parts = np.concatenate([oracle.syncmer_hashes_raw(p, k, s, t) for p in pieces])
+            assert np.array_equal(whole, parts)                     # same emissions in the same order
+        elif w == k:
+            assert np.array_equal(oracle.kmer_hashes(x, k), np.concatenate([oracle.kmer_hashes(p, k) for p in pieces]))
+        else:
+            whole = set(oracle.minimiser_hashes(x, k, w).tolist())
+            parts = set(np.concatenate([oracle.minimiser_hashes(p, k, w) for p in pieces]).tolist())
+            assert whole == parts                                   # a piece re-reports its first minimiser: equal as sets
+    assert n_cut > 200                                              # the sequences really were cut, ties and all
