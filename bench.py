@@ -66,6 +66,14 @@ def parse_args():
                     help="reads per internal batch (0: library default)")
     ap.add_argument("--cache", default=os.environ.get("TAXOR_BENCH_CACHE", "/dev/shm/taxor_b200_bench"))
     args = ap.parse_args()
+    try:                                     # the cache lives in /dev/shm when that is writable, else in the temp dir
+        os.makedirs(args.cache, exist_ok=True)
+        if not os.access(args.cache, os.W_OK):
+            raise OSError
+    except OSError:
+        import tempfile
+        args.cache = os.path.join(tempfile.gettempdir(), "taxor_b200_bench")
+        os.makedirs(args.cache, exist_ok=True)
     w = WORKLOADS[args.workload]
     args.k, args.s, args.t, args.use_syncmer = w.get("k", K), w.get("s", S), w.get("t", T), w.get("use_syncmer", True)
     args.window = 20 if args.use_syncmer else args.k
