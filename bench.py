@@ -454,7 +454,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # (1) device-resident: kernels only.  One pipeline slot so that the per-stage CUDA events are not overlapped
+    # (1) device-resident: kernels only (all kernels run on one stream in batch order, so the per-stage CUDA events do not overlap)
     mean_len = max(1, bases_per_step // max(n_reads, 1))
     batch_kw = dict(max_batch_reads=args.batch_reads, max_batch_bases=int(args.batch_reads * mean_len * 1.1)) if args.batch_reads else {}
     ctx.configure(n_slots=int(os.environ.get("TAXOR_BENCH_RESIDENT_SLOTS", 2)), **batch_kw)
