@@ -129,6 +129,8 @@ size_t RecordScanner::fill_bgzf(char *dst, size_t cap)
             const unsigned char *t = p + bsize - 8;
             const uint32_t crc = t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
             const size_t isize = t[4] | (size_t)t[5] << 8 | (size_t)t[6] << 16 | (size_t)t[7] << 24;
+            if (isize > (1u << 16)) // a BGZF block holds at most 64 KiB: a larger claim is damage, not a reason to allocate
+                throw std::runtime_error("read error (corrupt BGZF block size)");
             if (isize > cap - out)
                 break;
             blocks.push_back(Block{pos + hdr, bsize - hdr - 8, out, isize, crc});
@@ -506,8 +508,8 @@ void join_record(const char *raw, const RecordRef &r, std::string &out)
     while (p < end)
     {
         const char *e = static_cast<const char *>(memchr(p, '\n', (size_t)(end - p)));
-        const char *le = e ? e : end;
-        out.append(p, line_len(p, le));
+        // the span ends where the last line's bases end: its line terminator ('\r') is already outside
+        out.append(p, e ? line_len(p, e) : (size_t)(end - p));
         p = e ? e + 1 : end;
     }
 }

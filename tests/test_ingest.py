@@ -173,3 +173,21 @@ def test_bgzf_blocks_are_inflated_in_parallel_and_in_order(tmp_path, fmt):
     bad.write_bytes(bytes(raw))
     with pytest.raises(RuntimeError, match="corrupt|start"):
         _dump(bad, 1 << 20, tmp_path)
+
+
+def test_ingest_fuzz_under_sanitizers(tmp_path):
+    """tests/fuzz/ingest_fuzz.cpp built with -fsanitize=address,undefined: mutated FASTA/FASTQ through the streaming and the
+    mapped byte-range path; no crash, no sanitizer report, and both paths accept/reject and parse alike."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    exe = str(tmp_path / "ingest_fuzz")
+    build = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fopenmp", "-o", exe,
+                            os.path.join(root, "tests/fuzz/ingest_fuzz.cpp"), os.path.join(root, "taxor_b200/csrc/ingest.cpp"), "-lz"],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr.lower():
+        pytest.skip("compiler without sanitizer runtimes")
+    assert build.returncode == 0, build.stderr[-2000:]
+    run = subprocess.run([exe, str(tmp_path / "f.txt"), "3000", "11"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "fuzz ok" in run.stdout, run.stdout[-500:] + run.stderr[-3000:]
