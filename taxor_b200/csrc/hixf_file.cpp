@@ -131,7 +131,8 @@ struct Reader
         if (need(n * 8))
         {
             v.resize(n);
-            memcpy(v.data(), p, n * 8);
+            if (n)
+                memcpy(v.data(), p, n * 8);
             p += n * 8;
         }
         return v;
@@ -141,7 +142,9 @@ struct Reader
 // parses everything from the IXF vector to the end of the file with one candidate record order
 std::string parse_hixf_tail(Reader rd, TaxorIndexFile &idx, const IxfRecordSpec &spec)
 {
-    const uint64_t n_ixf = rd.count(8);
+    // every record is at least its scalars and the length of its fingerprint vector: a count beyond that is damage,
+    // not a reason to allocate
+    const uint64_t n_ixf = rd.count(8 * (spec.scalars.size() + 1));
     if (!rd.ok || n_ixf == 0)
         return "IXF vector length unreadable";
     idx.ixf.assign(n_ixf, IxfRecord{});

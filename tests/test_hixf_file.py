@@ -64,3 +64,23 @@ def test_malformed_files_are_rejected(tmp_path, built_libs):
     with pytest.raises(RuntimeError):
         tools.HixfFile(path, "bins,tbins,slots,seed")                      # wrong explicit order
     hx.close()
+
+
+def test_hixf_reader_fuzz_under_sanitizers(tmp_path):
+    """tests/fuzz/hixf_fuzz.cpp built with -fsanitize=address,undefined: damaged index files (flipped bytes, huge lengths,
+    truncation, trailing bytes) are parsed or rejected with a message -- never a crash or a sanitizer report."""
+    import os
+    import shutil
+    import subprocess
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    exe = str(tmp_path / "hixf_fuzz")
+    build = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", exe,
+                            os.path.join(root, "tests/fuzz/hixf_fuzz.cpp"), os.path.join(root, "taxor_b200/csrc/hixf_file.cpp")],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr.lower():
+        pytest.skip("compiler without sanitizer runtimes")
+    assert build.returncode == 0, build.stderr[-2000:]
+    run = subprocess.run([exe, str(tmp_path / "f.hixf"), "3000", "5"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "fuzz ok" in run.stdout and "runtime error" not in run.stderr, run.stdout[-300:] + run.stderr[-3000:]
