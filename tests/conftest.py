@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _native_libraries_are_current():
+    """`make` for the product libraries and the oracle before the first test: a fresh checkout has no .so files (they are
+    git-ignored) and an edited source must not be tested through a stale binary.  Test infrastructure only -- the
+    product itself never builds or falls back at run time."""
+    import taxor_b200
+    taxor_b200.build_all()
+    from oracle import oracle as orc
+    orc.build()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle.oracle import Oracle
