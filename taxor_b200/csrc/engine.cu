@@ -905,8 +905,15 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
         R.count.resize(base_hits + n_hits);
         R.keep.resize(base_hits + n_hits);
         uint64_t n_hashes = 0, hash_bytes = 0;
-        for (uint32_t r = 0; r < n; ++r)
+        const size_t base_reads = R.hash_count.size();
+        R.hash_count.resize(base_reads + n);
+        R.threshold.resize(base_reads + n);
+        R.hit_begin.resize(base_reads + n);
+        // reads are independent and write disjoint ranges: the pass of the LAST batch is what nothing overlaps
+#pragma omp parallel for schedule(static) reduction(+ : n_hashes, hash_bytes) if (n > 16384)
+        for (long rr = 0; rr < (long)n; ++rr)
         {
+            const uint32_t r = (uint32_t)rr;
             uint32_t *o = order.data() + begin[r];
             const uint32_t cnt = begin[r + 1] - begin[r];
             if (cnt > 1)
@@ -922,12 +929,12 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
                 // taxor_search.cpp:285: dropped iff double(count) < double(max_count) * 0.8
                 R.keep[at] = !(static_cast<double>(h_cnt[o[i]]) < static_cast<double>(max_count) * 0.8);
             }
-            R.hash_count.push_back(h_count[r]);
+            R.hash_count[base_reads + r] = h_count[r];
             if (c->per_read_thr)
-                R.threshold.push_back(s.h_thr.as<uint64_t>()[r]);
+                R.threshold[base_reads + r] = s.h_thr.as<uint64_t>()[r];
             else
-                R.threshold.push_back(h_count[r] < c->lut.size() ? c->lut[h_count[r]] : c->thresholder.get(h_count[r], 1.0));
-            R.hit_begin.push_back(base_hits + begin[r]);
+                R.threshold[base_reads + r] = h_count[r] < c->lut.size() ? c->lut[h_count[r]] : c->thresholder.get(h_count[r], 1.0);
+            R.hit_begin[base_reads + r] = base_hits + begin[r];
             n_hashes += h_count[r];
             hash_bytes += (m.len[r] + 3) / 4;
         }
