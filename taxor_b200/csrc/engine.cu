@@ -960,22 +960,26 @@ static void finish_result(txr_ctx *c, txr_result *out)
     out->keep = R.keep.data();
 }
 
-// split reads [0, n) into batches bounded by reads and bases.  `ramp`: when the reads come from the host, the first
-// batch is an eighth and the second a half of the limits, so that the copy nothing can overlap with is short.
+// split reads [0, n) into batches bounded by reads and bases.  `ramp`: when the reads come from the host, the batches
+// grow geometrically from 1/16 of the limits: nothing can overlap the first copy, and a batch's copy hides behind the
+// kernels of the batch before it only if it is not much larger (PCIe moves a batch in about half the time the kernels
+// need for it, hence the factor 1.8).
 static void plan_batches(const txr_ctx *c, const uint32_t *len, uint64_t n, std::vector<std::pair<uint64_t, uint32_t>> &out,
                          bool ramp = false)
 {
     out.clear();
+    double scale = ramp ? 1.0 / 16.0 : 1.0;
     uint64_t i = 0;
     while (i < n)
     {
-        const uint64_t div = !ramp ? 1 : out.empty() ? 8 : out.size() == 1 ? 2 : 1;
-        const uint64_t max_reads = std::max<uint64_t>(c->max_batch_reads / div, 1), max_bases = std::max<uint64_t>(c->max_batch_bases / div, 1);
+        const uint64_t max_reads = std::max<uint64_t>((uint64_t)((double)c->max_batch_reads * scale), 1);
+        const uint64_t max_bases = std::max<uint64_t>((uint64_t)((double)c->max_batch_bases * scale), 1);
         uint64_t bases = 0, j = i;
         while (j < n && j - i < max_reads && (j == i || bases + len[j] <= max_bases))
             bases += len[j++];
         out.emplace_back(i, (uint32_t)(j - i));
         i = j;
+        scale = std::min(1.0, scale * 1.8);
     }
 }
 
