@@ -149,10 +149,8 @@ def hash_genomes_cpu(args, genomes, lens):
     o = Oracle()
 
     def one(g):
-        c = unpack_2bit(genomes[g], lens[g])
-        if args.use_syncmer:
-            return o.syncmer_hashes(c, args.k, args.s, args.t)
-        return np.unique(o.kmer_hashes(c, args.k))
+        c = unpack_2bit(genomes[g], lens[g])      # raw emissions: the builder sorts and de-duplicates every user bin anyway
+        return o.syncmer_hashes_raw(c, args.k, args.s, args.t) if args.use_syncmer else o.kmer_hashes(c, args.k)
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
         return list(ex.map(one, range(len(genomes)))), 0
 

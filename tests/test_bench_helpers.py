@@ -39,7 +39,7 @@ def test_cpu_hashing_of_the_reference_arm_equals_the_oracle(oracle, tmp_path):
         ref = tools.genome(1000 + g, int(lens[g]))
         assert np.array_equal(genomes[g], ref)
         exp = oracle.syncmer_hashes(bench.unpack_2bit(ref, lens[g]), 22, 12, 5)
-        assert np.array_equal(np.sort(ub[g]), np.sort(exp))
+        assert np.array_equal(np.unique(ub[g]), np.sort(exp))
 
 
 def test_index_depth_from_cached_arrays(oracle, tmp_path):
