@@ -426,7 +426,9 @@ def main():
     if reference:
         n_s = min(n_reads, 2000)
         v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
-        n_s = int(min(n_reads, max(200, n_s * args.cpu_seconds / max(dt, 1e-3))))
+        # bounded sample per step: all warm-up + timed steps together stay within about two minutes
+        per_step = min(args.cpu_seconds, 120.0 / max(args.steps + args.warmup, 1))
+        n_s = int(min(n_reads, max(200, n_s * per_step / max(dt, 1e-3))))
         vals = []
         for i in range(args.warmup + args.steps):
             v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
