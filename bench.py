@@ -42,6 +42,11 @@ WORKLOADS = {
                  t_max=128, read_len_range=(1000, 50_000), read_error=0.03, error_rate=0.05),
     # configs[4] shape at 1/10 of its size: 20,000 genomes under t_max=64 give a three-level hierarchy
     "deep": dict(label="configs[4] shape (three-level hierarchy, 10 GB)", genomes=20000, genome_len=2_000_000, t_max=64),
+    # configs[4] shape with the WIDE root real GTDB layouts have (taxor build picks t_max up to 4096, taxor_build.cpp:173-187):
+    # 102,400 user bins, root of 4096 technical bins, 16-bin IXFs below it (three levels), ~1/20 of the 100 GB the config names
+    # (what one box hashes and peels in a few minutes); 250k reads per step because every read streams 11 MB of root rows
+    "gtdb": dict(label="configs[4] shape at ~1/20 scale (102,400 user bins, 4096-bin root, three levels)", genomes=102_400,
+                 genome_len=100_000, min_genome_len=30_000, t_max=4096, t_max_lower=16, reads=250_000),
 }
 
 
@@ -58,6 +63,7 @@ def parse_args():
     ap.add_argument("--genome-len", type=int, default=int(os.environ.get("TAXOR_BENCH_GENOME_LEN", 40_000_000)),
                     help="mean genome length; 40 Mbp x 1,000 genomes gives the ~10 GB HIXF configs[1] names")
     ap.add_argument("--t-max", type=int, default=64)
+    ap.add_argument("--t-max-lower", type=int, default=0, help="bin budget of the IXFs below the root (0: same as --t-max)")
     ap.add_argument("--read-error", type=float, default=0.05)
     ap.add_argument("--error-rate", type=float, default=0.10, help="taxor search --error-rate (see DESIGN.md workload)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
@@ -81,7 +87,7 @@ def parse_args():
     args.read_len_range = w.get("read_len_range")
     args.label = w["label"]
     explicit = {a.split("=")[0] for a in sys.argv[1:] if a.startswith("--")}
-    for key in ("genomes", "genome_len", "t_max", "read_error", "error_rate"):
+    for key in ("genomes", "genome_len", "t_max", "t_max_lower", "read_error", "error_rate", "reads"):
         if key in w and "--" + key.replace("_", "-") not in explicit:
             setattr(args, key, w[key])
     return args
@@ -131,6 +137,8 @@ def make_genomes(args, rank=0, barrier=None):
 
 def index_cache_paths(args):
     tag = f"g{args.genomes}_l{args.genome_len}_m{getattr(args, 'min_genome_len', 20_000)}_t{args.t_max}_k{getattr(args, 'k', K)}s{getattr(args, 's', S)}"
+    if getattr(args, "t_max_lower", 0):
+        tag += f"_tl{args.t_max_lower}"
     d = os.path.join(args.cache, tag)
     return d, os.path.join(d, "DONE")
 
@@ -187,7 +195,7 @@ def build_index_arrays(args, genomes, lens, ctx):
     ub, n_seg = hash_genomes_gpu(args, genomes, lens, ctx) if ctx is not None else hash_genomes_cpu(args, genomes, lens)
     t1 = time.time()
     # explicit thread count: torchrun exports OMP_NUM_THREADS=1, which would make the CPU peeling take half an hour
-    hx = tools.BuiltHixf(ub, t_max=args.t_max, seed=1, inplace=True, threads=os.cpu_count() or 1)
+    hx = tools.BuiltHixf(ub, t_max=args.t_max, seed=1, inplace=True, threads=os.cpu_count() or 1, t_max_lower=getattr(args, "t_max_lower", 0))
     del ub
     t2 = time.time()
     info = dict(hash_s=round(t1 - t0, 2), hash_segments=n_seg, build_s=round(t2 - t1, 2), n_ixf=hx.n_ixf, fp_bytes=hx.fp_bytes,
@@ -546,7 +554,9 @@ def main():
                               "source": "profiles/r1_gather_bench2.json (random rows of the root IXF's width, 8 GiB table)"}
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "ixf_query_small_kernel (kernel #2, all HIXF levels of a batch)",
+        wide = int(ix.tbins[0]) > 512
+        roof = {"bound": "hbm", "kernel": ("ixf_query_large_kernel (CTA per item, root rows of %d bytes) + ixf_query_small_kernel below" % int(ix.tbins[0])) if wide
+                else "ixf_query_small_kernel (kernel #2, all HIXF levels of a batch)",
                 "achieved": q_gbs, "peak": peak, "unit": "GB/s", "frac": q_gbs / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic": traffic, "traffic_source": traffic_src, "random_gather_ceiling": gather,

@@ -113,6 +113,9 @@ int txr_ctx_configure(txr_ctx *ctx, uint64_t max_batch_reads, uint64_t max_batch
 
 /* one-time re-layout of the index into HBM; replaces load_index() + index.ixf() (load_index.hpp:27-38) */
 int txr_index_upload(txr_ctx *ctx, const txr_hixf_view *index);
+/* replicate the index already resident in `src` (same or another GPU) into `dst`, device to device (NVLink between
+ * peers): the multi-GPU form of the reference's "load once, share between threads" (taxor_search.cpp:162-180) */
+int txr_index_clone(txr_ctx *dst, txr_ctx *src);
 int txr_params_set(txr_ctx *ctx, const txr_params *params);
 /* hixf::threshold::threshold::get (src/hixf/search/threshold.hpp:51-81) with the context's parameters */
 int txr_threshold_get(txr_ctx *ctx, uint64_t hash_count, double scaling_factor, uint64_t *out);

@@ -76,6 +76,7 @@ def lib():
     L.txr_ctx_set_stream.argtypes = [vp, vp]
     L.txr_ctx_configure.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int]
     L.txr_index_upload.argtypes = [vp, C.POINTER(HixfView)]
+    L.txr_index_clone.argtypes = [vp, vp]
     L.txr_params_set.argtypes = [vp, C.POINTER(Params)]
     L.txr_threshold_get.argtypes = [vp, C.c_uint64, C.c_double, C.POINTER(C.c_uint64)]
     L.txr_threshold_eval.argtypes = [C.POINTER(Params), C.c_uint64, C.c_double, C.POINTER(C.c_uint64)]
@@ -103,7 +104,7 @@ def lib():
 
 
 EXPORTED = ["txr_last_error", "txr_version", "txr_ctx_create", "txr_ctx_destroy", "txr_ctx_set_stream", "txr_ctx_configure",
-            "txr_index_upload", "txr_params_set", "txr_threshold_get", "txr_threshold_eval", "txr_packed_words", "txr_pack_2bit",
+            "txr_index_upload", "txr_index_clone", "txr_params_set", "txr_threshold_get", "txr_threshold_eval", "txr_packed_words", "txr_pack_2bit",
             "txr_pack_codes", "txr_unpack_codes", "txr_host_alloc", "txr_host_free", "txr_search",
             "txr_reads_upload", "txr_reads_free", "txr_search_resident", "txr_get_timing", "txr_hash_batch",
             "txr_hash_user_bins", "txr_plan_segments", "txr_ixf_bulk_count"]
@@ -267,6 +268,10 @@ class Context:
         ub = np.ascontiguousarray(bin_to_ub, dtype=np.int64)
         v = HixfView(n, ixfs, bin_off.ctypes.data, nx.ctypes.data, ub.ctypes.data, int(n_user_bins))
         _check(self._L.txr_index_upload(self._h, C.byref(v)))
+
+    def clone_index_from(self, other: "Context") -> None:
+        """txr_index_clone: device-to-device replica of the index resident in `other` (NVLink between peer GPUs)."""
+        _check(self._L.txr_index_clone(self._h, other._h))
 
     def set_params(self, *, k, s=0, t=0, use_syncmer=True, window_size=None, scaling=1, percentage=-1.0, error_rate=0.04):
         p = Params(k, s, t, int(use_syncmer), k if window_size is None else window_size, scaling, percentage, error_rate)

@@ -46,7 +46,18 @@ struct HashArgs
     SmFilter smf;
     int ctas_per_sm;           // host side: CTAs per SM of the persistent grid (0: fill the SM)
     int window;                // minimiser mode: k-mer values per window, window_size - k + 1 (2..kMaxMinimiserValues)
+    // fused per-read distinct set (syncmer_kernel only; the ankerl::set of syncmer.cpp:145 built while hashing):
+    uint32_t fuse_dedup;       // 1: reads whose capacity is <= kFuseMaxCap write DISTINCT hashes + hash_count directly
+    uint32_t fuse_max_keys;    // distinct keys the warp table takes before the read is handed over (<= kWarpMaxKeys; tests lower it)
+    uint32_t *hash_count;      // [n_reads] distinct (after the FracMin scaling filter)
+    uint32_t *deferred;        // reads whose distinct set outgrew the warp table: raw tail appended, dedup'd by a CTA later
+    uint32_t *n_deferred;
+    uint32_t scaling;          // FracMin scaling (1 = off), applied before the set insert
+    double scaling_limit;
 };
+constexpr uint32_t kFuseMaxCap = 2048;      // == the `ids_small` class of the engine
+constexpr int kWarpSlots = 2048;            // per-warp dedup table (u32 slots in shared memory)
+constexpr uint32_t kWarpMaxKeys = kWarpSlots * 3 / 4; // 1536: load factor 3/4; index + 1 fits the low 11 bits of a slot
 
 struct DedupArgs
 {

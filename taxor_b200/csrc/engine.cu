@@ -11,6 +11,7 @@
 #include "threshold.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -18,12 +19,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace txr
 {
 cudaError_t launch_syncmer(const HashArgs &a, int sm_count, cudaStream_t st);
+bool syncmer_has_fast_kernel(int k, int s, int t);
 cudaError_t launch_kmer(const HashArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_minimiser(const HashArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_dedup_warp(const DedupArgs &a, int sm_count, uint32_t *work_counter, uint32_t *deferred, uint32_t *n_deferred,
@@ -34,6 +38,7 @@ cudaError_t launch_dedup_global(const DedupArgs &a, cudaStream_t st);
 cudaError_t launch_filter(const DedupArgs &a, cudaStream_t st);
 cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_query_large(const QueryArgs &a, int sm_count, uint32_t max_tbins, cudaStream_t st);
+uint32_t query_large_max_tbins();
 cudaError_t launch_sort_items(const uint2 *items, const uint32_t *n_ptr, uint32_t cap, uint32_t *hist, uint32_t n_ixf, uint2 *out,
                               int sm_count, cudaStream_t st);
 cudaError_t launch_root_partitioned(const QueryArgs &q, const RootPartArgs &a, int sm_count, cudaStream_t st);
@@ -90,6 +95,18 @@ struct DevBuf
         size_t want = bytes + bytes / 8 + 256;
         CU(cudaMalloc(&p, want));
         cap = want;
+        return TXR_OK;
+    }
+    int ensure_exact(size_t bytes) // no growth slack: the index arena (an eighth of a 100 GB index is not small change)
+    {
+        if (bytes <= cap)
+            return TXR_OK;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        CU(cudaMalloc(&p, bytes ? bytes : 1));
+        cap = bytes;
         return TXR_OK;
     }
     void release()
@@ -215,6 +232,7 @@ struct Slot
     const uint64_t *d_words{nullptr};
     bool busy{false};
     bool split_used{false}, ran_query{true};
+    bool fused{false}; // the hash kernel of the batch in flight built the distinct sets itself
 };
 
 struct ResultStore
@@ -259,6 +277,8 @@ struct txr_ctx
     bool sort_items{true};     // group level queues by IXF (TXR_SORT_ITEMS=0 disables, for A/B measurements)
     bool early_exit{true};     // exact early exit of kernel #2 (TXR_EARLY_EXIT=0 disables)
     bool l2_hints{true};       // L2 eviction-priority plan for small child IXFs (TXR_L2_HINTS=0 disables)
+    bool fuse_dedup{true};     // distinct set built inside the syncmer kernel (TXR_FUSE_DEDUP=0: separate dedup kernel)
+    uint32_t fuse_max_keys{kWarpMaxKeys}; // TXR_FUSE_MAX_KEYS lowers it (tests: forces the hand-over to the CTA-per-read kernel)
     int root_partition{0};     // root level grouped by segment-0 slot: 0 off (default: measured slower), 1 auto, 2 always (TXR_ROOT_PARTITION)
     bool per_read_thr{false};  // FracMinHash model: the threshold depends on hash_count AND the read length
     std::vector<uint64_t> lut; // threshold by hash_count (host)
@@ -520,6 +540,18 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     h.window = (int)c->params.window_size - (int)c->params.kmer_size + 1;
     h.smf = c->smf_hash;
     h.ctas_per_sm = c->shape_hash;
+    // the distinct set of a read (syncmer.cpp:145) is built while hashing whenever the templated kernel runs: no raw list
+    // round trip through HBM for the reads of the `ids_small` class
+    const bool fused = dedup && c->fuse_dedup && c->params.use_syncmer &&
+                       syncmer_has_fast_kernel(c->params.kmer_size, c->params.syncmer_size, c->params.t_syncmer);
+    h.fuse_dedup = fused;
+    h.fuse_max_keys = std::min<uint32_t>(c->fuse_max_keys, kWarpMaxKeys);
+    h.hash_count = s.hash_count.as<uint32_t>();
+    h.deferred = s.deferred.as<uint32_t>();
+    h.n_deferred = cnt + C_DEDUP_DEFERRED;
+    h.scaling = c->params.scaling;
+    h.scaling_limit = double(UINT64_MAX) / double(c->params.scaling ? c->params.scaling : 1);
+    s.fused = fused;
     if (c->params.use_syncmer)
         CU(launch_syncmer(h, c->sm_count, cs));
     else if (h.window > 1)
@@ -547,12 +579,16 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     {
         if (!m.ids_small.empty())
         {
-            dd.read_ids = m.ids_small.size() == m.n_reads ? nullptr : d.ids_small.as<uint32_t>();
-            dd.n_ids = (uint32_t)m.ids_small.size();
-            CU(launch_dedup_warp(dd, c->sm_count, cnt + C_DEDUP_WORK, s.deferred.as<uint32_t>(), cnt + C_DEDUP_DEFERRED, cs));
-            dd.read_ids = s.deferred.as<uint32_t>(); // reads with too many raw hashes for the warp table
+            if (!fused)
+            {
+                dd.read_ids = m.ids_small.size() == m.n_reads ? nullptr : d.ids_small.as<uint32_t>();
+                dd.n_ids = (uint32_t)m.ids_small.size();
+                CU(launch_dedup_warp(dd, c->sm_count, cnt + C_DEDUP_WORK, s.deferred.as<uint32_t>(), cnt + C_DEDUP_DEFERRED, cs));
+                c->timing.dedup_launches += 1;
+            }
+            dd.read_ids = s.deferred.as<uint32_t>(); // reads with too many distinct / raw hashes for the warp table
             CU(launch_dedup_deferred(dd, c->sm_count, cnt + C_DEDUP_DEFERRED, cs));
-            c->timing.dedup_launches += 2;
+            c->timing.dedup_launches += 1;
         }
         if (!m.ids_medium.empty())
         {
@@ -766,7 +802,7 @@ static bool split_left_work_undone(const txr_ctx *c, const Slot &s, const BatchM
     const uint32_t *hc = s.h_counters.as<uint32_t>();
     if (hc[C_HASH_WORK] < m.n_reads)
         return true;
-    if (c->params.use_syncmer && !m.ids_small.empty() && hc[C_DEDUP_WORK] < m.ids_small.size())
+    if (c->params.use_syncmer && !s.fused && !m.ids_small.empty() && hc[C_DEDUP_WORK] < m.ids_small.size())
         return true;
     if (!s.ran_query)
         return false;
@@ -1071,6 +1107,10 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->early_exit = atoi(e) != 0;
     if (const char *e = getenv("TXR_L2_HINTS"))
         c->l2_hints = atoi(e) != 0;
+    if (const char *e = getenv("TXR_FUSE_DEDUP"))
+        c->fuse_dedup = atoi(e) != 0;
+    if (const char *e = getenv("TXR_FUSE_MAX_KEYS"))
+        c->fuse_max_keys = (uint32_t)std::max(32, atoi(e));
     if (const char *e = getenv("TXR_ROOT_PARTITION"))
         c->root_partition = atoi(e);
     *out = c.release();
@@ -1135,6 +1175,139 @@ int txr_ctx_configure(txr_ctx *c, uint64_t max_batch_reads, uint64_t max_batch_b
     return TXR_OK;
 }
 
+// Fingerprint rows -> HBM arena.  The source is usually an mmap of the .hixf (pageable, maybe not even faulted in): a
+// plain cudaMemcpy from it runs at ~8 GB/s, one bounce buffer at a time.  Here the rows are cut into pieces of whole rows;
+// worker threads copy (or, when rows have to be padded to 64 bytes, re-stride) pieces into their own PINNED staging
+// buffers and queue an async copy each on their own stream, so the page faults and memcpys of one piece overlap the DMA
+// of the others.  TXR_UPLOAD_THREADS overrides the worker count (1 = the simple serial copy, for A/B measurements).
+static int upload_fingerprints(txr_ctx *c, const txr_hixf_view *v, DeviceIndex &ix)
+{
+    struct Piece
+    {
+        uint64_t ixf, row0, rows;
+    };
+    constexpr uint64_t kStage = 16ull << 20;
+    std::vector<Piece> pieces;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < v->n_ixf; ++i)
+    {
+        const uint64_t rows = 3 * v->ixf[i].seg_len, stride = ix.ixf[i].tbins;
+        const uint64_t per = std::max<uint64_t>(1, kStage / stride);
+        for (uint64_t r0 = 0; r0 < rows; r0 += per)
+            pieces.push_back(Piece{i, r0, std::min(per, rows - r0)});
+        total += rows * stride;
+    }
+    int n_workers = (int)std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), 12);
+    if (const char *e = getenv("TXR_UPLOAD_THREADS"))
+        n_workers = std::max(1, atoi(e));
+    n_workers = (int)std::min<uint64_t>((uint64_t)n_workers, std::max<uint64_t>(1, total / kStage));
+    std::atomic<size_t> next{0};
+    std::atomic<int> failed{0};
+    std::string first_error;
+    std::mutex err_m;
+    auto work = [&](int) {
+        if (cudaSetDevice(c->device) != cudaSuccess)
+        {
+            failed = 1;
+            return;
+        }
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        uint8_t *buf[2] = {nullptr, nullptr};
+        auto fail = [&](const char *what, cudaError_t e) {
+            std::lock_guard<std::mutex> l(err_m);
+            if (first_error.empty())
+                first_error = std::string(what) + ": " + cudaGetErrorString(e);
+            failed = 1;
+        };
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b)
+        {
+            e = cudaHostAlloc((void **)&buf[b], kStage, cudaHostAllocDefault);
+            if (e == cudaSuccess)
+                e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess)
+            fail("upload staging", e);
+        int cur = 0;
+        bool used[2] = {false, false};
+        while (!failed)
+        {
+            const size_t p = next.fetch_add(1);
+            if (p >= pieces.size())
+                break;
+            const Piece &pc = pieces[p];
+            const txr_ixf_view &x = v->ixf[pc.ixf];
+            const uint64_t stride = ix.ixf[pc.ixf].tbins;
+            if (used[cur] && (e = cudaEventSynchronize(ev[cur])) != cudaSuccess)
+            {
+                fail("upload wait", e);
+                break;
+            }
+            const uint8_t *src = x.fp + pc.row0 * x.tbins;
+            if (stride == x.tbins)
+                memcpy(buf[cur], src, pc.rows * stride);
+            else
+                for (uint64_t r = 0; r < pc.rows; ++r)
+                {
+                    memcpy(buf[cur] + r * stride, src + r * x.tbins, x.tbins);
+                    memset(buf[cur] + r * stride + x.tbins, 0, stride - x.tbins);
+                }
+            uint8_t *dst = const_cast<uint8_t *>(ix.ixf[pc.ixf].fp) + pc.row0 * stride;
+            e = cudaMemcpyAsync(dst, buf[cur], pc.rows * stride, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess)
+                e = cudaEventRecord(ev[cur], st);
+            if (e != cudaSuccess)
+            {
+                fail("upload copy", e);
+                break;
+            }
+            used[cur] = true;
+            cur ^= 1;
+        }
+        if (st)
+        {
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess)
+                fail("upload sync", e);
+            cudaStreamDestroy(st);
+        }
+        for (int b = 0; b < 2; ++b)
+        {
+            if (ev[b])
+                cudaEventDestroy(ev[b]);
+            if (buf[b])
+                cudaFreeHost(buf[b]);
+        }
+    };
+    if (n_workers <= 1)
+    {
+        // the plain path: pageable copies, row-strided when padding is needed
+        for (uint64_t i = 0; i < v->n_ixf; ++i)
+        {
+            const txr_ixf_view &x = v->ixf[i];
+            uint8_t *dst = const_cast<uint8_t *>(ix.ixf[i].fp);
+            const uint64_t rows = 3 * x.seg_len, dev_tbins = ix.ixf[i].tbins;
+            if (dev_tbins == x.tbins)
+                CU(cudaMemcpy(dst, x.fp, rows * x.tbins, cudaMemcpyHostToDevice));
+            else
+            {
+                CU(cudaMemset(dst, 0, rows * dev_tbins));
+                CU(cudaMemcpy2D(dst, dev_tbins, x.fp, x.tbins, x.tbins, rows, cudaMemcpyHostToDevice));
+            }
+        }
+        return TXR_OK;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_workers; ++t)
+        th.emplace_back(work, t);
+    for (auto &t : th)
+        t.join();
+    if (failed)
+        return set_error(TXR_ERR_CUDA, "index upload failed: %s", first_error.c_str());
+    return TXR_OK;
+}
+
 int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
 {
     if (!c || !v || v->n_ixf == 0)
@@ -1159,9 +1332,9 @@ int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
         if (v->bin_off[i + 1] - v->bin_off[i] != x.bins)
             return set_error(TXR_ERR_ARG, "IXF %llu: bin metadata size != bins", (unsigned long long)i);
         const uint64_t dev_tbins = (x.tbins + 63) / 64 * 64;
-        if (dev_tbins > 65536)
-            return set_error(TXR_ERR_UNSUPPORTED, "IXF %llu: %llu technical bins not supported", (unsigned long long)i,
-                             (unsigned long long)x.tbins);
+        if (dev_tbins > query_large_max_tbins()) // the counters of one (read, IXF) must fit a CTA's shared memory
+            return set_error(TXR_ERR_UNSUPPORTED, "IXF %llu: %llu technical bins not supported (limit %u)", (unsigned long long)i,
+                             (unsigned long long)x.tbins, query_large_max_tbins());
         arena_off[i] = arena_bytes;
         arena_bytes += (3 * x.seg_len * dev_tbins + 255) / 256 * 256;
         ix.ixf[i] = IxfDev{nullptr, x.seed, (uint32_t)x.seg_len, (uint32_t)dev_tbins, (uint32_t)x.bins, (uint32_t)v->bin_off[i], 1u};
@@ -1169,21 +1342,10 @@ int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
         ix.any_large = ix.any_large || dev_tbins > kSmallRowBytes;
         ix.fp_bytes += 3 * x.seg_len * dev_tbins;
     }
-    TRY(ix.arena.ensure(arena_bytes));
+    TRY(ix.arena.ensure_exact(arena_bytes));
     for (uint64_t i = 0; i < n; ++i)
-    {
-        const txr_ixf_view &x = v->ixf[i];
-        uint8_t *dst = ix.arena.as<uint8_t>() + arena_off[i];
-        ix.ixf[i].fp = dst;
-        const uint64_t rows = 3 * x.seg_len, dev_tbins = ix.ixf[i].tbins;
-        if (dev_tbins == x.tbins)
-            CU(cudaMemcpy(dst, x.fp, rows * x.tbins, cudaMemcpyHostToDevice));
-        else
-        {
-            CU(cudaMemset(dst, 0, rows * dev_tbins));
-            CU(cudaMemcpy2D(dst, dev_tbins, x.fp, x.tbins, x.tbins, rows, cudaMemcpyHostToDevice));
-        }
-    }
+        ix.ixf[i].fp = ix.arena.as<uint8_t>() + arena_off[i];
+    TRY(upload_fingerprints(c, v, ix));
     // per-bin metadata: kind, user bin, child, first bin of the split run (hixf.hpp:313-338)
     std::vector<int32_t> ub(total_bins), child(total_bins);
     std::vector<uint32_t> run_begin(total_bins);
@@ -1279,6 +1441,65 @@ int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
     return TXR_OK;
 }
 
+// Replicates the index of `src` (same or another GPU) into `dst` without touching the host copy again: the arena
+// goes device to device (NVLink when the GPUs are peers), the small metadata arrays likewise.  This is how a multi-GPU
+// driver fills its contexts: one upload over PCIe, then a doubling tree of clones (taxor_main.cpp).
+int txr_index_clone(txr_ctx *dst, txr_ctx *src)
+{
+    if (!dst || !src || dst == src)
+        return set_error(TXR_ERR_ARG, "null or identical contexts");
+    if (!src->index.loaded)
+        return set_error(TXR_ERR_STATE, "source context has no index");
+    CU(cudaSetDevice(src->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaSetDevice(dst->device));
+    CU(cudaDeviceSynchronize());
+    if (dst->device != src->device)
+    {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, dst->device, src->device));
+        if (can)
+        {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return set_error(TXR_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    const DeviceIndex &a = src->index;
+    DeviceIndex &b = dst->index;
+    b.release();
+    b.ixf = a.ixf;
+    b.dfs_rank = a.dfs_rank;
+    b.depth = a.depth;
+    b.max_tbins = a.max_tbins;
+    b.any_large = a.any_large;
+    b.n_user_bins = a.n_user_bins;
+    b.fp_bytes = a.fp_bytes;
+    struct Pair
+    {
+        const DevBuf *from;
+        DevBuf *to;
+    };
+    const Pair bufs[] = {{&a.arena, &b.arena}, {&a.d_bin_ub, &b.d_bin_ub}, {&a.d_bin_child, &b.d_bin_child},
+                         {&a.d_bin_run_begin, &b.d_bin_run_begin}, {&a.d_bin_kind, &b.d_bin_kind}};
+    for (const Pair &p : bufs)
+    {
+        if (!p.from->cap)
+            continue;
+        TRY(p.to->ensure_exact(p.from->cap));
+        CU(cudaMemcpyPeer(p.to->p, dst->device, p.from->p, src->device, p.from->cap));
+    }
+    const uint8_t *base_a = a.arena.as<uint8_t>();
+    for (auto &d : b.ixf)
+        d.fp = b.arena.as<uint8_t>() + (d.fp - base_a);
+    TRY(b.d_ixf.ensure(b.ixf.size() * sizeof(IxfDev)));
+    CU(cudaMemcpy(b.d_ixf.p, b.ixf.data(), b.ixf.size() * sizeof(IxfDev), cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());
+    b.loaded = true;
+    return TXR_OK;
+}
+
 int txr_params_set(txr_ctx *c, const txr_params *p)
 {
     if (!c || !p)
@@ -1328,11 +1549,10 @@ int txr_threshold_eval(const txr_params *p, uint64_t hash_count, double scaling_
 // ---- packing ----
 uint64_t txr_packed_words(uint64_t n_bases) { return (n_bases + 31) / 32 + 1; }
 
-static const int8_t *dna4_table()
+struct Dna4Table
 {
-    static int8_t tab[256];
-    static bool init = false;
-    if (!init)
+    int8_t tab[256];
+    Dna4Table()
     {
         memset(tab, -1, sizeof tab);
         const char *groups[4] = {"ANRWMDHV", "CYSB", "GK", "TU"}; // seqan3::dna4 char_to_rank
@@ -1342,9 +1562,12 @@ static const int8_t *dna4_table()
                 tab[(unsigned char)*q] = (int8_t)r;
                 tab[(unsigned char)(*q + 32)] = (int8_t)r;
             }
-        init = true;
     }
-    return tab;
+};
+static const int8_t *dna4_table()
+{
+    static const Dna4Table t; // C++11 magic static: txr_pack_2bit is first called from many pack threads at once
+    return t.tab;
 }
 
 int txr_pack_2bit(const char *ascii, uint64_t len, uint64_t *dst)
@@ -1424,8 +1647,40 @@ static int validate_reads(const uint64_t *word_off, const uint32_t *len, uint64_
     return TXR_OK;
 }
 
+// A search that fails half way (overflow, allocation failure) must not leave batches in flight: their slots would still
+// be `busy` with Slot::bm pointing into the failed call's stack, and the next call on the context would collect them.
+static int fail_clean(txr_ctx *c, int rc)
+{
+    if (rc != TXR_OK && c)
+    {
+        const std::string keep = g_last_error;
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        for (auto &s : c->slots)
+        {
+            s->busy = false;
+            s->bm = nullptr;
+            s->bd = nullptr;
+            s->d_words = nullptr;
+        }
+        c->result.clear();
+        g_last_error = keep;
+    }
+    return rc;
+}
+
+static int search_host_impl(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
+                            txr_result *out, std::vector<BatchMeta> &metas);
+
 int txr_search(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
                txr_result *out)
+{
+    std::vector<BatchMeta> metas; // outlives every batch in flight: fail_clean() drains the device before it goes
+    return fail_clean(c, search_host_impl(c, words, word_off, len, n_reads, out, metas));
+}
+
+static int search_host_impl(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, const uint32_t *len, uint64_t n_reads,
+                            txr_result *out, std::vector<BatchMeta> &metas)
 {
     TRY(check_ready(c));
     if (!words || !word_off || !len || !out)
@@ -1437,7 +1692,7 @@ int txr_search(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, cons
     TRY(fork_streams(c));
     std::vector<std::pair<uint64_t, uint32_t>> plan;
     plan_batches(c, len, n_reads, plan, c->n_slots > 1);
-    std::vector<BatchMeta> metas(c->n_slots);
+    metas.resize(c->n_slots);
     const size_t S = (size_t)c->n_slots;
     for (size_t b = 0; b < plan.size() + S - 1; ++b)
     {
@@ -1509,7 +1764,12 @@ void txr_reads_free(txr_ctx *c, txr_reads *r)
     delete r;
 }
 
+static int search_resident_impl(txr_ctx *c, txr_reads *r, int fetch, txr_result *out);
 int txr_search_resident(txr_ctx *c, txr_reads *r, int fetch, txr_result *out)
+{
+    return fail_clean(c, search_resident_impl(c, r, fetch, out));
+}
+static int search_resident_impl(txr_ctx *c, txr_reads *r, int fetch, txr_result *out)
 {
     TRY(check_ready(c));
     if (!r || (fetch && !out))

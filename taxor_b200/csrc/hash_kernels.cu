@@ -29,6 +29,12 @@ constexpr int kHashWarps = 4; // warps per CTA of the syncmer kernel
 
 namespace
 {
+__device__ __forceinline__ bool scaling_keep(uint64_t h, uint32_t scaling, double limit)
+{
+    // taxor_search.cpp:227-228: double(wyhash(h)) <= double(UINT64_MAX) / double(scaling)
+    return scaling <= 1 || __ull2double_rn(wyhash_u64(h)) <= limit;
+}
+
 __device__ __forceinline__ uint64_t pair_swap(uint64_t y)
 {
     return ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);
@@ -270,7 +276,7 @@ __device__ bool resolve_tie_local(const uint64_t *w, const uint32_t *sv, uint64_
 } // namespace
 
 template <int K, int S, int T>
-__global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
+__global__ void __launch_bounds__(32 * kHashWarps, 4) syncmer_kernel(HashArgs a)
 {
     if (!sm_filter_keep(a.smf))
         return;
@@ -285,8 +291,15 @@ __global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
     // per warp: canonical s-mers of the tile (tie handling only), later reused for the compacted selected windows
     __shared__ uint32_t s_v[kHashWarps][kTileWindows + 32];
     __shared__ uint32_t s_sel[kHashWarps][32];      // per-lane selection masks written by the sequential replay
+    // fused distinct set: kWarpSlots u32 per warp (dynamic: with it the CTA exceeds the 48 KB static limit).  A slot is
+    // 21 tag bits of the key | 11 bits: 0 empty, 1..kWarpMaxKeys = 1 + position of the key in the read's output list,
+    // kPendingBase + lane = claimed in the current round of 32 keys by that lane (its key is still in a register).
+    extern __shared__ uint32_t s_tab_dyn[];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    volatile uint32_t *tab = s_tab_dyn + (a.fuse_dedup ? wib * kWarpSlots : 0);
+    constexpr uint32_t kPendingBase = 2016;
+    static_assert(kWarpMaxKeys < kPendingBase && kPendingBase + 31 < 2048, "slot payload ranges overlap");
     while (true)
     {
         uint32_t r = 0;
@@ -304,6 +317,20 @@ __global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
         uint64_t cursor = 0;
         bool carry_valid = false;
         ScanState carry{0, 0};
+        // set_mode: the hashes go through the warp's table and only first occurrences are written (distinct list);
+        // it ends (for the rest of the read) when the table would pass its load limit -- the tail is then written raw
+        // behind the distinct prefix and a CTA-per-read kernel finishes the read (same distinct set).
+        bool set_mode = a.fuse_dedup && cap <= kFuseMaxCap;
+        const bool fused_read = set_mode;
+        uint32_t emitted = 0; // raw emissions (capacity check)
+        if (set_mode)
+        {
+            uint4 *t4 = reinterpret_cast<uint4 *>(s_tab_dyn + wib * kWarpSlots);
+#pragma unroll
+            for (int i = 0; i < kWarpSlots / 128; ++i)
+                t4[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+        }
 
         uint64_t hi_next = (uint64_t)lane < nw && W ? w[lane] : 0;
         for (uint64_t tile = 0; tile < W; tile += kTileWindows)
@@ -475,21 +502,77 @@ __global__ void __launch_bounds__(32 * kHashWarps) syncmer_kernel(HashArgs a)
                 s_pos[at++] = (uint16_t)(32 * lane + b);
             }
             __syncwarp();
-            for (uint32_t it = lane; it < total; it += 32)
+            emitted += total;
+            for (uint32_t it0 = 0; it0 < total; it0 += 32)
             {
-                const uint64_t pos = tile + s_pos[it];
-                const uint64_t h = wyhash_u64(canon_mer_at(w, pos, K));
-                if (cursor + it < cap)
-                    out[cursor + it] = h;
+                const uint32_t it = it0 + lane;
+                const bool live = it < total;
+                const uint64_t h = live ? wyhash_u64(canon_mer_at(w, tile + s_pos[it], K)) : 0;
+                if (set_mode && cursor + 32 > a.fuse_max_keys)
+                    set_mode = false; // warp-uniform: the rest of the read is written raw
+                if (!set_mode)
+                {
+                    if (live && cursor + (it - it0) < cap)
+                        out[cursor + (it - it0)] = h;
+                    cursor += min(32u, total - it0);
+                    continue;
+                }
+                // ---- the ankerl::set insert of syncmer.cpp:145 for 32 keys at a time ----
+                // FracMin first (taxor_search.cpp:223-233 filters the set; filtering before the insert gives the same set)
+                bool pending = live && scaling_keep(h, a.scaling, a.scaling_limit);
+                bool first = false;
+                uint32_t slot = (uint32_t)(h ^ (h >> 29)) & (kWarpSlots - 1);
+                const uint32_t tag = (uint32_t)(h >> 43) << 11;
+                const uint32_t mine = tag | (kPendingBase + (uint32_t)lane);
+                while (__any_sync(0xffffffffu, pending))
+                {
+                    if (pending && tab[slot] == 0)
+                        tab[slot] = mine; // racy on purpose: lanes of this round that share the slot, one store lands
+                    __syncwarp();
+                    const uint32_t now = pending ? tab[slot] : 0u;
+                    const uint32_t low = now & 2047u;
+                    const bool same_tag = pending && now != mine && low != 0 && (now & ~2047u) == tag;
+                    // the key behind an equal tag: a lane of this round (register, by shuffle) or an earlier key (output list)
+                    const uint64_t theirs = __shfl_sync(0xffffffffu, h, same_tag && low >= kPendingBase ? (int)(low - kPendingBase) : lane);
+                    if (pending)
+                    {
+                        if (now == mine)
+                        {
+                            first = true;
+                            pending = false;
+                        }
+                        else if (same_tag && (low >= kPendingBase ? theirs : __ldcg(out + (low - 1))) == h)
+                            pending = false; // an earlier (or concurrent) occurrence owns this key
+                        else
+                            slot = (slot + 1) & (kWarpSlots - 1);
+                    }
+                    __syncwarp();
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, first);
+                if (first)
+                {
+                    const uint32_t idx = (uint32_t)cursor + __popc(bal & ((1u << lane) - 1u));
+                    tab[slot] = tag | (idx + 1); // settle the claim: position in the output list
+                    if (idx < cap)               // always, unless the capacity bound is violated (reported below)
+                        out[idx] = h;
+                }
+                cursor += __popc(bal);
+                __syncwarp();
             }
-            cursor += total;
             __syncwarp();
         }
         if (lane == 0)
         {
-            a.n_out[r] = (uint32_t)min(cursor, cap);
-            if (cursor > cap)
+            if (emitted > cap)
                 *a.overflow = 1u;
+            if (fused_read && set_mode)
+                a.hash_count[r] = (uint32_t)cursor;
+            else
+            {
+                a.n_out[r] = (uint32_t)min(cursor, cap);
+                if (fused_read)
+                    a.deferred[atomicAdd(a.n_deferred, 1u)] = r;
+            }
         }
     }
 }
@@ -772,12 +855,6 @@ __global__ void __launch_bounds__(32 * kMinWarps) minimiser_kernel(HashArgs a)
 // -----------------------------------------------------------------------------------------------------------
 namespace
 {
-__device__ __forceinline__ bool scaling_keep(uint64_t h, uint32_t scaling, double limit)
-{
-    // taxor_search.cpp:227-228: double(wyhash(h)) <= double(UINT64_MAX) / double(scaling)
-    return scaling <= 1 || __ull2double_rn(wyhash_u64(h)) <= limit;
-}
-
 template <typename table_ptr_t>
 __device__ __forceinline__ void table_insert(table_ptr_t tab, uint32_t mask, uint64_t h)
 {
@@ -841,9 +918,7 @@ __device__ uint32_t table_compact(const uint64_t *tab, uint32_t slots, uint64_t 
 // Pass 2 compacts the list in place in first-occurrence order (the order an ankerl set iterates in) and applies
 // the FracMin filter.  Reads with more raw hashes than the table takes at load factor 3/4 are appended to
 // `deferred` for the CTA-per-read kernel.
-constexpr int kWarpSlots = 2048;
 constexpr int kDedupWarps = 4; // 32 KB of static shared memory per CTA
-constexpr uint32_t kWarpMaxKeys = kWarpSlots * 3 / 4; // 1536 < 2^11: an index + 1 fits the low 11 bits of a slot
 __global__ void __launch_bounds__(32 * kDedupWarps) dedup_warp_kernel(DedupArgs a, uint32_t *work_counter, uint32_t *deferred,
                                                                       uint32_t *n_deferred)
 {
@@ -1142,13 +1217,26 @@ static bool try_launch_syncmer(const HashArgs &a, int k, int s, int t, int grid,
 {
     if (k != K || s != S || t != T)
         return false;
-    syncmer_kernel<K, S, T><<<grid, 32 * kHashWarps, 0, st>>>(a);
+    const size_t smem = a.fuse_dedup ? (size_t)kHashWarps * kWarpSlots * 4 : 0;
+    if (smem) // static + dynamic shared memory exceed 48 KB; the attribute is per device, so it is set on every launch
+        cudaFuncSetAttribute(syncmer_kernel<K, S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    syncmer_kernel<K, S, T><<<grid, 32 * kHashWarps, smem, st>>>(a);
     return true;
 }
 
 // CTAs per SM of the persistent hash / dedup grids come with the arguments (HashArgs / DedupArgs::ctas_per_sm): the
 // defaults fill the SM; the engine lowers them when these ALU-bound kernels share SMs with the probe kernels ("overlap").
 static int clamp_ctas(int v, int dflt) { return v <= 0 ? dflt : v > 16 ? 16 : v; }
+
+// the (k, s, t) triples with a templated kernel (the only ones that can build the distinct set while hashing)
+bool syncmer_has_fast_kernel(int k, int s, int t)
+{
+    static const int list[][3] = {{22, 12, 5}, {20, 10, 5}, {24, 12, 6}, {26, 14, 6}, {28, 14, 7}, {30, 16, 7}, {18, 10, 4}, {16, 8, 4}};
+    for (auto &e : list)
+        if (e[0] == k && e[1] == s && e[2] == t)
+            return true;
+    return false;
+}
 
 cudaError_t launch_syncmer(const HashArgs &a, int sm_count, cudaStream_t st)
 {

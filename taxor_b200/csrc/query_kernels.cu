@@ -17,6 +17,7 @@
 #include "device_types.cuh"
 #include "ixf_arith.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace txr
@@ -614,18 +615,127 @@ __global__ void __launch_bounds__(32 * kQueryWarps) root_part_scan_kernel2(Query
     }
 }
 
-// ---- IXFs with tbins > 512: one CTA per (read, IXF); warps take 512-byte column chunks of the rows ----
-__global__ void __launch_bounds__(256) ixf_query_large_kernel(QueryArgs a)
+// ---- IXFs with tbins > 512: one CTA per (read, IXF) ----
+// Real Taxor indexes with >= 10k user bins have wide upper levels (root t_max up to 4096, taxor_build.cpp:173-187): a
+// row is 1-4 KB, so one probe is three contiguous multi-line reads and the kernel is a streaming gather.  Work split:
+// the HASH LIST of the read is dealt to the 8 warps in blocks (kWideHashesPerWarp consecutive hashes per warp and
+// block), every warp covers whole rows -- a lane owns 16 bytes of every 512-byte column chunk, CP chunks (CP*3 16-byte
+// loads) in flight per hash, rows wider than CP*512 bytes in several passes of CP*512 contiguous bytes.  Counters are
+// byte-packed per lane and flushed to the CTA's 32-bit shared counters once per block (at most 8 per byte).  Between
+// blocks the CTA can take the exact early exit of the small kernel (same bound, max over the shared counters).
+constexpr int kWideWarps = 8;
+constexpr uint32_t kWideHashesPerWarp = 8;
+
+template <int CP, int U>
+__device__ __forceinline__ void wide_block(const IxfDev &d, const uint64_t *__restrict__ hp, uint32_t h_begin, uint32_t h_end,
+                                           uint32_t col0, uint32_t *s_cnt, int lane)
+{
+    uint32_t acc[CP][4];
+    bool col_ok[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+    {
+        acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0;
+        col_ok[c] = col0 + 512u * c + 16u * lane < d.tbins;
+    }
+    const uint8_t *base = d.fp + col0 + 16u * lane;
+    for (uint32_t h = h_begin; h < h_end; h += U)
+    {
+        uint4 r[U][CP][3];
+        uint32_t fs[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            const bool live = h + u < h_end;
+            const uint64_t x = ixf_mix(live ? hp[h + u] : 0, d.seed);
+            uint32_t p0, p1, p2;
+            ixf_slots(x, d.seg_len, p0, p1, p2);
+            fs[u] = ixf_fingerprint(x) * 0x01010101u;
+            const uint8_t *q0 = base + (uint64_t)p0 * d.tbins, *q1 = base + (uint64_t)p1 * d.tbins, *q2 = base + (uint64_t)p2 * d.tbins;
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+            {
+                if (live && col_ok[c])
+                {
+                    r[u][c][0] = ldg_row16(q0 + 512 * c);
+                    r[u][c][1] = ldg_row16(q1 + 512 * c);
+                    r[u][c][2] = ldg_row16(q2 + 512 * c);
+                }
+                else // r0 ^ r1 ^ r2 ^ fs != 0 in every byte unless fs == 0: make the row itself differ from fs
+                {
+                    r[u][c][0] = make_uint4(~fs[u], ~fs[u], ~fs[u], ~fs[u]);
+                    r[u][c][1] = r[u][c][2] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+            {
+                acc[c][0] += zero_bytes(r[u][c][0].x ^ r[u][c][1].x ^ r[u][c][2].x ^ fs[u]);
+                acc[c][1] += zero_bytes(r[u][c][0].y ^ r[u][c][1].y ^ r[u][c][2].y ^ fs[u]);
+                acc[c][2] += zero_bytes(r[u][c][0].z ^ r[u][c][1].z ^ r[u][c][2].z ^ fs[u]);
+                acc[c][3] += zero_bytes(r[u][c][0].w ^ r[u][c][1].w ^ r[u][c][2].w ^ fs[u]);
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+        if (col_ok[c])
+            acc_flush(acc[c], s_cnt + col0 + 512u * c + 16u * lane);
+}
+
+template <int CP, int U>
+__device__ __forceinline__ uint32_t wide_item(const IxfDev &d, const uint64_t *__restrict__ hp, uint32_t H, uint32_t *s_cnt,
+                                              uint32_t *s_red, uint64_t exit_thr)
+{
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr uint32_t HB = kWideWarps * kWideHashesPerWarp;
+    const uint64_t slack = exit_thr ? (exit_thr - 1) / d.max_run : 0;
+    if (exit_thr && slack >= H)
+        return 0; // hopeless before the first probe (see probe_chunk)
+    uint32_t next_check = exit_thr ? H - (uint32_t)slack : 0xffffffffu;
+    for (uint32_t b0 = 0; b0 < H; b0 += HB)
+    {
+        const uint32_t hb = min(H, b0 + wib * kWideHashesPerWarp), he = min(H, hb + kWideHashesPerWarp);
+        if (hb < he)
+            for (uint32_t col0 = 0; col0 < d.tbins; col0 += 512u * CP)
+                wide_block<CP, U>(d, hp, hb, he, col0, s_cnt, lane);
+        const uint32_t done = min(H, b0 + HB);
+        if (done >= next_check && done < H) // CTA-uniform
+        {
+            __syncthreads();
+            uint32_t m = 0;
+            for (uint32_t i = threadIdx.x; i < d.bins; i += blockDim.x)
+                m = max(m, s_cnt[i]);
+            m = __reduce_max_sync(0xffffffffu, m);
+            if (lane == 0)
+                s_red[wib] = m;
+            __syncthreads();
+            m = 0;
+#pragma unroll
+            for (int q = 0; q < kWideWarps; ++q)
+                m = max(m, s_red[q]);
+            if ((uint64_t)d.max_run * ((uint64_t)m + (H - done)) < exit_thr)
+                return done;
+            next_check = done + 2 * HB;
+        }
+    }
+    return H;
+}
+
+__global__ void __launch_bounds__(32 * kWideWarps, 2) ixf_query_large_kernel(QueryArgs a)
 {
     if (!sm_filter_keep(a.smf))
         return;
     extern __shared__ uint32_t s_cnt_dyn[]; // tbins counters
     __shared__ uint32_t s_item;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    __shared__ uint32_t s_red[kWideWarps];
     const uint32_t n_items = a.items ? *a.n_items_ptr : a.n_items_direct;
-    unsigned long long bytes = 0, items = 0;
+    unsigned long long bytes = 0, items = 0, skipped = 0;
     while (true)
     {
+        __syncthreads(); // the previous item's bin scan is over: counters and s_item may be rewritten
         if (threadIdx.x == 0)
             s_item = atomicAdd(a.cursor, 1u);
         __syncthreads();
@@ -646,23 +756,24 @@ __global__ void __launch_bounds__(256) ixf_query_large_kernel(QueryArgs a)
         const uint32_t H = a.hash_count[read];
         const uint64_t *hp = a.hashes + a.hash_off[read];
         const uint64_t thr = a.thr_read ? a.thr_read[read] : (H < a.lut_len ? a.thr_lut[H] : ~0ULL);
-        const uint32_t n_chunks = (d.tbins + kSmallRowBytes - 1) / kSmallRowBytes;
-        for (uint32_t c = wib; c < n_chunks; c += nwarps)
-        {
-            const uint32_t off = c * kSmallRowBytes;
-            const uint32_t width = min(kSmallRowBytes, d.tbins - off);
-            probe_chunk<kQueryUnroll>(d, hp, H, off, width >> 4, s_cnt_dyn + off, lane);
-        }
+        const uint64_t exit_thr = a.early_exit ? thr : 0;
+        uint32_t Hp;
+        if (d.tbins <= 1024)
+            Hp = wide_item<2, 2>(d, hp, H, s_cnt_dyn, s_red, exit_thr);
+        else
+            Hp = wide_item<4, 1>(d, hp, H, s_cnt_dyn, s_red, exit_thr);
         __syncthreads();
         scan_bins(a, d, read, thr, s_cnt_dyn, threadIdx.x, blockDim.x);
-        __syncthreads();
-        bytes += (unsigned long long)H * 3ull * d.tbins + 8ull * H;
+        bytes += (unsigned long long)Hp * 3ull * d.tbins + 8ull * Hp;
+        skipped += H - Hp;
         ++items;
     }
     if (threadIdx.x == 0 && items)
     {
         atomicAdd(a.stat_bytes, bytes);
         atomicAdd(a.stat_items, items);
+        if (skipped)
+            atomicAdd(a.stat_skipped, skipped);
     }
 }
 
@@ -791,18 +902,36 @@ cudaError_t launch_root_partitioned(const QueryArgs &q, const RootPartArgs &a, i
     return cudaGetLastError();
 }
 
+// widest IXF the CTA-per-item kernel can hold counters for (32-bit counters in at most 200 KB of dynamic shared memory)
+uint32_t query_large_max_tbins() { return 200u * 1024u / 4u; }
+
 cudaError_t launch_query_large(const QueryArgs &a, int sm_count, uint32_t max_tbins, cudaStream_t st)
 {
     const size_t smem = (size_t)max_tbins * 4;
-    cudaFuncSetAttribute(ixf_query_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ixf_query_large_kernel<<<sm_count * 4, 256, smem, st>>>(a);
+    if (max_tbins > query_large_max_tbins())
+        return cudaErrorInvalidValue; // txr_index_upload rejects such indexes
+    if (smem > 48 * 1024)
+    {
+        const cudaError_t e = cudaFuncSetAttribute(ixf_query_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+    }
+    // CTAs per SM: as many as the counters allow, up to 8 warps x 6 = 48 warps (registers cap it at 4-5 anyway)
+    const int by_smem = (int)std::max<size_t>(1, (200u * 1024u) / std::max<size_t>(smem + 64, 1));
+    const int ctas = std::min(a.ctas_per_sm > 0 ? a.ctas_per_sm : 6, std::min(by_smem, 6));
+    ixf_query_large_kernel<<<sm_count * ctas, 32 * kWideWarps, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_bulk_count(const IxfDev &d, const uint64_t *values, uint32_t n, uint32_t *counts, cudaStream_t st)
 {
     const size_t smem = (size_t)d.tbins * 4;
-    cudaFuncSetAttribute(ixf_bulk_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024)
+    {
+        const cudaError_t e = cudaFuncSetAttribute(ixf_bulk_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+    }
     ixf_bulk_count_kernel<<<1, 256, smem, st>>>(d, values, n, counts);
     return cudaGetLastError();
 }

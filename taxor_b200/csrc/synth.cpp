@@ -13,7 +13,9 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <deque>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <parallel/algorithm>
 #include <queue>
@@ -43,7 +45,8 @@ struct BuiltIxf
 
 struct Hixf
 {
-    std::vector<BuiltIxf> ixf;
+    std::deque<BuiltIxf> ixf; // a deque: references stay valid while other threads append
+    std::mutex ixf_mutex;
     // flattened accessors
     std::vector<uint64_t> seed, bins, tbins, seg_len, bin_off;
     std::vector<const uint8_t *> data;
@@ -129,13 +132,19 @@ struct Builder
     uint32_t t_max;
     uint64_t seed_state;
     Hixf *out;
+    uint32_t t_max_lower{0}; // != 0: bin budget of the IXFs below the root (a wide root over narrow lower levels)
 
     // returns the index of the IXF built for `ubs` (sorted by size, descending); `all` receives the sorted
     // distinct union of the subtree when want_union
-    size_t build(const std::vector<uint32_t> &ubs, bool want_union, std::vector<uint64_t> &all)
+    size_t build(const std::vector<uint32_t> &ubs, bool want_union, std::vector<uint64_t> &all, int depth = 0)
     {
-        const size_t my = out->ixf.size();
-        out->ixf.emplace_back();
+        size_t my;
+        {
+            std::lock_guard<std::mutex> g(out->ixf_mutex);
+            my = out->ixf.size();
+            out->ixf.emplace_back();
+        }
+        const uint32_t t_max = depth > 0 && t_max_lower ? t_max_lower : this->t_max;
         const size_t n = ubs.size();
         std::vector<BinSpec> spec;
         if (n <= t_max)
@@ -211,7 +220,13 @@ struct Builder
         std::vector<const uint64_t *> kptr(bins);
         std::vector<size_t> kn(bins);
         std::vector<int64_t> next(bins), ubv(bins);
+        // Children of a wide IXF (hundreds of merged bins) are built by different threads: each subtree's peels and
+        // sorts are small, so parallelism has to come from the subtrees.  IXF numbers then depend on the schedule, as in
+        // the reference (atomic counter, build_data.hpp:34-37); narrow IXFs keep the serial, reproducible order.
+        size_t n_merged = 0;
         for (size_t b = 0; b < bins; ++b)
+            n_merged += spec[b].ub < 0;
+        auto fill_bin = [&](size_t b)
         {
             if (spec[b].ub >= 0)
             {
@@ -224,13 +239,27 @@ struct Builder
             }
             else
             {
-                const size_t child = build(spec[b].group, true, owned[b]);
+                const size_t child = build(spec[b].group, true, owned[b], depth + 1);
                 kptr[b] = owned[b].data();
                 kn[b] = owned[b].size();
                 next[b] = (int64_t)child;
                 ubv[b] = -1;
             }
+        };
+#ifdef _OPENMP
+        const bool par_children = n_merged >= 128 && !omp_in_parallel() && omp_get_max_threads() > 1;
+#else
+        const bool par_children = false;
+#endif
+        if (par_children)
+        {
+#pragma omp parallel for schedule(dynamic, 1)
+            for (long b = 0; b < (long)bins; ++b)
+                fill_bin((size_t)b);
         }
+        else
+            for (size_t b = 0; b < bins; ++b)
+                fill_bin(b);
         BuiltIxf &x = out->ixf[my];
         size_t max_n = 0;
         for (size_t b = 0; b < bins; ++b)
@@ -240,7 +269,12 @@ struct Builder
         // capacity: the reference sizes an IXF from the layout's (HyperLogLog, i.e. approximate) max_bin_hashes
         // (construct_ixf.cpp:58).  1.23*n slots is marginal for peeling when all bins of an IXF must succeed with
         // ONE seed, so the generator adds 6 % headroom; otherwise a balanced 64-bin IXF needs ~1000 re-seeds.
-        x.seg_len = txr::ixf_seg_len_for(max_n + max_n / 16 + 32);
+        // With thousands of small bins (wide test indexes) every one of them has to peel under the same seed, and a small
+        // 3-wise XOR system fails far more often than a large one: more headroom per doubling of the bin count beyond 64.
+        size_t wide_extra = 0;
+        for (size_t bb = bins; bb > 64 && max_n < (1u << 16); bb >>= 1)
+            wide_extra += max_n / 24 + 16;
+        x.seg_len = txr::ixf_seg_len_for(max_n + max_n / 16 + 32 + wide_extra);
         x.seed = 13572355802537770549ULL; // default seed of the prototype (xorfilter.hpp:153)
         x.next = next;
         x.ub = ubv;
@@ -270,8 +304,11 @@ struct Builder
             if (!failed)
                 break;
             // construct_ixf.cpp:101-108: clear the whole IXF and draw a new seed
-            x.seed = splitmix64(seed_state);
-            ++out->reseeds;
+            {
+                std::lock_guard<std::mutex> g(out->ixf_mutex);
+                x.seed = splitmix64(seed_state);
+                ++out->reseeds;
+            }
         }
         // interleave: data[slot * tbins + bin]; every thread owns a block of rows, so no cache line is shared
         {
@@ -413,21 +450,31 @@ void txs_sort_unique_many(uint64_t *const *keys, uint64_t *counts, uint64_t n_ub
     }
 }
 
+void *txs_hixf_build2(const uint64_t *const *ub_hashes, const uint64_t *ub_n, uint64_t n_ub, uint32_t t_max, uint32_t t_max_lower,
+                      uint64_t seed, int threads);
 void *txs_hixf_build(const uint64_t *const *ub_hashes, const uint64_t *ub_n, uint64_t n_ub, uint32_t t_max, uint64_t seed,
                      int threads)
+{
+    return txs_hixf_build2(ub_hashes, ub_n, n_ub, t_max, 0, seed, threads);
+}
+
+// t_max_lower != 0: the IXFs below the root get that bin budget instead of t_max (GTDB-shaped test/bench indexes: a
+// 4096-bin root over narrow lower levels, several levels deep without needing millions of user bins)
+void *txs_hixf_build2(const uint64_t *const *ub_hashes, const uint64_t *ub_n, uint64_t n_ub, uint32_t t_max, uint32_t t_max_lower,
+                      uint64_t seed, int threads)
 {
 #ifdef _OPENMP
     if (threads > 0)
         omp_set_num_threads(threads);
 #endif
-    if (n_ub == 0 || t_max < 2)
+    if (n_ub == 0 || t_max < 2 || t_max_lower == 1)
         return nullptr;
     auto h = std::make_unique<Hixf>();
     h->n_user_bins = n_ub;
     std::vector<uint32_t> ubs(n_ub);
     std::iota(ubs.begin(), ubs.end(), 0u);
     std::stable_sort(ubs.begin(), ubs.end(), [&](uint32_t a, uint32_t b) { return ub_n[a] > ub_n[b]; });
-    Builder bld{ub_hashes, ub_n, t_max, seed, h.get()};
+    Builder bld{ub_hashes, ub_n, t_max, seed, h.get(), t_max_lower};
     std::vector<uint64_t> unused;
     bld.build(ubs, false, unused);
     h->bin_off.push_back(0);

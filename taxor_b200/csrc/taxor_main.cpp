@@ -375,14 +375,37 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
 
     const double t_load = since(t_start);
     const auto t_up = std::chrono::steady_clock::now();
+    // one upload over PCIe (staged, multi-threaded), then the other GPUs are filled device to device in a doubling
+    // tree (round r: every context that has the index clones it into one that has not -- NVLink between peers), instead
+    // of pushing the same 10-100 GB through the host once per GPU
     std::vector<txr_ctx *> ctxs;
     for (int d : devices)
     {
         txr_ctx *c = nullptr;
-        if (txr_ctx_create(d, &c) != TXR_OK || txr_index_upload(c, &hv) != TXR_OK || txr_params_set(c, &par) != TXR_OK)
+        if (txr_ctx_create(d, &c) != TXR_OK)
             throw std::runtime_error(std::string("GPU ") + std::to_string(d) + ": " + txr_last_error());
         ctxs.push_back(c);
     }
+    if (txr_index_upload(ctxs[0], &hv) != TXR_OK)
+        throw std::runtime_error(std::string("GPU ") + std::to_string(devices[0]) + ": " + txr_last_error());
+    for (size_t have = 1; have < ctxs.size(); have *= 2)
+    {
+        std::vector<std::thread> th;
+        std::vector<std::string> errs(ctxs.size());
+        for (size_t i = 0; i < have && have + i < ctxs.size(); ++i)
+            th.emplace_back([&, i] {
+                if (txr_index_clone(ctxs[have + i], ctxs[i]) != TXR_OK)
+                    errs[have + i] = txr_last_error();
+            });
+        for (auto &t : th)
+            t.join();
+        for (size_t i = 0; i < errs.size(); ++i)
+            if (!errs[i].empty())
+                throw std::runtime_error(std::string("GPU ") + std::to_string(devices[i]) + ": " + errs[i]);
+    }
+    for (size_t i = 0; i < ctxs.size(); ++i)
+        if (txr_params_set(ctxs[i], &par) != TXR_OK)
+            throw std::runtime_error(std::string("GPU ") + std::to_string(devices[i]) + ": " + txr_last_error());
 
     const double t_upload = since(t_up);
     const auto t_search = std::chrono::steady_clock::now();
@@ -409,6 +432,7 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     }
     std::string worker_error;
     std::mutex err_m;
+    std::atomic<bool> failed{false}; // a parse or search error: everything still queued drains without further work
     std::vector<std::thread> workers;
     for (txr_ctx *c : ctxs)
         workers.emplace_back([&, c] {
@@ -416,11 +440,15 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
             while (work_q.pop(ch))
             {
                 txr_result res{};
-                if (txr_search(c, ch->words, ch->word_off.data(), ch->len.data(), ch->n, &res) != TXR_OK)
+                if (failed.load()) // after the first failure no context is searched again; the chunks only circulate
+                    ch->text.clear();
+                else if (txr_search(c, ch->words, ch->word_off.data(), ch->len.data(), ch->n, &res) != TXR_OK)
                 {
                     std::lock_guard<std::mutex> l(err_m);
-                    worker_error = txr_last_error();
+                    if (worker_error.empty())
+                        worker_error = txr_last_error();
                     ch->text.clear();
+                    failed = true;
                 }
                 else
                     format_chunk(*ch, res, idx, user_bin_index);
@@ -447,7 +475,6 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
 
     // job threads: segment scans (mapped files) and packing (IUPAC -> dna4 -> 2 bit straight into the pinned chunk, ids)
     std::string parse_error;
-    std::atomic<bool> failed{false};
     auto fail = [&](const std::string &msg) {
         std::lock_guard<std::mutex> l(err_m);
         if (parse_error.empty())

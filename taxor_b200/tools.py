@@ -29,6 +29,8 @@ def tlib():
     T.txs_sort_unique_many.restype = None
     T.txs_hixf_build.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int]
     T.txs_hixf_build.restype = vp
+    T.txs_hixf_build2.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int]
+    T.txs_hixf_build2.restype = vp
     T.txs_hixf_free.argtypes = [vp]
     T.txs_hixf_free.restype = None
     T.txs_hixf_n_ixf.argtypes = [vp]
@@ -89,7 +91,8 @@ def simulate_reads(genomes, genome_len, read_len, err: float, seed: int, out_wor
 class BuiltHixf:
     """An HIXF built by the CPU tooling; exposes the plain arrays every consumer takes."""
 
-    def __init__(self, ub_hashes, t_max: int = 64, seed: int = 1, threads: int = 0, inplace: bool = False) -> None:
+    def __init__(self, ub_hashes, t_max: int = 64, seed: int = 1, threads: int = 0, inplace: bool = False,
+                 t_max_lower: int = 0) -> None:
         # sorted distinct key sets (in place on private copies -- or on the caller's arrays with inplace=True, which
         # halves the footprint of a multi-GB build -- parallel over user bins)
         if inplace:
@@ -103,7 +106,7 @@ class BuiltHixf:
         tlib().txs_sort_unique_many(ptrs, cnt.ctypes.data, n, threads)
         self._ub = [a[: int(c)] for a, c in zip(self._ub, cnt)]
         self.n_keys = int(cnt.sum())
-        self._h = tlib().txs_hixf_build(ptrs, cnt.ctypes.data, n, t_max, seed, threads)
+        self._h = tlib().txs_hixf_build2(ptrs, cnt.ctypes.data, n, t_max, t_max_lower, seed, threads)
         if not self._h:
             raise RuntimeError("txs_hixf_build failed")
         self.n_user_bins = n

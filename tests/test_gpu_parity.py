@@ -225,6 +225,60 @@ def test_search_large_rows(ctx, oracle):
     _search_case(ctx, oracle, ds2, reads2, error_rate=0.1)
 
 
+@pytest.mark.parametrize("t_max,n_genomes,early", [(1024, 1300, "1"), (2048, 2300, "1"), (4096, 4300, "1"), (4096, 4300, "0"), (1536, 1536, "1")])
+def test_search_wide_rows(monkeypatch, oracle, t_max, n_genomes, early):
+    """GTDB-shaped upper levels (root t_max up to 4096, taxor_build.cpp:173-187): every warp of the CTA probes a share of
+    the hash list over whole rows; wide rows in 2 KB passes; exact early exit between hash blocks"""
+    monkeypatch.setenv("TXR_EARLY_EXIT", early)
+    c = capi.Context(0)
+    try:
+        ds = H.make_dataset(oracle, n_genomes=n_genomes, genome_len=2_000, t_max=t_max, size_jitter=True, seed=9000 + t_max)
+        assert int(ds.hixf.tbins[0]) == t_max
+        rng = np.random.default_rng(t_max)
+        own = H.make_reads(ds, rng.integers(300, 1900, 80), err=0.02)
+        foreign = [rng.integers(0, 4, int(n), dtype=np.uint8) for n in rng.integers(300, 6000, 60)]
+        seqs = foreign + [capi.unpack_codes(own, i) for i in range(own.n)] + [np.zeros(0, np.uint8), np.zeros(21, np.uint8)]
+        reads = capi.pack_codes([seqs[i] for i in rng.permutation(len(seqs))])
+        res, ora = _search_case(c, oracle, ds, reads, error_rate=0.1)
+        assert int(res.hit_begin[-1]) > 20
+        tm = c.timing()
+        if early == "1":
+            assert tm["skipped_hashes"] > 0, tm
+        else:
+            assert tm["skipped_hashes"] == 0, tm
+        _search_case(c, oracle, ds, reads, percentage=0.5)
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("env", [{"TXR_FUSE_MAX_KEYS": "64"}, {"TXR_FUSE_MAX_KEYS": "300"}, {"TXR_FUSE_DEDUP": "0"}, {}])
+@pytest.mark.parametrize("scaling", [1, 5])
+def test_fused_distinct_set_variants(monkeypatch, oracle, env, scaling):
+    """the distinct set built inside the syncmer kernel: the hand-over of a read to the CTA-per-read kernel (forced early
+    by TXR_FUSE_MAX_KEYS), the separate dedup kernel (TXR_FUSE_DEDUP=0) and the default all give the oracle's sets; reads
+    made of repeated blocks have most of their hashes more than once"""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    c = capi.Context(0)
+    try:
+        k, s, t = 22, 12, 5
+        c.set_params(k=k, s=s, t=t, use_syncmer=True, window_size=20, scaling=scaling)
+        rng = np.random.default_rng(77 + scaling)
+        seqs = edge_reads(rng, k) + lowcomplexity_reads(rng)
+        seqs += [rng.integers(0, 4, int(n), dtype=np.uint8) for n in rng.integers(500, 10200, 60)]
+        for _ in range(10):                                               # repeated blocks: duplicates inside and across tiles
+            block = rng.integers(0, 4, int(rng.integers(50, 1500)), dtype=np.uint8)
+            seqs.append(np.resize(block, int(rng.integers(3000, 10000))).copy())
+        reads = capi.pack_codes(seqs)
+        off, h = c.hash_batch(reads, dedup=True)
+        for i, x in enumerate(seqs):
+            exp = [v for v in oracle.syncmer_hashes(x, k, s, t).tolist() if scaling == 1 or oracle.scaling_keep(v, scaling)]
+            got = h[int(off[i]):int(off[i + 1])]
+            assert len(got) == len(exp) and np.array_equal(np.sort(got), np.sort(np.array(exp, np.uint64))), (i, len(x), env)
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("k,w", [(20, 24), (20, 40), (8, 12), (31, 126), (16, 17), (4, 8)])
 def test_minimiser_hash_parity(ctx, oracle, k, w):
     """minimiser windows (window_size > k): same values, same order, same repeats as views::minimiser_hash; the
@@ -364,6 +418,43 @@ def test_hash_user_bins_build_side(monkeypatch, oracle, mode):
             assert set(got.tolist()) == exp, (mode, b, len(got), len(exp))
         assert off[4] == off[5]
     finally:
+        c.close()
+
+
+def test_index_clone_and_staged_upload(monkeypatch, oracle):
+    """txr_index_clone (device-to-device replica; second GPU when there is one, else a second context on GPU 0) and the
+    serial upload path (TXR_UPLOAD_THREADS=1) answer exactly like the staged multi-threaded upload; rows that need padding
+    (tbins not a multiple of 64 in the source) take the re-striding path of both"""
+    import torch
+    ds = H.make_dataset(oracle, n_genomes=300, genome_len=30_000, t_max=128)
+    rng = np.random.default_rng(5)
+    reads = H.make_reads(ds, rng.integers(300, 9000, 300), err=0.04)
+    a = capi.Context(0)
+    b = capi.Context(1 if torch.cuda.device_count() > 1 else 0)
+    monkeypatch.setenv("TXR_UPLOAD_THREADS", "1")
+    c = capi.Context(0)
+    try:
+        res, ora = _search_case(a, oracle, ds, reads, error_rate=0.1)
+        assert int(res.hit_begin[-1]) > 50
+        b.clone_index_from(a)
+        b.set_params(k=ds.k, s=ds.s, t=ds.t, use_syncmer=True, window_size=20, error_rate=0.1)
+        H.assert_same_search(b.search(reads), ora, reads.n)
+        _search_case(c, oracle, ds, reads, error_rate=0.1)
+        # unpadded source rows (tbins == bins, not a multiple of 64): both upload paths pad to 64-byte rows
+        hx = ds.hixf
+        data, tb = [], []
+        for i in range(hx.n_ixf):
+            rows = 3 * int(hx.seg_len[i])
+            m = hx.data[i].reshape(rows, int(hx.tbins[i]))[:, : int(hx.bins[i])]
+            data.append(np.ascontiguousarray(m).reshape(-1))
+            tb.append(int(hx.bins[i]))
+        for cx in (a, c):
+            cx.upload_index(hx.seed, hx.bins, np.array(tb, np.uint64), hx.seg_len, data, hx.bin_off, hx.next_ixf_id, hx.bin_to_ub, hx.n_user_bins)
+            cx.set_params(k=ds.k, s=ds.s, t=ds.t, use_syncmer=True, window_size=20, error_rate=0.1)
+            H.assert_same_search(cx.search(reads), ora, reads.n)
+    finally:
+        a.close()
+        b.close()
         c.close()
 
 
