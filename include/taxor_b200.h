@@ -49,9 +49,32 @@ typedef struct
     uint64_t seed;       /* per-IXF hash seed (re-seeded on build failure, construct_ixf.cpp:101-108)      */
     uint64_t bins;       /* counting-vector size == ixf_bin_to_filename_position[i].size() (hixf.hpp:313)  */
     uint64_t tbins;      /* stored fingerprints per slot row (bins padded to a multiple of 64)             */
-    uint64_t seg_len;    /* slots per segment; the filter has 3*seg_len rows                               */
-    const uint8_t *fp;   /* host pointer, fp[slot * tbins + bin]                                           */
+    uint64_t seg_len;    /* slots per segment (XOR3: the filter has 3*seg_len rows; FUSE3: a power of two) */
+    const uint8_t *fp;   /* host pointer, fp[slot * tbins + bin] (or bin-major, see txr_ixf_scheme.layout) */
+    uint64_t rows;       /* slots per bin; 0 = 3*seg_len.  FUSE3: (segment_count + 2) * seg_len            */
 } txr_ixf_view;
+
+/* The probe arithmetic of seqan3::interleaved_xor_filter<uint8_t> (call site hixf.hpp:307-309) lives in the SeqAn3 fork
+ * JensUweUlrich/seqan3@master, which is in neither the reference tree nor this image: PARITY UNPINNED.  It is therefore a
+ * descriptor handed over with the index, not a compile-time fact.  All-zero (or a NULL pointer) selects the arithmetic of
+ * the same author's in-tree prototype (src/main/xorfilter.hpp:22-45,60-62,336-350 + src/main/hashutil.hpp:50-61). */
+#define TXR_IXF_SLOTS_XOR3 0u   /* three equal segments: reduce((u32)rotl64(h, rot_i), seg_len) + i*seg_len             */
+#define TXR_IXF_SLOTS_FUSE3 1u  /* 3-wise binary fuse (Graf & Lemire 2022): h0 = mulhi64(h, count*L), h1/h2 in the next two
+                                   segments, low bits xor-ed with (h >> 18) / h  (the fork also ships an
+                                   interleaved_binary_fuse_filter, main.cpp:22)                                          */
+#define TXR_IXF_MIX_ADD_SEED 0u /* murmur fmix64(key + seed)   (hashutil.hpp:50-61)                                      */
+#define TXR_IXF_MIX_XOR_SEED 1u /* murmur fmix64(key ^ seed)                                                            */
+#define TXR_IXF_FP_FOLD32 0u    /* (u8)(h ^ (h >> 32))         (xorfilter.hpp:60-62)                                     */
+#define TXR_IXF_FP_LOW8 1u      /* (u8)h                                                                                */
+#define TXR_IXF_FP_HIGH8 2u     /* (u8)(h >> 56)                                                                        */
+#define TXR_IXF_LAYOUT_SLOT_MAJOR 0u /* fp[slot * tbins + bin]: the bins of one slot are contiguous (interleaved)        */
+#define TXR_IXF_LAYOUT_BIN_MAJOR 1u  /* fp[bin * rows + slot]: one plain filter after the other; re-laid-out on upload   */
+typedef struct
+{
+    uint32_t slots, mix, fingerprint;
+    uint32_t rot1, rot2;             /* XOR3 rotations for segments 1 and 2; 0,0 = the prototype's 21,42                 */
+    uint32_t layout;                 /* how the HOST arrays are laid out; HBM is always slot-major                        */
+} txr_ixf_scheme;
 
 typedef struct
 {
@@ -61,6 +84,7 @@ typedef struct
     const int64_t *next_ixf_id;        /* hixf.hpp:122                                                     */
     const int64_t *bin_to_user_bin;    /* user_bins.ixf_bin_to_filename_position (hixf.hpp:178), -1=merged */
     uint64_t n_user_bins;
+    const txr_ixf_scheme *scheme;      /* NULL = the prototype's arithmetic, slot-major arrays             */
 } txr_hixf_view;
 
 /* Parameters that the reference takes from the .hixf (taxor_search.cpp:165-169) and from the CLI. */

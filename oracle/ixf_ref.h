@@ -44,6 +44,48 @@ static inline uint64_t ixfref_slot(uint64_t hash, int index, uint64_t seg_len)
     uint32_t r = (uint32_t)ixfref_rotl64(hash, (unsigned)index * 21u);
     return (uint64_t)ixfref_reduce(r, (uint32_t)seg_len) + (uint64_t)index * seg_len;
 }
+/* ---- descriptor-driven form (test-side twin of txr_ixf_scheme / taxor_b200/csrc/ixf_arith.cuh, written independently) ----
+ * Until the fork is visible the arithmetic is a hypothesis, so it is data: which slot derivation, which seed mixing, which
+ * fingerprint fold.  {0,0,0,21,42} is the prototype above.  slots == 1 is the 3-wise binary fuse filter as published by
+ * Graf & Lemire (2022) and implemented in FastFilter's binaryfusefilter.h (binary_fuse8_contain):
+ *     hi = (u64)(((u128)hash * SegmentCountLength) >> 64);  h0 = hi;  h1 = h0 + SegmentLength;  h2 = h1 + SegmentLength;
+ *     h1 ^= (hash >> 18) & SegmentLengthMask;  h2 ^= hash & SegmentLengthMask;                                          */
+typedef struct
+{
+    uint32_t slots;       /* 0 xor3 | 1 fuse3 */
+    uint32_t mix;         /* 0 fmix64(key + seed) | 1 fmix64(key ^ seed) */
+    uint32_t fingerprint; /* 0 (u8)(h ^ h>>32) | 1 (u8)h | 2 (u8)(h>>56) */
+    uint32_t rot1, rot2;  /* xor3 rotations of segments 1, 2 */
+} ixfref_scheme;
+static inline uint64_t ixfref_mix_s(const ixfref_scheme *s, uint64_t key, uint64_t seed)
+{
+    return ixfref_fmix64(s->mix ? (key ^ seed) : (key + seed));
+}
+static inline uint8_t ixfref_fingerprint_s(const ixfref_scheme *s, uint64_t hash)
+{
+    switch (s->fingerprint)
+    {
+    case 1: return (uint8_t)hash;
+    case 2: return (uint8_t)(hash >> 56);
+    default: return (uint8_t)(hash ^ (hash >> 32));
+    }
+}
+/* rows: slots per bin; seg_len: slots per segment (xor3) / SegmentLength (fuse3, power of two) */
+static inline uint64_t ixfref_slot_s(const ixfref_scheme *s, uint64_t hash, int index, uint64_t seg_len, uint64_t rows)
+{
+    if (s->slots == 1)
+    {
+        const uint64_t count_len = rows - 2 * seg_len; /* SegmentCount * SegmentLength */
+        const uint64_t h0 = (uint64_t)(((unsigned __int128)hash * count_len) >> 64);
+        if (index == 0)
+            return h0;
+        if (index == 1)
+            return (h0 + seg_len) ^ ((hash >> 18) & (seg_len - 1));
+        return (h0 + 2 * seg_len) ^ (hash & (seg_len - 1));
+    }
+    const unsigned rot = index == 0 ? 0u : index == 1 ? s->rot1 : s->rot2;
+    return (uint64_t)ixfref_reduce((uint32_t)ixfref_rotl64(hash, rot), (uint32_t)seg_len) + (uint64_t)index * seg_len;
+}
 /* slots per segment for a bin capacity (prototype formula, xorfilter.hpp:67-68) */
 static inline uint64_t ixfref_seg_len(uint64_t max_bin_elements)
 {

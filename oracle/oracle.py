@@ -31,7 +31,7 @@ def build(force: bool = False) -> None:
 
 class _IXF(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("bins", C.c_uint64), ("tbins", C.c_uint64), ("seg_len", C.c_uint64),
-                ("data", C.c_void_p)]
+                ("data", C.c_void_p), ("rows", C.c_uint64)]
 
 
 class _HIXF(C.Structure):
@@ -60,6 +60,7 @@ class HixfArrays:
     bin_off: np.ndarray   # u64[n_ixf+1]
     next_ixf_id: np.ndarray  # i64[sum bins]
     bin_to_ub: np.ndarray    # i64[sum bins]
+    rows: np.ndarray = None  # u64[n_ixf] slots per bin; None = 3*seg_len (binary-fuse scheme: (segments+2)*seg_len)
 
     @property
     def n_ixf(self) -> int:
@@ -99,6 +100,8 @@ class Oracle:
         L.orc_kmer_ci.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.orc_ixf_slots.restype = None
         L.orc_ixf_slots.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint8)] + [C.POINTER(C.c_uint64)] * 3
+        L.orc_set_ixf_scheme.restype = None
+        L.orc_set_ixf_scheme.argtypes = [C.c_void_p]
         L.orc_ixf_bulk_count.restype = None
         L.orc_ixf_bulk_count.argtypes = [C.POINTER(_IXF), u64p, C.c_uint64, u32p]
         L.orc_hixf_bulk_contains.restype = C.c_int64
@@ -176,11 +179,20 @@ class Oracle:
         self.lib.orc_ixf_slots(key, seed, seg_len, C.byref(f), *[C.byref(x) for x in p])
         return f.value, p[0].value, p[1].value, p[2].value
 
+    def set_ixf_scheme(self, scheme=None):
+        """Switch the (unpinned) probe arithmetic: None = the prototype's, else (slots, mix, fingerprint, rot1, rot2).
+        Process-global; tests that change it restore it."""
+        if scheme is None:
+            self.lib.orc_set_ixf_scheme(None)
+        else:
+            self.lib.orc_set_ixf_scheme(np.array([int(x) for x in scheme], dtype=np.uint32).ctypes.data)
+
     def make_hixf(self, a: HixfArrays):
         ixfs = (_IXF * a.n_ixf)()
         for i in range(a.n_ixf):
-            assert a.data[i].dtype == np.uint8 and a.data[i].size == 3 * int(a.seg_len[i]) * int(a.tbins[i])
-            ixfs[i] = _IXF(int(a.seed[i]), int(a.bins[i]), int(a.tbins[i]), int(a.seg_len[i]), a.data[i].ctypes.data)
+            rows = 3 * int(a.seg_len[i]) if a.rows is None else int(a.rows[i])
+            assert a.data[i].dtype == np.uint8 and a.data[i].size == rows * int(a.tbins[i])
+            ixfs[i] = _IXF(int(a.seed[i]), int(a.bins[i]), int(a.tbins[i]), int(a.seg_len[i]), a.data[i].ctypes.data, rows)
         h = _HIXF(a.n_ixf, ixfs, a.bin_off.ctypes.data, a.next_ixf_id.ctypes.data, a.bin_to_ub.ctypes.data)
         h._keep = (ixfs, a)
         return h

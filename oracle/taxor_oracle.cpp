@@ -412,6 +412,15 @@ extern "C" uint64_t orc_threshold_get(const orc_thresholder *t, uint64_t minimis
  * IXF / HIXF
  * ---------------------------------------------------------------------------------------------- */
 
+static ixfref_scheme g_scheme = {0, 0, 0, 21, 42};
+extern "C" void orc_set_ixf_scheme(const uint32_t *s5)
+{
+    if (!s5)
+        g_scheme = ixfref_scheme{0, 0, 0, 21, 42};
+    else
+        g_scheme = ixfref_scheme{s5[0], s5[1], s5[2], (s5[3] | s5[4]) ? s5[3] : 21u, (s5[3] | s5[4]) ? s5[4] : 42u};
+}
+
 extern "C" void orc_ixf_slots(uint64_t key, uint64_t seed, uint64_t seg_len,
                               uint8_t *f, uint64_t *p0, uint64_t *p1, uint64_t *p2)
 {
@@ -429,9 +438,11 @@ extern "C" void orc_ixf_bulk_count(const orc_ixf *x, const uint64_t *values, uin
     std::memset(counts, 0, sizeof(uint32_t) * x->bins);
     for (uint64_t v = 0; v < n; ++v)
     {
-        uint8_t f;
-        uint64_t p0, p1, p2;
-        orc_ixf_slots(values[v], x->seed, x->seg_len, &f, &p0, &p1, &p2);
+        const uint64_t rows = x->rows ? x->rows : 3 * x->seg_len;
+        const uint64_t h = ixfref_mix_s(&g_scheme, values[v], x->seed);
+        const uint8_t f = ixfref_fingerprint_s(&g_scheme, h);
+        const uint64_t p0 = ixfref_slot_s(&g_scheme, h, 0, x->seg_len, rows), p1 = ixfref_slot_s(&g_scheme, h, 1, x->seg_len, rows),
+                       p2 = ixfref_slot_s(&g_scheme, h, 2, x->seg_len, rows);
         const uint8_t *r0 = x->data + p0 * x->tbins;
         const uint8_t *r1 = x->data + p1 * x->tbins;
         const uint8_t *r2 = x->data + p2 * x->tbins;

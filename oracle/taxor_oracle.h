@@ -78,7 +78,12 @@ typedef struct {
     uint64_t tbins;       /* stored row width in fingerprints (bins padded to 64)           */
     uint64_t seg_len;     /* slots per segment; 3*seg_len rows                              */
     const uint8_t *data;  /* data[slot * tbins + bin]                                       */
+    uint64_t rows;        /* slots per bin, 0 = 3*seg_len (binary fuse: (segments+2)*seg_len) */
 } orc_ixf;
+
+/* The probe arithmetic is a hypothesis (see ixf_ref.h), so the oracle can be switched between candidate schemes:
+ * scheme5 = {slots, mix, fingerprint, rot1, rot2}; NULL restores the prototype's.  Process-global (test infrastructure). */
+void orc_set_ixf_scheme(const uint32_t *scheme5);
 
 typedef struct {
     uint64_t        n_ixf;

@@ -20,12 +20,19 @@ class TaxorError(RuntimeError):
 
 class IxfView(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("bins", C.c_uint64), ("tbins", C.c_uint64), ("seg_len", C.c_uint64),
-                ("fp", C.c_void_p)]
+                ("fp", C.c_void_p), ("rows", C.c_uint64)]
+
+
+class IxfScheme(C.Structure):
+    """txr_ixf_scheme: the probe arithmetic an index was built with (all zero = the prototype's)."""
+    _fields_ = [("slots", C.c_uint32), ("mix", C.c_uint32), ("fingerprint", C.c_uint32), ("rot1", C.c_uint32), ("rot2", C.c_uint32),
+                ("layout", C.c_uint32)]
 
 
 class HixfView(C.Structure):
     _fields_ = [("n_ixf", C.c_uint64), ("ixf", C.POINTER(IxfView)), ("bin_off", C.c_void_p),
-                ("next_ixf_id", C.c_void_p), ("bin_to_user_bin", C.c_void_p), ("n_user_bins", C.c_uint64)]
+                ("next_ixf_id", C.c_void_p), ("bin_to_user_bin", C.c_void_p), ("n_user_bins", C.c_uint64),
+                ("scheme", C.POINTER(IxfScheme))]
 
 
 class Params(C.Structure):
@@ -256,17 +263,23 @@ class Context:
     def configure(self, max_batch_reads=262144, max_batch_bases=3_000_000_000, n_slots=3):
         _check(self._L.txr_ctx_configure(self._h, max_batch_reads, max_batch_bases, n_slots))
 
-    def upload_index(self, seed, bins, tbins, seg_len, data, bin_off, next_ixf_id, bin_to_ub, n_user_bins):
+    def upload_index(self, seed, bins, tbins, seg_len, data, bin_off, next_ixf_id, bin_to_ub, n_user_bins, rows=None, scheme=None,
+                     layout=0):
+        """scheme: None or (slots, mix, fingerprint, rot1, rot2); layout 1 = the host arrays are bin-major"""
         n = len(seed)
         ixfs = (IxfView * n)()
         for i in range(n):
             d = data[i]
             ptr = d.ctypes.data if isinstance(d, np.ndarray) else int(d)
-            ixfs[i] = IxfView(int(seed[i]), int(bins[i]), int(tbins[i]), int(seg_len[i]), ptr)
+            ixfs[i] = IxfView(int(seed[i]), int(bins[i]), int(tbins[i]), int(seg_len[i]), ptr, 0 if rows is None else int(rows[i]))
         bin_off = np.ascontiguousarray(bin_off, dtype=np.uint64)
         nx = np.ascontiguousarray(next_ixf_id, dtype=np.int64)
         ub = np.ascontiguousarray(bin_to_ub, dtype=np.int64)
-        v = HixfView(n, ixfs, bin_off.ctypes.data, nx.ctypes.data, ub.ctypes.data, int(n_user_bins))
+        sch = None
+        if scheme is not None or layout:
+            sc = tuple(scheme) if scheme is not None else (0, 0, 0, 21, 42)
+            sch = C.pointer(IxfScheme(*[int(x) for x in sc], int(layout)))
+        v = HixfView(n, ixfs, bin_off.ctypes.data, nx.ctypes.data, ub.ctypes.data, int(n_user_bins), sch)
         _check(self._L.txr_index_upload(self._h, C.byref(v)))
 
     def clone_index_from(self, other: "Context") -> None:

@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "ixf_arith.cuh"
+
 namespace txr
 {
 constexpr int kTileWindows = 1024;         // windows per warp tile in the hash kernels (32 per lane)
@@ -105,6 +107,7 @@ struct IxfDev
     uint32_t bins;             // counting-vector size
     uint32_t meta_off;         // first entry of this IXF in the per-bin metadata arrays
     uint32_t max_run;          // longest run of technical bins that belong to one user bin (>= 1)
+    uint32_t count_len;        // FUSE3 only: segment_count * seg_len, the range of the first slot
 };
 
 enum : uint8_t { kBinMid = 0, kBinRunEnd = 1, kBinMerged = 2 };
@@ -146,6 +149,8 @@ struct QueryArgs
     int ctas_per_sm;                // host side: CTAs per SM of the persistent probe grid (0: fill the SM)
     uint32_t early_exit;            // 1: stop probing an item once no user bin can reach the threshold any more
     uint32_t l2_hints;              // 1: items are grouped by IXF, use the L2 eviction-priority plan (query_kernels.cu)
+    uint32_t generic;               // 1: the index was uploaded with a non-default probe arithmetic (`scheme`)
+    IxfScheme scheme;
     unsigned long long *stat_bytes; // algorithmic bytes: sum H*3*tbins + 8*H
     unsigned long long *stat_items;
     unsigned long long *stat_skipped; // hashes NOT probed thanks to the early exit (their bytes are not in stat_bytes)

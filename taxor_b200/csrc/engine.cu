@@ -43,7 +43,7 @@ cudaError_t launch_sort_items(const uint2 *items, const uint32_t *n_ptr, uint32_
                               int sm_count, cudaStream_t st);
 cudaError_t launch_root_partitioned(const QueryArgs &q, const RootPartArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_binset(const BinSetArgs &a, int sm_count, cudaStream_t st);
-cudaError_t launch_bulk_count(const IxfDev &d, const uint64_t *values, uint32_t n, uint32_t *counts, cudaStream_t st);
+cudaError_t launch_bulk_count(const IxfDev &d, const IxfScheme &sch, const uint64_t *values, uint32_t n, uint32_t *counts, cudaStream_t st);
 } // namespace txr
 
 using namespace txr;
@@ -160,6 +160,8 @@ struct DeviceIndex
     bool any_large{false};
     uint64_t n_user_bins{0};
     uint64_t fp_bytes{0};
+    IxfScheme scheme{kIxfSlotsXor3, kIxfMixAddSeed, kIxfFpFold32, 21u, 42u}; // probe arithmetic the index was built with
+    bool generic{false};                // scheme != the prototype's: the descriptor-driven kernels run
     void release()
     {
         arena.release();
@@ -462,7 +464,7 @@ static int upload_batch_meta(const BatchMeta &m, BatchDev &d, cudaStream_t st, u
 constexpr uint32_t kPartCtlWords = 4 + 1025 + 1024;
 static uint32_t root_partition_bits(const txr_ctx *c, const BatchMeta &m)
 {
-    if (!c->root_partition || !c->index.loaded)
+    if (!c->root_partition || !c->index.loaded || c->index.generic) // the partition key is the prototype's segment-0 slot
         return 0;
     const IxfDev &root = c->index.ixf[0];
     const uint64_t seg_bytes = (uint64_t)root.seg_len * root.tbins;
@@ -645,6 +647,8 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
     q.stat_items = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 2);
     q.stat_skipped = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 4);
     q.early_exit = c->early_exit;
+    q.generic = ix.generic;
+    q.scheme = ix.scheme;
     q.smf = c->smf_query;
     q.ctas_per_sm = c->shape_query;
     uint2 *queues = s.queues.as<uint2>();
@@ -1180,6 +1184,8 @@ int txr_ctx_configure(txr_ctx *c, uint64_t max_batch_reads, uint64_t max_batch_b
 // worker threads copy (or, when rows have to be padded to 64 bytes, re-stride) pieces into their own PINNED staging
 // buffers and queue an async copy each on their own stream, so the page faults and memcpys of one piece overlap the DMA
 // of the others.  TXR_UPLOAD_THREADS overrides the worker count (1 = the simple serial copy, for A/B measurements).
+static inline uint64_t view_rows(const txr_ixf_view &x) { return x.rows ? x.rows : 3 * x.seg_len; }
+
 static int upload_fingerprints(txr_ctx *c, const txr_hixf_view *v, DeviceIndex &ix)
 {
     struct Piece
@@ -1187,11 +1193,12 @@ static int upload_fingerprints(txr_ctx *c, const txr_hixf_view *v, DeviceIndex &
         uint64_t ixf, row0, rows;
     };
     constexpr uint64_t kStage = 16ull << 20;
+    const bool bin_major = v->scheme && v->scheme->layout == TXR_IXF_LAYOUT_BIN_MAJOR;
     std::vector<Piece> pieces;
     uint64_t total = 0;
     for (uint64_t i = 0; i < v->n_ixf; ++i)
     {
-        const uint64_t rows = 3 * v->ixf[i].seg_len, stride = ix.ixf[i].tbins;
+        const uint64_t rows = view_rows(v->ixf[i]), stride = ix.ixf[i].tbins;
         const uint64_t per = std::max<uint64_t>(1, kStage / stride);
         for (uint64_t r0 = 0; r0 < rows; r0 += per)
             pieces.push_back(Piece{i, r0, std::min(per, rows - r0)});
@@ -1201,6 +1208,8 @@ static int upload_fingerprints(txr_ctx *c, const txr_hixf_view *v, DeviceIndex &
     if (const char *e = getenv("TXR_UPLOAD_THREADS"))
         n_workers = std::max(1, atoi(e));
     n_workers = (int)std::min<uint64_t>((uint64_t)n_workers, std::max<uint64_t>(1, total / kStage));
+    if (bin_major)
+        n_workers = std::max(n_workers, 1);
     std::atomic<size_t> next{0};
     std::atomic<int> failed{0};
     std::string first_error;
@@ -1245,7 +1254,19 @@ static int upload_fingerprints(txr_ctx *c, const txr_hixf_view *v, DeviceIndex &
                 break;
             }
             const uint8_t *src = x.fp + pc.row0 * x.tbins;
-            if (stride == x.tbins)
+            if (bin_major)
+            {
+                // fp[bin * rows + slot] -> rows of `stride` bytes (HBM is always slot-major: one probe = three rows)
+                const uint64_t all_rows = view_rows(x);
+                memset(buf[cur], 0, pc.rows * stride);
+                for (uint64_t b = 0; b < x.bins; ++b)
+                {
+                    const uint8_t *col = x.fp + b * all_rows + pc.row0;
+                    for (uint64_t r = 0; r < pc.rows; ++r)
+                        buf[cur][r * stride + b] = col[r];
+                }
+            }
+            else if (stride == x.tbins)
                 memcpy(buf[cur], src, pc.rows * stride);
             else
                 for (uint64_t r = 0; r < pc.rows; ++r)
@@ -1280,14 +1301,14 @@ static int upload_fingerprints(txr_ctx *c, const txr_hixf_view *v, DeviceIndex &
                 cudaFreeHost(buf[b]);
         }
     };
-    if (n_workers <= 1)
+    if (n_workers <= 1 && !bin_major)
     {
         // the plain path: pageable copies, row-strided when padding is needed
         for (uint64_t i = 0; i < v->n_ixf; ++i)
         {
             const txr_ixf_view &x = v->ixf[i];
             uint8_t *dst = const_cast<uint8_t *>(ix.ixf[i].fp);
-            const uint64_t rows = 3 * x.seg_len, dev_tbins = ix.ixf[i].tbins;
+            const uint64_t rows = view_rows(x), dev_tbins = ix.ixf[i].tbins;
             if (dev_tbins == x.tbins)
                 CU(cudaMemcpy(dst, x.fp, rows * x.tbins, cudaMemcpyHostToDevice));
             else
@@ -1317,6 +1338,21 @@ int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
     DeviceIndex &ix = c->index;
     ix.release();
     const uint64_t n = v->n_ixf;
+    IxfScheme sch = ixf_default_scheme();
+    if (v->scheme)
+    {
+        sch = IxfScheme{v->scheme->slots, v->scheme->mix, v->scheme->fingerprint, v->scheme->rot1, v->scheme->rot2};
+        if (sch.rot1 == 0 && sch.rot2 == 0)
+        {
+            sch.rot1 = 21;
+            sch.rot2 = 42;
+        }
+        if (!ixf_scheme_valid(sch) || v->scheme->layout > TXR_IXF_LAYOUT_BIN_MAJOR)
+            return set_error(TXR_ERR_ARG, "unknown interleaved-XOR-filter scheme (slots %u mix %u fingerprint %u rot %u/%u layout %u)",
+                             v->scheme->slots, v->scheme->mix, v->scheme->fingerprint, v->scheme->rot1, v->scheme->rot2, v->scheme->layout);
+    }
+    ix.scheme = sch;
+    ix.generic = !ixf_scheme_is_default(sch);
     // validate + size the arena (rows padded to a multiple of 64 bytes, each IXF 256-byte aligned)
     std::vector<uint64_t> arena_off(n);
     uint64_t arena_bytes = 0, total_bins = v->bin_off[n];
@@ -1327,8 +1363,11 @@ int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
     for (uint64_t i = 0; i < n; ++i)
     {
         const txr_ixf_view &x = v->ixf[i];
-        if (x.bins == 0 || x.tbins < x.bins || x.seg_len == 0 || x.seg_len >= (1ull << 31) || !x.fp)
-            return set_error(TXR_ERR_ARG, "IXF %llu: inconsistent geometry", (unsigned long long)i);
+        uint64_t count_len = 0;
+        if (x.bins == 0 || x.tbins < x.bins || !x.fp || !ixf_geometry_ok(sch, x.seg_len, view_rows(x), count_len))
+            return set_error(TXR_ERR_ARG, "IXF %llu: inconsistent geometry (bins %llu, row width %llu, %llu slots per segment, %llu rows)",
+                             (unsigned long long)i, (unsigned long long)x.bins, (unsigned long long)x.tbins,
+                             (unsigned long long)x.seg_len, (unsigned long long)view_rows(x));
         if (v->bin_off[i + 1] - v->bin_off[i] != x.bins)
             return set_error(TXR_ERR_ARG, "IXF %llu: bin metadata size != bins", (unsigned long long)i);
         const uint64_t dev_tbins = (x.tbins + 63) / 64 * 64;
@@ -1336,11 +1375,12 @@ int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
             return set_error(TXR_ERR_UNSUPPORTED, "IXF %llu: %llu technical bins not supported (limit %u)", (unsigned long long)i,
                              (unsigned long long)x.tbins, query_large_max_tbins());
         arena_off[i] = arena_bytes;
-        arena_bytes += (3 * x.seg_len * dev_tbins + 255) / 256 * 256;
-        ix.ixf[i] = IxfDev{nullptr, x.seed, (uint32_t)x.seg_len, (uint32_t)dev_tbins, (uint32_t)x.bins, (uint32_t)v->bin_off[i], 1u};
+        arena_bytes += (view_rows(x) * dev_tbins + 255) / 256 * 256;
+        ix.ixf[i] = IxfDev{nullptr, x.seed, (uint32_t)x.seg_len, (uint32_t)dev_tbins, (uint32_t)x.bins, (uint32_t)v->bin_off[i], 1u,
+                           (uint32_t)count_len};
         ix.max_tbins = std::max<uint32_t>(ix.max_tbins, (uint32_t)dev_tbins);
         ix.any_large = ix.any_large || dev_tbins > kSmallRowBytes;
-        ix.fp_bytes += 3 * x.seg_len * dev_tbins;
+        ix.fp_bytes += view_rows(x) * dev_tbins;
     }
     TRY(ix.arena.ensure_exact(arena_bytes));
     for (uint64_t i = 0; i < n; ++i)
@@ -1476,6 +1516,8 @@ int txr_index_clone(txr_ctx *dst, txr_ctx *src)
     b.any_large = a.any_large;
     b.n_user_bins = a.n_user_bins;
     b.fp_bytes = a.fp_bytes;
+    b.scheme = a.scheme;
+    b.generic = a.generic;
     struct Pair
     {
         const DevBuf *from;
@@ -2151,7 +2193,7 @@ int txr_ixf_bulk_count(txr_ctx *c, uint64_t ixf_idx, const uint64_t *values, uin
     cudaStream_t st = c->slots[0]->stream;
     if (n)
         CU(cudaMemcpyAsync(c->scratch_a.p, values, n * 8, cudaMemcpyHostToDevice, st));
-    CU(launch_bulk_count(d, c->scratch_a.as<uint64_t>(), (uint32_t)n, c->scratch_b.as<uint32_t>(), st));
+    CU(launch_bulk_count(d, c->index.scheme, c->scratch_a.as<uint64_t>(), (uint32_t)n, c->scratch_b.as<uint32_t>(), st));
     CU(cudaMemcpyAsync(counts, c->scratch_b.p, (size_t)d.bins * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return TXR_OK;

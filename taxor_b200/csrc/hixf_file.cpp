@@ -2,6 +2,7 @@
 // types raw little-endian, bool one byte, std::string / std::vector prefixed by a u64 element count, vectors of
 // arithmetic types as one raw block, classes with serialize() without any header.
 #include "hixf_file.hpp"
+#include "ixf_arith.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -40,6 +41,55 @@ std::string IxfRecordSpec::str() const
     std::string r;
     for (auto &x : scalars)
         r += (r.empty() ? "" : ",") + x;
+    return r;
+}
+
+bool IxfSchemeSpec::parse(const std::string &text, IxfSchemeSpec &out, std::string &error)
+{
+    out = IxfSchemeSpec{};
+    const size_t colon = text.find(':');
+    const std::string head = text.substr(0, colon);
+    if (head == "xor3" || head.empty())
+        out.slots = kIxfSlotsXor3;
+    else if (head == "fuse3")
+        out.slots = kIxfSlotsFuse3;
+    else
+    {
+        error = "unknown filter scheme '" + head + "' (xor3 | fuse3)";
+        return false;
+    }
+    if (colon == std::string::npos)
+        return true;
+    std::stringstream ss(text.substr(colon + 1));
+    std::string kv;
+    while (std::getline(ss, kv, ','))
+    {
+        const size_t eq = kv.find('=');
+        const std::string k = kv.substr(0, eq), v = eq == std::string::npos ? "" : kv.substr(eq + 1);
+        if (k == "mix" && (v == "add" || v == "xor"))
+            out.mix = v == "xor" ? kIxfMixXorSeed : kIxfMixAddSeed;
+        else if (k == "fp" && (v == "fold32" || v == "low8" || v == "high8"))
+            out.fingerprint = v == "fold32" ? kIxfFpFold32 : v == "low8" ? kIxfFpLow8 : kIxfFpHigh8;
+        else if (k == "rot" && sscanf(v.c_str(), "%u/%u", &out.rot1, &out.rot2) == 2 && out.rot1 < 64 && out.rot2 < 64)
+            ;
+        else if (k == "layout" && (v == "slot" || v == "bin"))
+            out.layout = v == "bin" ? 1u : 0u;
+        else
+        {
+            error = "bad filter scheme option '" + kv + "' (mix=add|xor, fp=fold32|low8|high8, rot=R1/R2, layout=slot|bin)";
+            return false;
+        }
+    }
+    return true;
+}
+
+std::string IxfSchemeSpec::str() const
+{
+    std::string r = slots == kIxfSlotsFuse3 ? "fuse3" : "xor3";
+    r += std::string(":mix=") + (mix == kIxfMixXorSeed ? "xor" : "add");
+    r += std::string(",fp=") + (fingerprint == kIxfFpFold32 ? "fold32" : fingerprint == kIxfFpLow8 ? "low8" : "high8");
+    r += ",rot=" + std::to_string(rot1) + "/" + std::to_string(rot2);
+    r += std::string(",layout=") + (layout ? "bin" : "slot");
     return r;
 }
 
@@ -139,9 +189,12 @@ struct Reader
     }
 };
 
-// parses everything from the IXF vector to the end of the file with one candidate record order
-std::string parse_hixf_tail(Reader rd, TaxorIndexFile &idx, const IxfRecordSpec &spec)
+// parses everything from the IXF vector to the end of the file with one candidate record order.
+// capacity_ok (optional): every IXF carries a non-zero max_elems and its geometry is what the scheme derives from it
+std::string parse_hixf_tail(Reader rd, TaxorIndexFile &idx, const IxfRecordSpec &spec, const IxfSchemeSpec &sc, bool *capacity_ok)
 {
+    const IxfScheme scheme{sc.slots, sc.mix, sc.fingerprint, sc.rot1, sc.rot2};
+    bool cap_ok = true;
     // every record is at least its scalars and the length of its fingerprint vector: a count beyond that is damage,
     // not a reason to allocate
     const uint64_t n_ixf = rd.count(8 * (spec.scalars.size() + 1));
@@ -173,13 +226,27 @@ std::string parse_hixf_tail(Reader rd, TaxorIndexFile &idx, const IxfRecordSpec 
         x.fp_len = len;
         rd.p += len;
         if (have_slots && !have_seg)
+        {
+            if (scheme.slots != kIxfSlotsXor3)
+                return "a binary-fuse record needs both 'seg_len' and 'slots' in the record order";
             x.seg_len = slots / 3;
+        }
         if (!have_slots)
             slots = 3 * x.seg_len;
+        x.rows = slots;
         if (x.bins == 0 || x.tbins < x.bins || x.tbins % 64 != 0 || x.tbins > (1u << 20))
             return "IXF " + std::to_string(i) + ": implausible bins/technical bins";
-        if (x.seg_len == 0 || slots != 3 * x.seg_len)
-            return "IXF " + std::to_string(i) + ": slot count is not three equal segments";
+        uint64_t count_len = 0;
+        if (!ixf_geometry_ok(scheme, x.seg_len, x.rows, count_len))
+            return "IXF " + std::to_string(i) + (scheme.slots == kIxfSlotsXor3 ? ": slot count is not three equal segments"
+                                                                                : ": slots are not whole power-of-two segments");
+        if (x.max_elems == 0)
+            cap_ok = false;
+        else
+        {
+            const IxfGeometry g = ixf_geometry_for(scheme, x.max_elems);
+            cap_ok = cap_ok && g.seg_len == x.seg_len && g.rows == x.rows;
+        }
         if (have_ftype && x.ftype != 8 && x.ftype != 16)
             return "IXF " + std::to_string(i) + ": fingerprint width is neither 8 nor 16";
         if (have_words && bin_words * 64 != x.tbins)
@@ -215,6 +282,8 @@ std::string parse_hixf_tail(Reader rd, TaxorIndexFile &idx, const IxfRecordSpec 
             if (ub >= (int64_t)n_names)
                 return "user bin id beyond user_bin_filenames";
     }
+    if (capacity_ok)
+        *capacity_ok = cap_ok;
     return "";
 }
 } // namespace
@@ -262,7 +331,7 @@ std::string write_hixf(const std::string &path, const TaxorIndexFile &idx, const
             uint64_t v = 0;
             if (name == "bins") v = x.bins;
             else if (name == "tbins") v = x.tbins;
-            else if (name == "slots") v = 3 * x.seg_len;
+            else if (name == "slots") v = x.rows ? x.rows : 3 * x.seg_len;
             else if (name == "seg_len") v = x.seg_len;
             else if (name == "bin_words") v = x.tbins / 64;
             else if (name == "max_elems") v = x.max_elems;
@@ -288,8 +357,10 @@ std::string write_hixf(const std::string &path, const TaxorIndexFile &idx, const
     return "";
 }
 
-std::string read_hixf(const std::string &path, TaxorIndexFile &idx, const IxfRecordSpec *spec, IxfRecordSpec *used)
+std::string read_hixf(const std::string &path, TaxorIndexFile &idx, const IxfRecordSpec *spec, IxfRecordSpec *used,
+                      const IxfSchemeSpec *scheme_in, HixfReadReport *report)
 {
+    const IxfSchemeSpec scheme = scheme_in ? *scheme_in : IxfSchemeSpec{};
     const int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0)
         return "cannot open " + path;
@@ -348,18 +419,55 @@ std::string read_hixf(const std::string &path, TaxorIndexFile &idx, const IxfRec
         return "truncated header (parameters / bin paths / species table)";
     if (idx.kmer_size == 0 || idx.kmer_size > 32)
         return "implausible k-mer size " + std::to_string(idx.kmer_size);
+    // Every candidate order is tried.  "The file tiles" cannot tell orders apart that only permute free u64 scalars (seed
+    // vs. max_elems), so orders whose max_elems reproduces the stored geometry through the scheme's capacity formula
+    // (rows == geometry(max_elems), ixf_arith.cuh) win; what is left ambiguous is reported, not hidden.
     std::string errors;
     const std::vector<IxfRecordSpec> one = spec ? std::vector<IxfRecordSpec>{*spec} : std::vector<IxfRecordSpec>{};
-    for (auto &cand : spec ? one : IxfRecordSpec::candidates())
+    const std::vector<IxfRecordSpec> &cands = spec ? one : IxfRecordSpec::candidates();
+    int first_tiling = -1, first_consistent = -1;
+    unsigned n_tiling = 0, n_consistent = 0;
+    std::string tiling_list;
+    for (size_t ci = 0; ci < cands.size(); ++ci)
     {
-        const std::string e = parse_hixf_tail(rd, idx, cand);
+        bool cap_ok = false;
+        TaxorIndexFile probe;
+        const std::string e = parse_hixf_tail(rd, probe, cands[ci], scheme, &cap_ok);
         if (e.empty())
         {
-            if (used)
-                *used = cand;
-            return "";
+            ++n_tiling;
+            tiling_list += (tiling_list.empty() ? "" : " | ") + cands[ci].str();
+            if (first_tiling < 0)
+                first_tiling = (int)ci;
+            if (cap_ok)
+            {
+                ++n_consistent;
+                if (first_consistent < 0)
+                    first_consistent = (int)ci;
+            }
         }
-        errors += "\n  [" + cand.str() + "] " + e;
+        else
+            errors += "\n  [" + cands[ci].str() + "] " + e;
+    }
+    if (first_tiling >= 0)
+    {
+        const int pick = first_consistent >= 0 ? first_consistent : first_tiling;
+        parse_hixf_tail(rd, idx, cands[(size_t)pick], scheme, nullptr);
+        if (used)
+            *used = cands[(size_t)pick];
+        if (report)
+        {
+            report->used = cands[(size_t)pick];
+            report->tiling_candidates = n_tiling;
+            report->capacity_consistent = n_consistent;
+            const unsigned ambiguous = first_consistent >= 0 ? n_consistent : n_tiling;
+            if (ambiguous > 1)
+                report->note = std::to_string(ambiguous) + " record orders fit this file equally well (" + tiling_list +
+                               "); using [" + cands[(size_t)pick].str() + "] -- seed and capacity may be swapped, pass --ixf-record to pin the order";
+            else if (first_consistent < 0 && !spec)
+                report->note = "record order [" + cands[(size_t)pick].str() + "] accepted on tiling alone (no max_elems/geometry cross-check possible)";
+        }
+        return "";
     }
     return "the interleaved-XOR-filter records of " + path + " do not parse with any known field order "
            "(the order is defined by the SeqAn3 fork; pass --ixf-record to override):" + errors;

@@ -23,7 +23,8 @@ struct SpeciesRecord // src/taxonomy/Species.hpp:14-21, serialised fields :43-49
 struct IxfRecord
 {
     uint64_t seed{0}, bins{0}, tbins{0}, seg_len{0}, max_elems{0}, ftype{8};
-    const uint8_t *fp{nullptr}; // fp[slot * tbins + bin], 3 * seg_len slots: points into `owned` or into the mapped file
+    uint64_t rows{0};           // slots per bin (0: 3 * seg_len)
+    const uint8_t *fp{nullptr}; // fp[slot * tbins + bin], `rows` slots: points into `owned` or into the mapped file
     uint64_t fp_len{0};
     std::vector<uint8_t> owned;
 };
@@ -60,8 +61,28 @@ struct IxfRecordSpec
     std::string str() const;
 };
 
+// The filter arithmetic the records are checked against (ixf_arith.cuh; mirrors txr_ixf_scheme of the C ABI).
+// Text form: "xor3" | "fuse3", then optional ":key=value,..." with mix=add|xor, fp=fold32|low8|high8, rot=R1/R2, layout=slot|bin.
+struct IxfSchemeSpec
+{
+    uint32_t slots{0}, mix{0}, fingerprint{0}, rot1{21}, rot2{42}, layout{0};
+    static bool parse(const std::string &text, IxfSchemeSpec &out, std::string &error);
+    std::string str() const;
+};
+
+// What the reader found out about the record order (the free scalars of a candidate order cannot all be told apart by
+// "the file tiles": `seed` and `max_elems` are both arbitrary u64s).
+struct HixfReadReport
+{
+    IxfRecordSpec used;              // the accepted order
+    unsigned tiling_candidates{0};   // candidate orders under which every record is self-consistent and the file tiles
+    unsigned capacity_consistent{0}; // ... of which also satisfy rows == geometry(max_elems) in every IXF (0 if none carries max_elems)
+    std::string note;                // human-readable summary of the above (empty when the choice was unambiguous)
+};
+
 // Both return an empty string on success, else a description of what failed.
 std::string write_hixf(const std::string &path, const TaxorIndexFile &idx, const IxfRecordSpec &spec);
 // spec == nullptr: try every candidate; `used` (optional) receives the accepted order
-std::string read_hixf(const std::string &path, TaxorIndexFile &idx, const IxfRecordSpec *spec, IxfRecordSpec *used);
+std::string read_hixf(const std::string &path, TaxorIndexFile &idx, const IxfRecordSpec *spec, IxfRecordSpec *used,
+                      const IxfSchemeSpec *scheme = nullptr, HixfReadReport *report = nullptr);
 } // namespace txr

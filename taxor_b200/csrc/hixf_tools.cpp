@@ -25,7 +25,8 @@ int txs_hixf_write(const char *path, const char *record_spec, uint64_t window_si
                    const uint64_t *tbins, const uint64_t *seg_len, const uint8_t *const *data, const uint64_t *bin_off,
                    const int64_t *next_ixf_id, const int64_t *bin_to_ub, uint64_t n_user_bins, const char *const *ub_filenames,
                    uint64_t n_species, const char *const *organism, const char *const *accession, const char *const *taxid,
-                   const char *const *taxnames, const char *const *taxids, const uint64_t *sp_user_bin, const uint64_t *sp_seq_len)
+                   const char *const *taxnames, const char *const *taxids, const uint64_t *sp_user_bin, const uint64_t *sp_seq_len,
+                   const uint64_t *rows, const uint64_t *max_elems) // rows / max_elems may be null (3*seg_len / 0)
 {
     TaxorIndexFile f;
     f.window_size = window_size;
@@ -61,7 +62,9 @@ int txs_hixf_write(const char *path, const char *record_spec, uint64_t window_si
         x.tbins = tbins[i];
         x.seg_len = seg_len[i];
         x.fp = data[i];
-        x.fp_len = 3 * seg_len[i] * tbins[i];
+        x.rows = rows ? rows[i] : 3 * seg_len[i];
+        x.max_elems = max_elems ? max_elems[i] : 0;
+        x.fp_len = x.rows * tbins[i];
         f.ixf.push_back(std::move(x));
         f.next_ixf_id.emplace_back(next_ixf_id + bin_off[i], next_ixf_id + bin_off[i + 1]);
         f.ixf_bin_to_filename_position.emplace_back(bin_to_ub + bin_off[i], bin_to_ub + bin_off[i + 1]);
@@ -71,24 +74,42 @@ int txs_hixf_write(const char *path, const char *record_spec, uint64_t window_si
     return g_err.empty() ? 0 : -1;
 }
 
-void *txs_hixf_open(const char *path, const char *record_spec)
+static std::string g_note;
+void *txs_hixf_open2(const char *path, const char *record_spec, const char *scheme_text)
 {
     auto *f = new TaxorIndexFile;
     IxfRecordSpec used;
+    IxfSchemeSpec scheme;
+    HixfReadReport rep;
+    g_note.clear();
+    if (scheme_text && *scheme_text && !IxfSchemeSpec::parse(scheme_text, scheme, g_err))
+    {
+        delete f;
+        return nullptr;
+    }
     if (record_spec && *record_spec)
     {
         const IxfRecordSpec spec = IxfRecordSpec::parse(record_spec);
-        g_err = read_hixf(path, *f, &spec, &used);
+        g_err = read_hixf(path, *f, &spec, &used, &scheme, &rep);
     }
     else
-        g_err = read_hixf(path, *f, nullptr, &used);
+        g_err = read_hixf(path, *f, nullptr, &used, &scheme, &rep);
     if (!g_err.empty())
     {
         delete f;
         return nullptr;
     }
     g_err = used.str();
+    g_note = rep.note;
     return f;
+}
+void *txs_hixf_open(const char *path, const char *record_spec) { return txs_hixf_open2(path, record_spec, nullptr); }
+// the reader's remark about the last successful open (ambiguous record orders); empty when there was nothing to say
+const char *txs_hixf_open_note(void) { return g_note.c_str(); }
+uint64_t txs_hixf_ixf_rows(void *p, uint64_t i)
+{
+    const IxfRecord &x = static_cast<TaxorIndexFile *>(p)->ixf[i];
+    return x.rows ? x.rows : 3 * x.seg_len;
 }
 void txs_hixf_close(void *p) { delete static_cast<TaxorIndexFile *>(p); }
 

@@ -92,16 +92,35 @@ __device__ __forceinline__ L2Plan l2_plan_for(const IxfDev &d, bool enabled)
     return p;
 }
 
-__device__ __forceinline__ void probe_issue(Probe &p, const IxfDev &d, const uint8_t *col_base, uint64_t key, bool live,
-                                            const L2Plan &l2 = L2Plan{false, 0, 0})
+// the three rows + fingerprint of a key.  GEN == false: the prototype's arithmetic with folded constants (the default
+// scheme); GEN == true: driven by the descriptor the index was uploaded with (ixf_arith.cuh)
+template <bool GEN>
+__device__ __forceinline__ uint32_t probe_address(const IxfDev &d, const IxfScheme &sch, uint64_t key, uint32_t &p0, uint32_t &p1,
+                                                  uint32_t &p2)
+{
+    if constexpr (GEN)
+    {
+        const uint64_t h = ixf_mix_g(key, d.seed, sch);
+        ixf_slots_g(h, d.seg_len, d.count_len, sch, p0, p1, p2);
+        return ixf_fingerprint_g(h, sch) * 0x01010101u;
+    }
+    else
+    {
+        const uint64_t h = ixf_mix(key, d.seed);
+        ixf_slots(h, d.seg_len, p0, p1, p2);
+        return ixf_fingerprint(h) * 0x01010101u;
+    }
+}
+
+template <bool GEN>
+__device__ __forceinline__ void probe_issue(Probe &p, const IxfDev &d, const IxfScheme &sch, const uint8_t *col_base, uint64_t key,
+                                            bool live, const L2Plan &l2 = L2Plan{false, 0, 0})
 {
     p.live = live;
     if (live)
     {
-        const uint64_t h = ixf_mix(key, d.seed);
         uint32_t p0, p1, p2;
-        ixf_slots(h, d.seg_len, p0, p1, p2);
-        p.fs = ixf_fingerprint(h) * 0x01010101u;
+        p.fs = probe_address<GEN>(d, sch, key, p0, p1, p2);
         if (l2.split)
         {
             p.r0 = ldg_row16_hint(col_base + (uint64_t)p0 * d.tbins, l2.keep);
@@ -172,8 +191,8 @@ __device__ __forceinline__ uint32_t max_byte4(const uint32_t (&acc)[4])
 //   cnt       : shared counters of the chunk's first bin
 //   exit_thr  : != 0: the chunk is the whole row and the item may stop early against this threshold
 // Returns the number of hashes probed.
-template <int UNROLL>
-__device__ __forceinline__ uint32_t probe_chunk(const IxfDev &d, const uint64_t *__restrict__ hp, uint32_t H,
+template <int UNROLL, bool GEN>
+__device__ __forceinline__ uint32_t probe_chunk(const IxfDev &d, const IxfScheme &sch, const uint64_t *__restrict__ hp, uint32_t H,
                                                 uint32_t chunk_off, uint32_t lpr, uint32_t *cnt, int lane,
                                                 const L2Plan &l2 = L2Plan{false, 0, 0}, uint64_t exit_thr = 0)
 {
@@ -200,7 +219,7 @@ __device__ __forceinline__ uint32_t probe_chunk(const IxfDev &d, const uint64_t 
             const uint32_t idx = h0 + u * G + sub;
             const bool live = active && idx < H;
             const uint64_t key = live ? hp[idx] : 0;
-            probe_issue(pr[u], d, col_base, key, live, l2);
+            probe_issue<GEN>(pr[u], d, sch, col_base, key, live, l2);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
@@ -321,6 +340,7 @@ __device__ __forceinline__ void scan_bins(const QueryArgs &a, const IxfDev &d, u
 } // namespace
 
 // ---- IXFs with tbins <= 512: one warp per (read, IXF) ----
+template <bool GEN>
 __global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(QueryArgs a)
 {
     if (!sm_filter_keep(a.smf))
@@ -352,8 +372,8 @@ __global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(Query
         const uint32_t H = a.hash_count[read];
         const uint64_t *hp = a.hashes + a.hash_off[read];
         const uint64_t thr = a.thr_read ? a.thr_read[read] : (H < a.lut_len ? a.thr_lut[H] : ~0ULL);
-        const uint32_t Hp = probe_chunk<kQueryUnroll>(d, hp, H, 0u, d.tbins >> 4, cnt, lane, l2_plan_for(d, a.l2_hints != 0),
-                                                      a.early_exit ? thr : 0);
+        const uint32_t Hp = probe_chunk<kQueryUnroll, GEN>(d, a.scheme, hp, H, 0u, d.tbins >> 4, cnt, lane,
+                                                           l2_plan_for(d, a.l2_hints != 0), a.early_exit ? thr : 0);
         __syncwarp();
         scan_bins(a, d, read, thr, cnt, (uint32_t)lane, 32u);
         __syncwarp();
@@ -544,7 +564,7 @@ __global__ void __launch_bounds__(32 * kQueryWarps) root_part_probe_kernel(RootP
                 const bool live = active && idx < e1;
                 const uint64_t key = live ? a.part_hash[idx] : 0;
                 rd[u] = live ? a.part_read[idx] : 0;
-                probe_issue(pr[u], d, col_base, key, live);
+                probe_issue<false>(pr[u], d, IxfScheme{}, col_base, key, live);
             }
 #pragma unroll
             for (int u = 0; u < kQueryUnroll; ++u)
@@ -626,9 +646,9 @@ __global__ void __launch_bounds__(32 * kQueryWarps) root_part_scan_kernel2(Query
 constexpr int kWideWarps = 8;
 constexpr uint32_t kWideHashesPerWarp = 8;
 
-template <int CP, int U>
-__device__ __forceinline__ void wide_block(const IxfDev &d, const uint64_t *__restrict__ hp, uint32_t h_begin, uint32_t h_end,
-                                           uint32_t col0, uint32_t *s_cnt, int lane)
+template <int CP, int U, bool GEN>
+__device__ __forceinline__ void wide_block(const IxfDev &d, const IxfScheme &sch, const uint64_t *__restrict__ hp, uint32_t h_begin,
+                                           uint32_t h_end, uint32_t col0, uint32_t *s_cnt, int lane)
 {
     uint32_t acc[CP][4];
     bool col_ok[CP];
@@ -647,10 +667,8 @@ __device__ __forceinline__ void wide_block(const IxfDev &d, const uint64_t *__re
         for (int u = 0; u < U; ++u)
         {
             const bool live = h + u < h_end;
-            const uint64_t x = ixf_mix(live ? hp[h + u] : 0, d.seed);
             uint32_t p0, p1, p2;
-            ixf_slots(x, d.seg_len, p0, p1, p2);
-            fs[u] = ixf_fingerprint(x) * 0x01010101u;
+            fs[u] = probe_address<GEN>(d, sch, live ? hp[h + u] : 0, p0, p1, p2);
             const uint8_t *q0 = base + (uint64_t)p0 * d.tbins, *q1 = base + (uint64_t)p1 * d.tbins, *q2 = base + (uint64_t)p2 * d.tbins;
 #pragma unroll
             for (int c = 0; c < CP; ++c)
@@ -685,9 +703,9 @@ __device__ __forceinline__ void wide_block(const IxfDev &d, const uint64_t *__re
             acc_flush(acc[c], s_cnt + col0 + 512u * c + 16u * lane);
 }
 
-template <int CP, int U>
-__device__ __forceinline__ uint32_t wide_item(const IxfDev &d, const uint64_t *__restrict__ hp, uint32_t H, uint32_t *s_cnt,
-                                              uint32_t *s_red, uint64_t exit_thr)
+template <int CP, int U, bool GEN>
+__device__ __forceinline__ uint32_t wide_item(const IxfDev &d, const IxfScheme &sch, const uint64_t *__restrict__ hp, uint32_t H,
+                                              uint32_t *s_cnt, uint32_t *s_red, uint64_t exit_thr)
 {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     constexpr uint32_t HB = kWideWarps * kWideHashesPerWarp;
@@ -700,7 +718,7 @@ __device__ __forceinline__ uint32_t wide_item(const IxfDev &d, const uint64_t *_
         const uint32_t hb = min(H, b0 + wib * kWideHashesPerWarp), he = min(H, hb + kWideHashesPerWarp);
         if (hb < he)
             for (uint32_t col0 = 0; col0 < d.tbins; col0 += 512u * CP)
-                wide_block<CP, U>(d, hp, hb, he, col0, s_cnt, lane);
+                wide_block<CP, U, GEN>(d, sch, hp, hb, he, col0, s_cnt, lane);
         const uint32_t done = min(H, b0 + HB);
         if (done >= next_check && done < H) // CTA-uniform
         {
@@ -724,6 +742,7 @@ __device__ __forceinline__ uint32_t wide_item(const IxfDev &d, const uint64_t *_
     return H;
 }
 
+template <bool GEN>
 __global__ void __launch_bounds__(32 * kWideWarps, 2) ixf_query_large_kernel(QueryArgs a)
 {
     if (!sm_filter_keep(a.smf))
@@ -759,9 +778,9 @@ __global__ void __launch_bounds__(32 * kWideWarps, 2) ixf_query_large_kernel(Que
         const uint64_t exit_thr = a.early_exit ? thr : 0;
         uint32_t Hp;
         if (d.tbins <= 1024)
-            Hp = wide_item<2, 2>(d, hp, H, s_cnt_dyn, s_red, exit_thr);
+            Hp = wide_item<2, 2, GEN>(d, a.scheme, hp, H, s_cnt_dyn, s_red, exit_thr);
         else
-            Hp = wide_item<4, 1>(d, hp, H, s_cnt_dyn, s_red, exit_thr);
+            Hp = wide_item<4, 1, GEN>(d, a.scheme, hp, H, s_cnt_dyn, s_red, exit_thr);
         __syncthreads();
         scan_bins(a, d, read, thr, s_cnt_dyn, threadIdx.x, blockDim.x);
         bytes += (unsigned long long)Hp * 3ull * d.tbins + 8ull * Hp;
@@ -778,7 +797,8 @@ __global__ void __launch_bounds__(32 * kWideWarps, 2) ixf_query_large_kernel(Que
 }
 
 // bulk_count of a single IXF for a single value list (parity entry point txr_ixf_bulk_count)
-__global__ void __launch_bounds__(256) ixf_bulk_count_kernel(IxfDev d, const uint64_t *values, uint32_t n, uint32_t *counts)
+template <bool GEN>
+__global__ void __launch_bounds__(256) ixf_bulk_count_kernel(IxfDev d, IxfScheme sch, const uint64_t *values, uint32_t n, uint32_t *counts)
 {
     extern __shared__ uint32_t s_cnt_dyn[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -790,7 +810,7 @@ __global__ void __launch_bounds__(256) ixf_bulk_count_kernel(IxfDev d, const uin
     {
         const uint32_t off = c * kSmallRowBytes;
         const uint32_t width = min(kSmallRowBytes, d.tbins - off);
-        probe_chunk<kQueryUnroll>(d, values, n, off, width >> 4, s_cnt_dyn + off, lane);
+        probe_chunk<kQueryUnroll, GEN>(d, sch, values, n, off, width >> 4, s_cnt_dyn + off, lane);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < d.bins; i += blockDim.x)
@@ -887,7 +907,10 @@ static int query_ctas(const QueryArgs &a) { return a.ctas_per_sm <= 0 ? 8 : a.ct
 
 cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st)
 {
-    ixf_query_small_kernel<<<sm_count * query_ctas(a), 32 * kQueryWarps, 0, st>>>(a);
+    if (a.generic)
+        ixf_query_small_kernel<true><<<sm_count * query_ctas(a), 32 * kQueryWarps, 0, st>>>(a);
+    else
+        ixf_query_small_kernel<false><<<sm_count * query_ctas(a), 32 * kQueryWarps, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -912,27 +935,36 @@ cudaError_t launch_query_large(const QueryArgs &a, int sm_count, uint32_t max_tb
         return cudaErrorInvalidValue; // txr_index_upload rejects such indexes
     if (smem > 48 * 1024)
     {
-        const cudaError_t e = cudaFuncSetAttribute(ixf_query_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const cudaError_t e = a.generic ? cudaFuncSetAttribute(ixf_query_large_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                        : cudaFuncSetAttribute(ixf_query_large_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
     }
     // CTAs per SM: as many as the counters allow, up to 8 warps x 6 = 48 warps (registers cap it at 4-5 anyway)
     const int by_smem = (int)std::max<size_t>(1, (200u * 1024u) / std::max<size_t>(smem + 64, 1));
     const int ctas = std::min(a.ctas_per_sm > 0 ? a.ctas_per_sm : 6, std::min(by_smem, 6));
-    ixf_query_large_kernel<<<sm_count * ctas, 32 * kWideWarps, smem, st>>>(a);
+    if (a.generic)
+        ixf_query_large_kernel<true><<<sm_count * ctas, 32 * kWideWarps, smem, st>>>(a);
+    else
+        ixf_query_large_kernel<false><<<sm_count * ctas, 32 * kWideWarps, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bulk_count(const IxfDev &d, const uint64_t *values, uint32_t n, uint32_t *counts, cudaStream_t st)
+cudaError_t launch_bulk_count(const IxfDev &d, const IxfScheme &sch, const uint64_t *values, uint32_t n, uint32_t *counts, cudaStream_t st)
 {
     const size_t smem = (size_t)d.tbins * 4;
+    const bool gen = !ixf_scheme_is_default(sch);
     if (smem > 48 * 1024)
     {
-        const cudaError_t e = cudaFuncSetAttribute(ixf_bulk_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const cudaError_t e = gen ? cudaFuncSetAttribute(ixf_bulk_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute(ixf_bulk_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
     }
-    ixf_bulk_count_kernel<<<1, 256, smem, st>>>(d, values, n, counts);
+    if (gen)
+        ixf_bulk_count_kernel<true><<<1, 256, smem, st>>>(d, sch, values, n, counts);
+    else
+        ixf_bulk_count_kernel<false><<<1, 256, smem, st>>>(d, sch, values, n, counts);
     return cudaGetLastError();
 }
 } // namespace txr

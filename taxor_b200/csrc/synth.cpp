@@ -38,7 +38,7 @@ inline unsigned base_at(const uint64_t *w, uint64_t i) { return (unsigned)((w[i 
 
 struct BuiltIxf
 {
-    uint64_t seed{}, bins{}, tbins{}, seg_len{};
+    uint64_t seed{}, bins{}, tbins{}, seg_len{}, rows{}, count_len{}, capacity{};
     std::vector<uint8_t> data;
     std::vector<int64_t> next, ub;
 };
@@ -48,7 +48,8 @@ struct Hixf
     std::deque<BuiltIxf> ixf; // a deque: references stay valid while other threads append
     std::mutex ixf_mutex;
     // flattened accessors
-    std::vector<uint64_t> seed, bins, tbins, seg_len, bin_off;
+    std::vector<uint64_t> seed, bins, tbins, seg_len, bin_off, rows, capacity;
+    txr::IxfScheme scheme{txr::kIxfSlotsXor3, txr::kIxfMixAddSeed, txr::kIxfFpFold32, 21u, 42u};
     std::vector<const uint8_t *> data;
     std::vector<int64_t> next, ub;
     uint64_t n_user_bins{};
@@ -56,11 +57,10 @@ struct Hixf
 };
 
 // peel one bin; fp (3*seg_len bytes) receives the fingerprints.  false: not peelable with this seed
-bool peel_bin(const uint64_t *keys, size_t n, uint64_t seed, uint32_t seg_len, uint8_t *fp, std::vector<uint32_t> &cnt,
-              std::vector<uint64_t> &xr, std::vector<uint32_t> &queue, std::vector<uint64_t> &stack_h,
-              std::vector<uint32_t> &stack_s)
+bool peel_bin(const uint64_t *keys, size_t n, uint64_t seed, const txr::IxfScheme &sch, uint32_t seg_len, uint32_t count_len, size_t slots,
+              uint8_t *fp, std::vector<uint32_t> &cnt, std::vector<uint64_t> &xr, std::vector<uint32_t> &queue,
+              std::vector<uint64_t> &stack_h, std::vector<uint32_t> &stack_s)
 {
-    const size_t slots = 3 * (size_t)seg_len;
     std::memset(fp, 0, slots);
     if (n == 0)
         return true;
@@ -68,9 +68,9 @@ bool peel_bin(const uint64_t *keys, size_t n, uint64_t seed, uint32_t seg_len, u
     xr.assign(slots, 0);
     for (size_t i = 0; i < n; ++i)
     {
-        const uint64_t h = txr::ixf_mix(keys[i], seed);
+        const uint64_t h = txr::ixf_mix_g(keys[i], seed, sch);
         uint32_t p[3];
-        txr::ixf_slots(h, seg_len, p[0], p[1], p[2]);
+        txr::ixf_slots_g(h, seg_len, count_len, sch, p[0], p[1], p[2]);
         for (int j = 0; j < 3; ++j)
         {
             ++cnt[p[j]];
@@ -93,7 +93,7 @@ bool peel_bin(const uint64_t *keys, size_t n, uint64_t seed, uint32_t seg_len, u
         stack_h.push_back(h);
         stack_s.push_back(s);
         uint32_t p[3];
-        txr::ixf_slots(h, seg_len, p[0], p[1], p[2]);
+        txr::ixf_slots_g(h, seg_len, count_len, sch, p[0], p[1], p[2]);
         for (int j = 0; j < 3; ++j)
         {
             --cnt[p[j]];
@@ -108,8 +108,8 @@ bool peel_bin(const uint64_t *keys, size_t n, uint64_t seed, uint32_t seg_len, u
     {
         const uint64_t h = stack_h[i];
         uint32_t p[3];
-        txr::ixf_slots(h, seg_len, p[0], p[1], p[2]);
-        uint8_t f = (uint8_t)txr::ixf_fingerprint(h);
+        txr::ixf_slots_g(h, seg_len, count_len, sch, p[0], p[1], p[2]);
+        uint8_t f = (uint8_t)txr::ixf_fingerprint_g(h, sch);
         for (int j = 0; j < 3; ++j)
             if (p[j] != stack_s[i])
                 f ^= fp[p[j]];
@@ -274,11 +274,17 @@ struct Builder
         size_t wide_extra = 0;
         for (size_t bb = bins; bb > 64 && max_n < (1u << 16); bb >>= 1)
             wide_extra += max_n / 24 + 16;
-        x.seg_len = txr::ixf_seg_len_for(max_n + max_n / 16 + 32 + wide_extra);
+        const txr::IxfScheme &sch = out->scheme;
+        // binary fuse filters come with their own size factor (>= 1.125): no extra headroom beyond the wide-index one
+        x.capacity = sch.slots == txr::kIxfSlotsFuse3 ? max_n + wide_extra + (max_n < 4096 ? max_n / 8 + 16 : 0) : max_n + max_n / 16 + 32 + wide_extra;
+        const txr::IxfGeometry geo = txr::ixf_geometry_for(sch, x.capacity);
+        x.seg_len = geo.seg_len;
+        x.rows = geo.rows;
+        x.count_len = geo.count_len;
         x.seed = 13572355802537770549ULL; // default seed of the prototype (xorfilter.hpp:153)
         x.next = next;
         x.ub = ubv;
-        const size_t slots = 3 * x.seg_len;
+        const size_t slots = x.rows;
         x.data.assign(slots * x.tbins, 0);
         std::vector<uint8_t> cols(slots * bins); // bin-major scratch: cols[b * slots + slot]
         while (true)
@@ -293,8 +299,8 @@ struct Builder
                 {
                     if (failed)
                         continue;
-                    if (!peel_bin(kptr[b], kn[b], x.seed, (uint32_t)x.seg_len, cols.data() + (size_t)b * slots, cnt, xr, queue, stack_h,
-                                  stack_s))
+                    if (!peel_bin(kptr[b], kn[b], x.seed, sch, (uint32_t)x.seg_len, (uint32_t)x.count_len, slots,
+                                  cols.data() + (size_t)b * slots, cnt, xr, queue, stack_h, stack_s))
                     {
 #pragma omp atomic write
                         failed = 1;
@@ -450,8 +456,13 @@ void txs_sort_unique_many(uint64_t *const *keys, uint64_t *counts, uint64_t n_ub
     }
 }
 
+void *txs_hixf_build3(const uint64_t *const *ub_hashes, const uint64_t *ub_n, uint64_t n_ub, uint32_t t_max, uint32_t t_max_lower,
+                      uint64_t seed, int threads, const uint32_t *scheme5);
 void *txs_hixf_build2(const uint64_t *const *ub_hashes, const uint64_t *ub_n, uint64_t n_ub, uint32_t t_max, uint32_t t_max_lower,
-                      uint64_t seed, int threads);
+                      uint64_t seed, int threads)
+{
+    return txs_hixf_build3(ub_hashes, ub_n, n_ub, t_max, t_max_lower, seed, threads, nullptr);
+}
 void *txs_hixf_build(const uint64_t *const *ub_hashes, const uint64_t *ub_n, uint64_t n_ub, uint32_t t_max, uint64_t seed,
                      int threads)
 {
@@ -460,8 +471,9 @@ void *txs_hixf_build(const uint64_t *const *ub_hashes, const uint64_t *ub_n, uin
 
 // t_max_lower != 0: the IXFs below the root get that bin budget instead of t_max (GTDB-shaped test/bench indexes: a
 // 4096-bin root over narrow lower levels, several levels deep without needing millions of user bins)
-void *txs_hixf_build2(const uint64_t *const *ub_hashes, const uint64_t *ub_n, uint64_t n_ub, uint32_t t_max, uint32_t t_max_lower,
-                      uint64_t seed, int threads)
+// scheme5 (may be null = the prototype's arithmetic): {slots, mix, fingerprint, rot1, rot2} of txr_ixf_scheme / txr::IxfScheme
+void *txs_hixf_build3(const uint64_t *const *ub_hashes, const uint64_t *ub_n, uint64_t n_ub, uint32_t t_max, uint32_t t_max_lower,
+                      uint64_t seed, int threads, const uint32_t *scheme5)
 {
 #ifdef _OPENMP
     if (threads > 0)
@@ -471,6 +483,17 @@ void *txs_hixf_build2(const uint64_t *const *ub_hashes, const uint64_t *ub_n, ui
         return nullptr;
     auto h = std::make_unique<Hixf>();
     h->n_user_bins = n_ub;
+    if (scheme5)
+    {
+        h->scheme = txr::IxfScheme{scheme5[0], scheme5[1], scheme5[2], scheme5[3], scheme5[4]};
+        if (h->scheme.rot1 == 0 && h->scheme.rot2 == 0)
+        {
+            h->scheme.rot1 = 21;
+            h->scheme.rot2 = 42;
+        }
+        if (!txr::ixf_scheme_valid(h->scheme))
+            return nullptr;
+    }
     std::vector<uint32_t> ubs(n_ub);
     std::iota(ubs.begin(), ubs.end(), 0u);
     std::stable_sort(ubs.begin(), ubs.end(), [&](uint32_t a, uint32_t b) { return ub_n[a] > ub_n[b]; });
@@ -484,6 +507,8 @@ void *txs_hixf_build2(const uint64_t *const *ub_hashes, const uint64_t *ub_n, ui
         h->bins.push_back(x.bins);
         h->tbins.push_back(x.tbins);
         h->seg_len.push_back(x.seg_len);
+        h->rows.push_back(x.rows);
+        h->capacity.push_back(x.capacity);
         h->data.push_back(x.data.data());
         h->next.insert(h->next.end(), x.next.begin(), x.next.end());
         h->ub.insert(h->ub.end(), x.ub.begin(), x.ub.end());
@@ -495,6 +520,8 @@ void *txs_hixf_build2(const uint64_t *const *ub_hashes, const uint64_t *ub_n, ui
 void txs_hixf_free(void *p) { delete static_cast<Hixf *>(p); }
 uint64_t txs_hixf_n_ixf(void *p) { return static_cast<Hixf *>(p)->ixf.size(); }
 uint64_t txs_hixf_reseeds(void *p) { return static_cast<Hixf *>(p)->reseeds; }
+const uint64_t *txs_hixf_rows(void *p) { return static_cast<Hixf *>(p)->rows.data(); }
+const uint64_t *txs_hixf_capacity(void *p) { return static_cast<Hixf *>(p)->capacity.data(); } // the max_elems an IXF was sized for
 void txs_hixf_arrays(void *p, const uint64_t **seed, const uint64_t **bins, const uint64_t **tbins, const uint64_t **seg_len,
                      const uint8_t *const **data, const uint64_t **bin_off, const int64_t **next, const int64_t **ub)
 {

@@ -41,9 +41,20 @@ def tlib():
     T.txs_hixf_arrays.restype = None
     T.txs_last_error.restype = C.c_char_p
     T.txs_hixf_write.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint16,
-                                 C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp]
+                                 C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     T.txs_hixf_open.argtypes = [C.c_char_p, C.c_char_p]
     T.txs_hixf_open.restype = vp
+    T.txs_hixf_open2.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    T.txs_hixf_open2.restype = vp
+    T.txs_hixf_open_note.restype = C.c_char_p
+    T.txs_hixf_ixf_rows.argtypes = [vp, C.c_uint64]
+    T.txs_hixf_ixf_rows.restype = C.c_uint64
+    T.txs_hixf_build3.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, vp]
+    T.txs_hixf_build3.restype = vp
+    T.txs_hixf_rows.argtypes = [vp]
+    T.txs_hixf_rows.restype = vp
+    T.txs_hixf_capacity.argtypes = [vp]
+    T.txs_hixf_capacity.restype = vp
     T.txs_hixf_close.argtypes = [vp]
     T.txs_hixf_close.restype = None
     T.txs_hixf_info.argtypes = [vp, vp]
@@ -92,7 +103,8 @@ class BuiltHixf:
     """An HIXF built by the CPU tooling; exposes the plain arrays every consumer takes."""
 
     def __init__(self, ub_hashes, t_max: int = 64, seed: int = 1, threads: int = 0, inplace: bool = False,
-                 t_max_lower: int = 0) -> None:
+                 t_max_lower: int = 0, scheme=None) -> None:
+        """scheme: None (the prototype's arithmetic) or (slots, mix, fingerprint, rot1, rot2) as in txr_ixf_scheme"""
         # sorted distinct key sets (in place on private copies -- or on the caller's arrays with inplace=True, which
         # halves the footprint of a multi-GB build -- parallel over user bins)
         if inplace:
@@ -106,7 +118,9 @@ class BuiltHixf:
         tlib().txs_sort_unique_many(ptrs, cnt.ctypes.data, n, threads)
         self._ub = [a[: int(c)] for a, c in zip(self._ub, cnt)]
         self.n_keys = int(cnt.sum())
-        self._h = tlib().txs_hixf_build2(ptrs, cnt.ctypes.data, n, t_max, t_max_lower, seed, threads)
+        self.scheme = None if scheme is None else tuple(int(v) for v in scheme)
+        sch = None if scheme is None else np.array(self.scheme, dtype=np.uint32)
+        self._h = tlib().txs_hixf_build3(ptrs, cnt.ctypes.data, n, t_max, t_max_lower, seed, threads, None if sch is None else sch.ctypes.data)
         if not self._h:
             raise RuntimeError("txs_hixf_build failed")
         self.n_user_bins = n
@@ -123,6 +137,8 @@ class BuiltHixf:
         self.bins = arr(outs[1], k, C.c_uint64, np.uint64)
         self.tbins = arr(outs[2], k, C.c_uint64, np.uint64)
         self.seg_len = arr(outs[3], k, C.c_uint64, np.uint64)
+        self.rows = arr(T.txs_hixf_rows(self._h), k, C.c_uint64, np.uint64)
+        self.capacity = arr(T.txs_hixf_capacity(self._h), k, C.c_uint64, np.uint64)
         dptr = np.ctypeslib.as_array(C.cast(outs[4], C.POINTER(C.c_uint64)), (k,)).copy()
         self.bin_off = arr(outs[5], k + 1, C.c_uint64, np.uint64)
         nb = int(self.bin_off[-1])
@@ -131,7 +147,7 @@ class BuiltHixf:
         # zero-copy views of the fingerprint arrays (owned by the native object)
         self.data = []
         for i in range(k):
-            size = 3 * int(self.seg_len[i]) * int(self.tbins[i])
+            size = int(self.rows[i]) * int(self.tbins[i])
             buf = (C.c_uint8 * size).from_address(int(dptr[i]))
             self.data.append(np.frombuffer(buf, dtype=np.uint8))
 
@@ -171,11 +187,14 @@ def write_hixf(path, hx, *, k, s, t, use_syncmer=True, window_size=20, scaling=1
     arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in (hx.seed, hx.bins, hx.tbins, hx.seg_len, hx.bin_off)]
     nxt = np.ascontiguousarray(hx.next_ixf_id, dtype=np.int64)
     ub = np.ascontiguousarray(hx.bin_to_ub, dtype=np.int64)
+    rows = np.ascontiguousarray(hx.rows, dtype=np.uint64) if getattr(hx, "rows", None) is not None else None
+    cap = np.ascontiguousarray(hx.capacity, dtype=np.uint64) if getattr(hx, "capacity", None) is not None else None
     rc = tlib().txs_hixf_write(str(path).encode(), record_spec.encode(), window_size, k, s, t, int(use_syncmer), scaling, len(data),
                                arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data, dptr,
                                arrs[4].ctypes.data, nxt.ctypes.data, ub.ctypes.data, n_ub, names, len(species),
                                cols["organism_name"][0], cols["accession_id"][0], cols["taxid"][0], cols["taxnames_string"][0],
-                               cols["taxid_string"][0], sp_ub.ctypes.data, sp_len.ctypes.data)
+                               cols["taxid_string"][0], sp_ub.ctypes.data, sp_len.ctypes.data,
+                               rows.ctypes.data if rows is not None else None, cap.ctypes.data if cap is not None else None)
     if rc != 0:
         raise RuntimeError(tlib().txs_last_error().decode())
 
@@ -190,24 +209,27 @@ def default_species(n_ub):
 class HixfFile:
     """A `.hixf` file opened with the library's reader (mmap); exposes the same arrays as BuiltHixf."""
 
-    def __init__(self, path, record_spec=""):
+    def __init__(self, path, record_spec="", scheme=""):
         T = tlib()
-        self._h = T.txs_hixf_open(str(path).encode(), record_spec.encode())
+        self._h = T.txs_hixf_open2(str(path).encode(), record_spec.encode(), scheme.encode())
         if not self._h:
             raise RuntimeError(T.txs_last_error().decode())
         self.record_spec = T.txs_last_error().decode()
+        self.note = T.txs_hixf_open_note().decode()
         info = np.zeros(14, dtype=np.uint64)
         T.txs_hixf_info(self._h, info.ctypes.data)
         (self.version, self.window_size, self.shape_size, self.shape_bits, self.k, self.s, self.t, self.parts, self.use_syncmer,
          self.scaling, self.compressed, n_ixf, self.n_user_bins, self.n_species) = [int(x) for x in info]
-        self.seed, self.bins, self.tbins, self.seg_len = (np.zeros(n_ixf, np.uint64) for _ in range(4))
+        self.seed, self.bins, self.tbins, self.seg_len, self.rows = (np.zeros(n_ixf, np.uint64) for _ in range(5))
         self.data, nxt, ub, off = [], [], [], [0]
         for i in range(n_ixf):
             sc = [C.c_uint64() for _ in range(4)]
             ptr = [C.c_void_p() for _ in range(3)]
             T.txs_hixf_ixf(self._h, i, *[C.byref(x) for x in sc], *[C.byref(x) for x in ptr])
             self.seed[i], self.bins[i], self.tbins[i], self.seg_len[i] = [x.value for x in sc]
-            size = 3 * sc[3].value * sc[2].value
+            rows_i = int(T.txs_hixf_ixf_rows(self._h, i))
+            self.rows[i] = rows_i
+            size = rows_i * sc[2].value
             self.data.append(np.frombuffer((C.c_uint8 * size).from_address(ptr[0].value), dtype=np.uint8))
             nb = sc[1].value
             nxt.append(np.ctypeslib.as_array(C.cast(ptr[1], C.POINTER(C.c_int64)), (nb,)).copy())

@@ -28,7 +28,7 @@ class Dataset:
 
 
 def make_dataset(oracle, *, n_genomes=24, genome_len=60_000, k=22, s=12, t=None, use_syncmer=True, t_max=8,
-                 seed=1000, size_jitter=True, scaling=1, window_size=None) -> Dataset:
+                 seed=1000, size_jitter=True, scaling=1, window_size=None, scheme=None) -> Dataset:
     rng = np.random.default_rng(seed)
     lens = [int(genome_len * (0.5 + rng.random())) if size_jitter else genome_len for _ in range(n_genomes)]
     genomes = [tools.genome(seed + g, lens[g]) for g in range(n_genomes)]
@@ -46,14 +46,15 @@ def make_dataset(oracle, *, n_genomes=24, genome_len=60_000, k=22, s=12, t=None,
         if scaling > 1:
             h = np.array([x for x in h.tolist() if oracle.scaling_keep(x, scaling)], dtype=np.uint64)
         ub.append(h)
-    hx = tools.BuiltHixf(ub, t_max=t_max, seed=seed)
-    arrays = HixfArrays(hx.seed, hx.bins, hx.tbins, hx.seg_len, hx.data, hx.bin_off, hx.next_ixf_id, hx.bin_to_ub)
+    hx = tools.BuiltHixf(ub, t_max=t_max, seed=seed, scheme=scheme)
+    arrays = HixfArrays(hx.seed, hx.bins, hx.tbins, hx.seg_len, hx.data, hx.bin_off, hx.next_ixf_id, hx.bin_to_ub, hx.rows)
     return Dataset(k, s, t, use_syncmer, genomes, lens, hx, arrays)
 
 
 def upload(ctx, ds: Dataset) -> None:
     h = ds.hixf
-    ctx.upload_index(h.seed, h.bins, h.tbins, h.seg_len, h.data, h.bin_off, h.next_ixf_id, h.bin_to_ub, h.n_user_bins)
+    ctx.upload_index(h.seed, h.bins, h.tbins, h.seg_len, h.data, h.bin_off, h.next_ixf_id, h.bin_to_ub, h.n_user_bins,
+                     rows=getattr(h, "rows", None), scheme=getattr(h, "scheme", None))
 
 
 def make_reads(ds: Dataset, lengths, err=0.05, seed=42) -> capi.PackedReads:

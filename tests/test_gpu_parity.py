@@ -421,6 +421,47 @@ def test_hash_user_bins_build_side(monkeypatch, oracle, mode):
         c.close()
 
 
+@pytest.mark.parametrize("scheme", [(1, 0, 0, 0, 0), (0, 1, 1, 13, 37), (1, 1, 2, 0, 0)])
+@pytest.mark.parametrize("t_max", [16, 1024])
+def test_ixf_scheme_variants(oracle, scheme, t_max):
+    """the probe arithmetic is a descriptor chosen at txr_index_upload (the SeqAn3 fork that defines it is absent): binary-fuse
+    slots and the seed-mix / fingerprint / rotation variants through the small and the wide kernels, bulk_count and the
+    whole search, against the oracle's independently written twin switched to the same scheme; bin-major host arrays too"""
+    c = capi.Context(0)
+    try:
+        oracle.set_ixf_scheme(scheme)
+        n_genomes = 60 if t_max == 16 else 1100
+        ds = H.make_dataset(oracle, n_genomes=n_genomes, genome_len=30_000 if t_max == 16 else 2_000, t_max=t_max, scheme=scheme,
+                            seed=4000 + t_max)
+        H.upload(c, ds)
+        oh = oracle.make_hixf(ds.arrays)
+        rng = np.random.default_rng(9)
+        values = np.concatenate([ds.hixf._ub[3][:400], ds.hixf._ub[11][:300], rng.integers(0, 2**63, 1500, dtype=np.uint64)])
+        for x in range(min(ds.hixf.n_ixf, 4)):
+            assert np.array_equal(c.ixf_bulk_count(x, values, int(ds.hixf.bins[x])), oracle.ixf_bulk_count(oh, x, values)), x
+        reads = H.make_reads(ds, rng.integers(300, 1900 if t_max > 16 else 9000, 150), err=0.03)
+        res, ora = _search_case(c, oracle, ds, reads, error_rate=0.1)
+        assert int(res.hit_begin[-1]) > 30
+        # the same index handed over bin-major (one plain filter after the other): re-laid-out on upload
+        hx = ds.hixf
+        data = [np.ascontiguousarray(hx.data[i].reshape(int(hx.rows[i]), int(hx.tbins[i]))[:, : int(hx.bins[i])].T).reshape(-1)
+                for i in range(hx.n_ixf)]
+        c.upload_index(hx.seed, hx.bins, hx.bins, hx.seg_len, data, hx.bin_off, hx.next_ixf_id, hx.bin_to_ub, hx.n_user_bins,
+                       rows=hx.rows, scheme=scheme, layout=1)
+        c.set_params(k=ds.k, s=ds.s, t=ds.t, use_syncmer=True, window_size=20, error_rate=0.1)
+        H.assert_same_search(c.search(reads), ora, reads.n)
+        # the wrong scheme on the same arrays: rejected by the geometry check or simply different counts, never a crash
+        wrong = (1 - scheme[0], scheme[1], scheme[2], 21, 42)
+        try:
+            c.upload_index(hx.seed, hx.bins, hx.tbins, hx.seg_len, hx.data, hx.bin_off, hx.next_ixf_id, hx.bin_to_ub, hx.n_user_bins,
+                           rows=hx.rows, scheme=wrong)
+        except capi.TaxorError as e:
+            assert "geometry" in str(e)
+    finally:
+        oracle.set_ixf_scheme(None)
+        c.close()
+
+
 def test_index_clone_and_staged_upload(monkeypatch, oracle):
     """txr_index_clone (device-to-device replica; second GPU when there is one, else a second context on GPU 0) and the
     serial upload path (TXR_UPLOAD_THREADS=1) answer exactly like the staged multi-threaded upload; rows that need padding
