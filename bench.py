@@ -346,10 +346,27 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # CPU arm (oracle port)
 # ----------------------------------------------------------------------------------------------------------
-def cpu_run(args, ix, pin_words, off, ln, n_sample, threads):
-    """Times oracle.search_batch (restated CPU path, OpenMP over reads) on the first n_sample reads."""
-    from oracle.oracle import HixfArrays, Oracle
-    o = Oracle()
+_ORACLES = {}
+
+
+def cpu_oracle():
+    """The CPU arm's library: the oracle restatement compiled ON THIS BOX with -O3 -march=native (oracle/Makefile `native`;
+    BASELINE.md section 2).  Falls back to the portable test build if the box has no compiler."""
+    if "o" not in _ORACLES:
+        from oracle.oracle import Oracle
+        try:
+            _ORACLES["o"], _ORACLES["build"] = Oracle(native=True), "-O3 -march=native, built on this box"
+        except Exception as e:                                     # no compiler on the box: say so in the line
+            _ORACLES["o"], _ORACLES["build"] = Oracle(), f"portable -march=x86-64-v2 build (native build failed: {type(e).__name__})"
+    return _ORACLES["o"]
+
+
+def cpu_run(args, ix, pin_words, off, ln, n_sample, threads, tuned=False):
+    """Times oracle.search_batch (restated CPU path, OpenMP over reads) on the first n_sample reads.  tuned: bulk_count with
+    software prefetch and 64-bin SIMD compares (same results) instead of the plain restatement of the reference's loop."""
+    from oracle.oracle import HixfArrays
+    o = cpu_oracle()
+    o.set_tuned(tuned)
     arrays = HixfArrays(np.ascontiguousarray(ix.seed), np.ascontiguousarray(ix.bins), np.ascontiguousarray(ix.tbins),
                         np.ascontiguousarray(ix.seg_len), [np.ascontiguousarray(x) for x in ix.data],
                         np.ascontiguousarray(ix.bin_off), np.ascontiguousarray(ix.next_ixf_id), np.ascontiguousarray(ix.bin_to_ub))
@@ -367,7 +384,63 @@ def cpu_run(args, ix, pin_words, off, ln, n_sample, threads):
                          error_rate=args.error_rate,
                          threads=threads, want_raw=False)
     dt = time.perf_counter() - t0
+    o.set_tuned(False)
     return at / dt / 1e6, dt, res
+
+
+def cpu_baseline_block(args, ix, pin, off_pin, len_pin, n_reads, cores, seconds):
+    """Both CPU variants on a bounded sample: `port` (the reference's loop restated) and `port_tuned` (prefetch + SIMD).  The
+    block's own value is the TUNED one -- the fair yardstick; returns (block, oracle answers for the sample, sample size)."""
+    n_s = min(n_reads, 1000)
+    v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores, tuned=True)
+    n_s = int(min(n_reads, max(200, n_s * seconds / max(dt, 1e-3))))
+    vt, dtt, ora = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores, tuned=True)
+    n_p = int(min(n_s, max(200, n_s * 0.5 * seconds / max(dtt * 3, 1e-3))))   # the plain port is slower: a shorter sample
+    vp, dtp, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_p, cores, tuned=False)
+    flags = cpu_oracle().lib.orc_build_flags()
+    block = {"value": vt, "unit": UNIT, "cores": cores, "kind": "port", "variant": "port_tuned",
+             "sample": f"first {n_s} of the {n_reads} reads, {dtt:.1f} s (restated CPU path, OpenMP over reads, bulk_count with software "
+                       f"prefetch + 64-bin SIMD compares; not the reference binary)",
+             "build": _ORACLES.get("build"), "simd": "avx512bw" if flags & 1 else "avx2" if flags & 2 else "scalar",
+             "variants": {"port_tuned": {"value": vt, "sample_reads": n_s, "seconds": dtt},
+                          "port": {"value": vp, "sample_reads": n_p, "seconds": dtp,
+                                   "note": "the reference's per-value loop restated as is (no prefetch, scalar compare)"}}}
+    return block, ora, n_s
+
+
+def random_access_block(stage, args, ix, gather):
+    """kernel #2 as random row reads per second: 3 per probed hash (per visited IXF), from the device counters of the timed region"""
+    if stage["query_ms"] <= 0:
+        return None
+    # query_bytes = sum Hp * (3 * tbins + 8): the probes of every IXF weigh in with their own row width; the access count
+    # is exact for the root-dominated workloads (one row width) and a lower bound otherwise
+    row = int(ix.tbins[0])
+    probes = stage["query_bytes"] / (3.0 * row + 8.0)
+    rate = 3.0 * probes / (stage["query_ms"] / 1e3) / 1e9
+    out = {"achieved_G_rows_per_s": rate, "row_bytes_root": row}
+    if gather:
+        ceil = gather["useful_GBps"] / row                                        # G rows/s of the pure gather at this width
+        out.update({"ceiling_G_rows_per_s": ceil, "frac": rate / ceil, "ceiling_source": gather["source"]})
+    return out
+
+
+def compare_with_oracle(g, ora, n_s):
+    """GPU answers (capi.SearchResult) for the first n_s reads against oracle.search_batch for the same reads."""
+    nh = int(g.hit_begin[n_s])
+    keep = g.keep[:nh]
+    kept_per_read = np.concatenate([[0], np.cumsum(keep)])[g.hit_begin[: n_s + 1].astype(np.int64)]
+    parity = {"reads": n_s,
+              "hash_count_mismatches": int(np.count_nonzero(g.hash_count[:n_s] != ora["hash_count"])),
+              "threshold_mismatches": int(np.count_nonzero(g.threshold[:n_s] != ora["threshold"])),
+              "hit_offsets_equal": bool(np.array_equal(kept_per_read.astype(np.uint64), ora["hit_off"])),
+              "hit_user_bins_equal": bool(np.array_equal(g.user_bin[:nh][keep], ora["ub"])),
+              "hit_counts_equal": bool(np.array_equal(g.count[:nh][keep], ora["cnt"])),
+              "reported_hits": int(len(ora["ub"]))}
+    parity["ok"] = (parity["hash_count_mismatches"] == 0 and parity["threshold_mismatches"] == 0 and parity["hit_offsets_equal"]
+                    and parity["hit_user_bins_equal"] and parity["hit_counts_equal"])
+    parity["mismatches"] = (parity["hash_count_mismatches"] + parity["threshold_mismatches"] + (not parity["hit_offsets_equal"])
+                            + (not parity["hit_user_bins_equal"]) + (not parity["hit_counts_equal"]))
+    return parity
 
 
 def main():
@@ -433,21 +506,29 @@ def main():
     # ---------------------------------------------------------------- reference arm (CPU)
     if reference:
         n_s = min(n_reads, 2000)
-        v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
+        v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores, tuned=True)
         # bounded sample per step: all warm-up + timed steps together stay within about two minutes
-        per_step = min(args.cpu_seconds, 120.0 / max(args.steps + args.warmup, 1))
+        per_step = min(args.cpu_seconds, 100.0 / max(args.steps + args.warmup, 1))
         n_s = int(min(n_reads, max(200, n_s * per_step / max(dt, 1e-3))))
         vals = []
         for i in range(args.warmup + args.steps):
-            v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
+            v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores, tuned=True)
             if i >= args.warmup:
                 vals.append((v, dt))
         value = float(np.mean([x[0] for x in vals]))
+        n_p = max(200, n_s // 4)
+        v_plain, dt_plain, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_p, cores, tuned=False)
+        flags = cpu_oracle().lib.orc_build_flags()
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": float(np.mean([x[1] for x in vals]) * 1e3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload,
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"{n_s} of the {n_reads} reads per step (restated CPU path, OpenMP over reads; not the reference binary)"},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "variant": "port_tuned",
+                                 "sample": f"{n_s} of the {n_reads} reads per step (restated CPU path, OpenMP over reads, bulk_count with "
+                                           f"software prefetch + 64-bin SIMD compares; not the reference binary)",
+                                 "build": _ORACLES.get("build"), "simd": "avx512bw" if flags & 1 else "avx2" if flags & 2 else "scalar",
+                                 "variants": {"port_tuned": {"value": value, "sample_reads": n_s},
+                                              "port": {"value": v_plain, "sample_reads": n_p, "seconds": dt_plain,
+                                                       "note": "the reference's per-value loop restated as is (no prefetch, scalar compare)"}}},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -516,7 +597,44 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms.item())
     tm_e2e = ctx.timing()
-    gpu_result = capi.SearchResult(r) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None  # copy: the view dies with the next call
+    gpu_result = capi.SearchResult(r) if not args.no_cpu_baseline else None  # copy: the view dies with the next call
+
+    # per-rank view of the end-to-end step (the 8-GPU curve is bounded by the host side, not by the kernels): this rank's own
+    # step time, the H2D time its batches saw, and -- all ranks at once -- the pure pinned-host -> HBM copy rate of the
+    # same buffer, i.e. what the host's memory system gives N GPUs pulling 2.5 GB each at the same moment
+    e2e_own_ms = max(ev0.elapsed_time(ev1), 0.0) / args.steps
+    probe = torch.empty(pin.nbytes, dtype=torch.uint8, device="cuda")
+    hsrc = torch.frombuffer(memoryview(pin.array), dtype=torch.uint8)
+    direct = bool(hsrc.is_pinned())           # cudaHostAlloc'ed by the library: torch sees it as pinned and copies straight from it
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev2.record()
+        for _ in range(3):
+            probe.copy_(hsrc, non_blocking=True)
+        ev3.record()
+    barrier()
+    h2d_gbs = 3 * pin.nbytes / max(ev2.elapsed_time(ev3), 1e-3) / 1e6 if direct else float("nan")
+    del probe, hsrc
+    rank_stats = torch.tensor([e2e_own_ms, tm_e2e["h2d_ms"], h2d_gbs], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        allst = [torch.zeros_like(rank_stats) for _ in range(world)]
+        dist.all_gather(allst, rank_stats)
+        rank_stats_all = [[round(float(v), 2) for v in t.tolist()] for t in allst]
+    else:
+        rank_stats_all = [[round(float(v), 2) for v in rank_stats.tolist()]]
+
+    # answers checked on the hardware of EVERY rank: a bounded sample of this rank's own shard against the oracle
+    # (N > 1: a short sample per rank, mismatches summed over ranks; N == 1: the cpu_baseline sample below serves)
+    multi_parity = None
+    if world > 1 and not args.no_cpu_baseline:
+        n_chk = min(n_reads, 3000)
+        _, _, ora_chk = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_chk, max(1, cores // world), tuned=True)
+        bad = compare_with_oracle(gpu_result, ora_chk, n_chk)
+        t = torch.tensor([bad["mismatches"], n_chk, bad["reported_hits"]], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        multi_parity = {"reads": int(t[1].item()), "ranks": world, "mismatches": int(t[0].item()), "reported_hits": int(t[2].item()),
+                        "ok": int(t[0].item()) == 0, "note": "every rank compares the first reads of ITS shard with the CPU oracle"}
 
     total_bases = bases_per_step * world
     value = total_bases * args.steps / (resident_ms / 1e3) / 1e6
@@ -567,30 +685,17 @@ def main():
                 "bytes_note": "bytes of the probes actually issued (Hp*3*tbins + 8*Hp per visited IXF); probes saved by the exact "
                               "early exit are NOT counted",
                 "early_exit_skipped_hashes_per_step": stage["skipped_hashes"] / args.steps,
+                # rows narrower than two DRAM lines are bound by random ACCESSES per second, not by bytes (the .L2::64B variant of
+                # the gather microbenchmark moves half the bytes in the same time, profiles/r1_gather_bench2_ncu.txt): three row
+                # reads per probed hash, against the microbenchmark's rate for rows of this width
+                "random_access": random_access_block(stage, args, ix, gather),
                 "stage_ms_per_step": {"hash": stage["hash_ms"] / args.steps, "dedup": stage["dedup_ms"] / args.steps,
                                       "query": stage["query_ms"] / args.steps}}
-        cpu, parity = None, None
+        cpu, parity = None, multi_parity
         if world == 1 and not args.no_cpu_baseline:
-            n_s = min(n_reads, 1000)
-            v, dt, _ = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
-            n_s = int(min(n_reads, max(200, n_s * args.cpu_seconds / max(dt, 1e-3))))
-            v, dt, ora = cpu_run(args, ix, pin.array, off_pin.array, len_pin.array, n_s, cores)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"first {n_s} of the {n_reads} reads, {dt:.1f} s (restated CPU path with OpenMP over reads; not the reference binary)"}
+            cpu, ora, n_s = cpu_baseline_block(args, ix, pin, off_pin, len_pin, n_reads, cores, args.cpu_seconds)
             # parity at full size, for free: the oracle's answers for the CPU sample against the GPU's answers for the same reads
-            g = gpu_result
-            nh = int(g.hit_begin[n_s])
-            keep = g.keep[:nh]
-            kept_per_read = np.concatenate([[0], np.cumsum(keep)])[g.hit_begin[: n_s + 1].astype(np.int64)]
-            parity = {"reads": n_s,
-                      "hash_count_mismatches": int(np.count_nonzero(g.hash_count[:n_s] != ora["hash_count"])),
-                      "threshold_mismatches": int(np.count_nonzero(g.threshold[:n_s] != ora["threshold"])),
-                      "hit_offsets_equal": bool(np.array_equal(kept_per_read.astype(np.uint64), ora["hit_off"])),
-                      "hit_user_bins_equal": bool(np.array_equal(g.user_bin[:nh][keep], ora["ub"])),
-                      "hit_counts_equal": bool(np.array_equal(g.count[:nh][keep], ora["cnt"])),
-                      "reported_hits": int(len(ora["ub"]))}
-            parity["ok"] = (parity["hash_count_mismatches"] == 0 and parity["threshold_mismatches"] == 0 and parity["hit_offsets_equal"]
-                            and parity["hit_user_bins_equal"] and parity["hit_counts_equal"])
+            parity = compare_with_oracle(gpu_result, ora, n_s)
         line = {"metric": METRIC if args.use_syncmer else METRIC.replace("syncmer hash", "k-mer hash"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": workload,
@@ -599,7 +704,11 @@ def main():
                         "h2d_bytes_per_step": int(pin.nbytes + off_pin.nbytes + len_pin.nbytes + 8 * (n_reads + 1)),
                         "d2h_bytes_per_step": int(4 * n_reads + 12 * n_hits + 576 * (-(-n_reads // (args.batch_reads or 262144)) + 2)),
                         "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "hits_per_step": n_hits,
-                        "stage_ms_per_step_overlapped": {kk: tm_e2e[kk] for kk in ("h2d_ms", "hash_ms", "dedup_ms", "query_ms", "d2h_ms")}},
+                        "stage_ms_per_step_overlapped": {kk: tm_e2e[kk] for kk in ("h2d_ms", "hash_ms", "dedup_ms", "query_ms", "d2h_ms")},
+                        "per_rank": {"columns": ["e2e_ms_per_step", "h2d_ms_last_step", "concurrent_h2d_GBps"], "rows": rank_stats_all,
+                                     "note": "concurrent_h2d_GBps: all ranks copy their pinned read buffer to HBM at the same moment, nothing "
+                                             "else running -- the host-side ceiling of the e2e step at this N (bytes per step / this rate "
+                                             "is the time the copies need even when perfectly overlapped)"}},
                 "gpu_launches": int(stage["launches"]),
                 "roofline": roof, "cpu_baseline": cpu, "parity_at_scale": parity, "clocks": clocks,
                 "index_build": ix.info, "host_cores": cores}

@@ -67,10 +67,23 @@ class HixfArrays:
         return len(self.seed)
 
 
+NATIVE_SO = os.path.join(HERE, "liboracle_native.so")
+
+
+def build_native() -> str:
+    """`make native` on THIS machine (-O3 -march=native): the CPU-baseline build of bench.py.  Always rebuilt, so that a
+    library compiled on another CPU never travels here."""
+    subprocess.run(["make", "-C", HERE, "-B", "native"], check=True, capture_output=True)
+    return NATIVE_SO
+
+
 class Oracle:
-    def __init__(self) -> None:
+    def __init__(self, native: bool = False) -> None:
         build()
-        L = self.lib = C.CDLL(ORACLE_SO)
+        L = self.lib = C.CDLL(build_native() if native else ORACLE_SO)
+        L.orc_set_tuned.restype = None
+        L.orc_set_tuned.argtypes = [C.c_int]
+        L.orc_build_flags.restype = C.c_int
         L.orc_wyhash_u64.restype = C.c_uint64
         L.orc_wyhash_u64.argtypes = [C.c_uint64]
         L.orc_adjust_seed.restype = C.c_uint64
@@ -178,6 +191,10 @@ class Oracle:
         p = [C.c_uint64() for _ in range(3)]
         self.lib.orc_ixf_slots(key, seed, seg_len, C.byref(f), *[C.byref(x) for x in p])
         return f.value, p[0].value, p[1].value, p[2].value
+
+    def set_tuned(self, on: bool) -> None:
+        """prefetching / SIMD bulk_count (same results) -- the port_tuned CPU baseline"""
+        self.lib.orc_set_tuned(int(on))
 
     def set_ixf_scheme(self, scheme=None):
         """Switch the (unpinned) probe arithmetic: None = the prototype's, else (slots, mix, fingerprint, rot1, rot2).

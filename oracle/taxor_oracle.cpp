@@ -6,6 +6,9 @@
  */
 #include "taxor_oracle.h"
 #include "ixf_ref.h"
+#if defined(__AVX512BW__) || defined(__AVX2__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -431,10 +434,97 @@ extern "C" void orc_ixf_slots(uint64_t key, uint64_t seed, uint64_t seg_len,
     *p2 = ixfref_slot(h, 2, seg_len);
 }
 
+/* ---- "tuned" CPU baseline (bench.py cpu_baseline.port_tuned; not used by the parity tests) ----
+ * The same bulk_count, written the way a CPU implementation that cares would write it (the fork's agent is SIMD as well,
+ * SURVEY 2.1): the three row addresses of value i+D are computed and prefetched while value i is reduced, rows are compared
+ * 64 bins at a time (AVX-512BW when the build has it: xor, compare-equal against the broadcast fingerprint, byte counters
+ * bumped through the mask), byte counters spill into the u32 counts every 255 values.  Same results, fewer stalls. */
+static int g_tuned = 0;
+extern "C" void orc_set_tuned(int on) { g_tuned = on; }
+extern "C" int orc_build_flags(void)
+{
+    int f = 0;
+#if defined(__AVX512BW__)
+    f |= 1;
+#endif
+#if defined(__AVX2__)
+    f |= 2;
+#endif
+    return f;
+}
+
+static void bulk_count_tuned(const orc_ixf *x, const uint64_t *values, uint64_t n, uint32_t *counts)
+{
+    constexpr int D = 12; /* prefetch distance in values: ~36 lines in flight per thread */
+    const uint64_t rows = x->rows ? x->rows : 3 * x->seg_len;
+    const uint64_t tb = x->tbins, chunks = tb / 64; /* tbins is a multiple of 64 (HBM/IXF row padding) */
+    struct Slot
+    {
+        const uint8_t *r0, *r1, *r2;
+        uint8_t f;
+    } ring[D];
+    std::vector<uint8_t> acc(tb, 0);
+    std::memset(counts, 0, sizeof(uint32_t) * x->bins);
+    auto flush = [&]() {
+        for (uint64_t b = 0; b < x->bins; ++b)
+            counts[b] += acc[b];
+        std::memset(acc.data(), 0, tb);
+    };
+    uint32_t since_flush = 0;
+    for (uint64_t i = 0; i < n + D; ++i)
+    {
+        if (i >= D)
+        {
+            const Slot &s = ring[i % D];
+#if defined(__AVX512BW__)
+            const __m512i fv = _mm512_set1_epi8((char)s.f);
+            for (uint64_t c = 0; c < chunks; ++c)
+            {
+                const __m512i v = _mm512_xor_si512(_mm512_xor_si512(_mm512_loadu_si512(s.r0 + 64 * c), _mm512_loadu_si512(s.r1 + 64 * c)),
+                                                   _mm512_loadu_si512(s.r2 + 64 * c));
+                const __mmask64 m = _mm512_cmpeq_epi8_mask(v, fv);
+                __m512i a = _mm512_loadu_si512(acc.data() + 64 * c);
+                a = _mm512_sub_epi8(a, _mm512_movm_epi8(m)); /* mask bytes are 0xFF: subtracting adds one */
+                _mm512_storeu_si512(acc.data() + 64 * c, a);
+            }
+#else
+            for (uint64_t b = 0; b < tb; ++b)
+                acc[b] += (uint8_t)((uint8_t)(s.r0[b] ^ s.r1[b] ^ s.r2[b]) == s.f);
+#endif
+            if (++since_flush == 255)
+            {
+                flush();
+                since_flush = 0;
+            }
+        }
+        if (i < n)
+        {
+            const uint64_t h = ixfref_mix_s(&g_scheme, values[i], x->seed);
+            Slot &s = ring[i % D];
+            s.f = ixfref_fingerprint_s(&g_scheme, h);
+            s.r0 = x->data + ixfref_slot_s(&g_scheme, h, 0, x->seg_len, rows) * tb;
+            s.r1 = x->data + ixfref_slot_s(&g_scheme, h, 1, x->seg_len, rows) * tb;
+            s.r2 = x->data + ixfref_slot_s(&g_scheme, h, 2, x->seg_len, rows) * tb;
+            for (uint64_t c = 0; c < chunks && c < 4; ++c) /* the first lines of a wide row; the hardware streams the rest */
+            {
+                __builtin_prefetch(s.r0 + 64 * c, 0, 0);
+                __builtin_prefetch(s.r1 + 64 * c, 0, 0);
+                __builtin_prefetch(s.r2 + 64 * c, 0, 0);
+            }
+        }
+    }
+    flush();
+}
+
 /* seqan3::interleaved_xor_filter<uint8_t>::counting_agent<uint32_t>().bulk_count (call site hixf.hpp:307-309).
  * PARITY UNPINNED (see ixf_ref.h): per value, fingerprint == xor of the three interleaved rows -> bin hit. */
 extern "C" void orc_ixf_bulk_count(const orc_ixf *x, const uint64_t *values, uint64_t n, uint32_t *counts)
 {
+    if (g_tuned && x->tbins % 64 == 0)
+    {
+        bulk_count_tuned(x, values, n, counts);
+        return;
+    }
     std::memset(counts, 0, sizeof(uint32_t) * x->bins);
     for (uint64_t v = 0; v < n; ++v)
     {

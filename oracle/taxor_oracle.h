@@ -84,6 +84,9 @@ typedef struct {
 /* The probe arithmetic is a hypothesis (see ixf_ref.h), so the oracle can be switched between candidate schemes:
  * scheme5 = {slots, mix, fingerprint, rot1, rot2}; NULL restores the prototype's.  Process-global (test infrastructure). */
 void orc_set_ixf_scheme(const uint32_t *scheme5);
+/* bulk_count with software prefetch + 64-bin SIMD compares (same results; the "port_tuned" CPU baseline of bench.py) */
+void orc_set_tuned(int on);
+int  orc_build_flags(void);   /* bit 0: compiled with AVX-512BW, bit 1: AVX2 */
 
 typedef struct {
     uint64_t        n_ixf;

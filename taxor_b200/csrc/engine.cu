@@ -280,6 +280,7 @@ struct txr_ctx
     bool early_exit{true};     // exact early exit of kernel #2 (TXR_EARLY_EXIT=0 disables)
     bool l2_hints{true};       // L2 eviction-priority plan for small child IXFs (TXR_L2_HINTS=0 disables)
     bool fuse_dedup{true};     // distinct set built inside the syncmer kernel (TXR_FUSE_DEDUP=0: separate dedup kernel)
+    uint32_t query_unroll{0};  // TXR_QUERY_UNROLL: probe steps in flight per warp (experiments with fewer probe CTAs per SM)
     uint32_t fuse_max_keys{kWarpMaxKeys}; // TXR_FUSE_MAX_KEYS lowers it (tests: forces the hand-over to the CTA-per-read kernel)
     int root_partition{0};     // root level grouped by segment-0 slot: 0 off (default: measured slower), 1 auto, 2 always (TXR_ROOT_PARTITION)
     bool per_read_thr{false};  // FracMinHash model: the threshold depends on hash_count AND the read length
@@ -647,6 +648,7 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
     q.stat_items = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 2);
     q.stat_skipped = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 4);
     q.early_exit = c->early_exit;
+    q.unroll = c->query_unroll;
     q.generic = ix.generic;
     q.scheme = ix.scheme;
     q.smf = c->smf_query;
@@ -1111,6 +1113,8 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->early_exit = atoi(e) != 0;
     if (const char *e = getenv("TXR_L2_HINTS"))
         c->l2_hints = atoi(e) != 0;
+    if (const char *e = getenv("TXR_QUERY_UNROLL"))
+        c->query_unroll = (uint32_t)atoi(e);
     if (const char *e = getenv("TXR_FUSE_DEDUP"))
         c->fuse_dedup = atoi(e) != 0;
     if (const char *e = getenv("TXR_FUSE_MAX_KEYS"))

@@ -293,13 +293,13 @@ __global__ void __launch_bounds__(32 * kHashWarps, 4) syncmer_kernel(HashArgs a)
     __shared__ uint32_t s_sel[kHashWarps][32];      // per-lane selection masks written by the sequential replay
     // fused distinct set: kWarpSlots u32 per warp (dynamic: with it the CTA exceeds the 48 KB static limit).  A slot is
     // 21 tag bits of the key | 11 bits: 0 empty, 1..kWarpMaxKeys = 1 + position of the key in the read's output list,
-    // kPendingBase + lane = claimed in the current round of 32 keys by that lane (its key is still in a register).
+    // kPendingBase + n = claimed by key n of the group of keys being inserted (staged in shared memory until it settles).
     extern __shared__ uint32_t s_tab_dyn[];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     volatile uint32_t *tab = s_tab_dyn + (a.fuse_dedup ? wib * kWarpSlots : 0);
-    constexpr uint32_t kPendingBase = 2016;
-    static_assert(kWarpMaxKeys < kPendingBase && kPendingBase + 31 < 2048, "slot payload ranges overlap");
+    constexpr uint32_t kPendingBase = 1920; // + the key's number inside its group of 128
+    static_assert(kWarpMaxKeys < kPendingBase && kPendingBase + 127 < 2048, "slot payload ranges overlap");
     while (true)
     {
         uint32_t r = 0;
@@ -503,60 +503,98 @@ __global__ void __launch_bounds__(32 * kHashWarps, 4) syncmer_kernel(HashArgs a)
             }
             __syncwarp();
             emitted += total;
-            for (uint32_t it0 = 0; it0 < total; it0 += 32)
+            // Keys are handled kGroup = 32 * KB at a time (a typical tile of a random read selects ~93 windows: one group): all
+            // KB hashes of a lane are computed first -- their packed-word loads overlap -- and the claim rounds then work on
+            // KB independent table slots per lane.  (A version that inserted 32 keys at a time exposed one load latency and two
+            // or three warp-synchronous rounds per chunk and lost 12 ms per 1 M reads against the separate dedup kernel.)
+            constexpr int KB = 4;
+            volatile uint64_t *s_keys = reinterpret_cast<volatile uint64_t *>(s_v[wib] + 512); // 128 keys; s_pos ends below byte 2048
+            for (uint32_t it0 = 0; it0 < total; it0 += 32 * KB)
             {
-                const uint32_t it = it0 + lane;
-                const bool live = it < total;
-                const uint64_t h = live ? wyhash_u64(canon_mer_at(w, tile + s_pos[it], K)) : 0;
-                if (set_mode && cursor + 32 > a.fuse_max_keys)
+                uint64_t h[KB];
+                bool live[KB];
+#pragma unroll
+                for (int j = 0; j < KB; ++j)
+                {
+                    const uint32_t it = it0 + 32 * j + lane;
+                    live[j] = it < total;
+                    h[j] = live[j] ? wyhash_u64(canon_mer_at(w, tile + s_pos[live[j] ? it : 0], K)) : 0;
+                }
+                const uint32_t group = min((uint32_t)(32 * KB), total - it0);
+                if (set_mode && cursor + group > a.fuse_max_keys)
                     set_mode = false; // warp-uniform: the rest of the read is written raw
                 if (!set_mode)
                 {
-                    if (live && cursor + (it - it0) < cap)
-                        out[cursor + (it - it0)] = h;
-                    cursor += min(32u, total - it0);
+#pragma unroll
+                    for (int j = 0; j < KB; ++j)
+                        if (live[j] && cursor + 32 * j + lane < cap)
+                            out[cursor + 32 * j + lane] = h[j];
+                    cursor += group;
                     continue;
                 }
-                // ---- the ankerl::set insert of syncmer.cpp:145 for 32 keys at a time ----
+                // ---- the ankerl::set insert of syncmer.cpp:145 for one group of keys ----
                 // FracMin first (taxor_search.cpp:223-233 filters the set; filtering before the insert gives the same set)
-                bool pending = live && scaling_keep(h, a.scaling, a.scaling_limit);
-                bool first = false;
-                uint32_t slot = (uint32_t)(h ^ (h >> 29)) & (kWarpSlots - 1);
-                const uint32_t tag = (uint32_t)(h >> 43) << 11;
-                const uint32_t mine = tag | (kPendingBase + (uint32_t)lane);
-                while (__any_sync(0xffffffffu, pending))
+                bool pending[KB], first[KB];
+                uint32_t slot[KB], mine[KB];
+                __syncwarp(); // the previous group's readers of s_keys are done
+#pragma unroll
+                for (int j = 0; j < KB; ++j)
                 {
-                    if (pending && tab[slot] == 0)
-                        tab[slot] = mine; // racy on purpose: lanes of this round that share the slot, one store lands
+                    s_keys[32 * j + lane] = h[j];
+                    pending[j] = live[j] && scaling_keep(h[j], a.scaling, a.scaling_limit);
+                    first[j] = false;
+                    slot[j] = (uint32_t)(h[j] ^ (h[j] >> 29)) & (kWarpSlots - 1);
+                    mine[j] = ((uint32_t)(h[j] >> 43) << 11) | (kPendingBase + 32u * j + (uint32_t)lane);
+                }
+                __syncwarp();
+                while (true)
+                {
+                    bool any = false;
+#pragma unroll
+                    for (int j = 0; j < KB; ++j)
+                        any |= pending[j];
+                    if (!__any_sync(0xffffffffu, any))
+                        break;
+#pragma unroll
+                    for (int j = 0; j < KB; ++j)
+                        if (pending[j] && tab[slot[j]] == 0)
+                            tab[slot[j]] = mine[j]; // racy on purpose: lanes of this round that share the slot, one store lands
                     __syncwarp();
-                    const uint32_t now = pending ? tab[slot] : 0u;
-                    const uint32_t low = now & 2047u;
-                    const bool same_tag = pending && now != mine && low != 0 && (now & ~2047u) == tag;
-                    // the key behind an equal tag: a lane of this round (register, by shuffle) or an earlier key (output list)
-                    const uint64_t theirs = __shfl_sync(0xffffffffu, h, same_tag && low >= kPendingBase ? (int)(low - kPendingBase) : lane);
-                    if (pending)
+#pragma unroll
+                    for (int j = 0; j < KB; ++j)
                     {
-                        if (now == mine)
+                        if (!pending[j])
+                            continue;
+                        const uint32_t now = tab[slot[j]];
+                        const uint32_t low = now & 2047u;
+                        if (now == mine[j])
                         {
-                            first = true;
-                            pending = false;
+                            first[j] = true;
+                            pending[j] = false;
                         }
-                        else if (same_tag && (low >= kPendingBase ? theirs : __ldcg(out + (low - 1))) == h)
-                            pending = false; // an earlier (or concurrent) occurrence owns this key
+                        // an equal tag: compare the keys -- a key of this group (staged in shared memory) or an earlier one
+                        // (already in the output list)
+                        else if (low != 0 && (now & ~2047u) == (mine[j] & ~2047u) &&
+                                 (low >= kPendingBase ? s_keys[low - kPendingBase] : __ldcg(out + (low - 1))) == h[j])
+                            pending[j] = false; // an earlier (or concurrent) occurrence owns this key
                         else
-                            slot = (slot + 1) & (kWarpSlots - 1);
+                            slot[j] = (slot[j] + 1) & (kWarpSlots - 1);
                     }
                     __syncwarp();
                 }
-                const uint32_t bal = __ballot_sync(0xffffffffu, first);
-                if (first)
+#pragma unroll
+                for (int j = 0; j < KB; ++j)
                 {
-                    const uint32_t idx = (uint32_t)cursor + __popc(bal & ((1u << lane) - 1u));
-                    tab[slot] = tag | (idx + 1); // settle the claim: position in the output list
-                    if (idx < cap)               // always, unless the capacity bound is violated (reported below)
-                        out[idx] = h;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, first[j]);
+                    if (first[j])
+                    {
+                        const uint32_t idx = (uint32_t)cursor + __popc(bal & ((1u << lane) - 1u));
+                        tab[slot[j]] = (mine[j] & ~2047u) | (idx + 1); // settle the claim: position in the output list
+                        if (idx < cap)                                 // always, unless the capacity bound is violated (reported below)
+                            out[idx] = h[j];
+                    }
+                    cursor += __popc(bal);
                 }
-                cursor += __popc(bal);
                 __syncwarp();
             }
             __syncwarp();

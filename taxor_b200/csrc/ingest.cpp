@@ -1,6 +1,8 @@
 #include "ingest.hpp"
 
+#include <algorithm>
 #include <cstring>
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <stdexcept>
 #include <sys/mman.h>
@@ -34,6 +36,56 @@ size_t bgzf_block_size(const unsigned char *p, size_t n)
 }
 } // namespace
 
+// ---- bzip2 through libbz2.so.1.0, bound at run time ----
+namespace
+{
+struct BzStream // bz_stream of bzlib.h (libbz2 1.0.x; the ABI has been frozen since 1.0.0)
+{
+    char *next_in;
+    unsigned int avail_in, total_in_lo32, total_in_hi32;
+    char *next_out;
+    unsigned int avail_out, total_out_lo32, total_out_hi32;
+    void *state;
+    void *(*bzalloc)(void *, int, int);
+    void (*bzfree)(void *, void *);
+    void *opaque;
+};
+struct BzApi
+{
+    int (*init)(BzStream *, int, int){nullptr};
+    int (*run)(BzStream *){nullptr};
+    int (*end)(BzStream *){nullptr};
+    bool ok{false};
+};
+const BzApi &bz_api()
+{
+    static const BzApi api = [] {
+        BzApi a;
+        void *h = nullptr;
+        for (const char *name : {"libbz2.so.1.0", "libbz2.so.1", "libbz2.so"})
+            if ((h = dlopen(name, RTLD_NOW | RTLD_LOCAL)))
+                break;
+        if (h)
+        {
+            a.init = reinterpret_cast<int (*)(BzStream *, int, int)>(dlsym(h, "BZ2_bzDecompressInit"));
+            a.run = reinterpret_cast<int (*)(BzStream *)>(dlsym(h, "BZ2_bzDecompress"));
+            a.end = reinterpret_cast<int (*)(BzStream *)>(dlsym(h, "BZ2_bzDecompressEnd"));
+            a.ok = a.init && a.run && a.end;
+        }
+        return a;
+    }();
+    return api;
+}
+struct BzState
+{
+    BzStream zs{};
+    bool open{false};
+    std::vector<char> in;
+    BzState() : in(1 << 20) {}
+};
+constexpr int kBzOk = 0, kBzStreamEnd = 4;
+} // namespace
+
 RecordScanner::RecordScanner(const std::string &path)
 {
     fd_ = ::open(path.c_str(), O_RDONLY);
@@ -41,6 +93,19 @@ RecordScanner::RecordScanner(const std::string &path)
         return;
     unsigned char magic[18] = {0};
     const ssize_t n = ::pread(fd_, magic, sizeof magic, 0);
+    if (n >= 4 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h' && magic[3] >= '1' && magic[3] <= '9')
+    {
+        if (!bz_api().ok)
+        {
+            open_error_ = "bzip2 input needs libbz2.so.1.0 at run time and it could not be loaded; decompress the file (bzip2 -d) or "
+                          "recompress it with gzip / bgzip";
+            ::close(fd_);
+            fd_ = -1;
+            return;
+        }
+        bz_ = new BzState;
+        return; // fd_ stays open: fill_bz2 reads the compressed bytes from it
+    }
     struct stat st;
     if (n == 18 && fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && st.st_size >= 28)
     {
@@ -84,6 +149,13 @@ RecordScanner::RecordScanner(const std::string &path)
 
 RecordScanner::~RecordScanner()
 {
+    if (bz_)
+    {
+        BzState *b = static_cast<BzState *>(bz_);
+        if (b->open)
+            bz_api().end(&b->zs);
+        delete b;
+    }
     if (bgzf_data_)
         munmap(const_cast<unsigned char *>(bgzf_data_), bgzf_size_);
     if (gz_)
@@ -198,10 +270,62 @@ size_t RecordScanner::fill_bgzf(char *dst, size_t cap)
     return got;
 }
 
+// one bzip2 stream after the other (pbzip2 / `cat a.bz2 b.bz2` files are concatenations), single-threaded like zlib's
+size_t RecordScanner::fill_bz2(char *dst, size_t cap)
+{
+    BzState &b = *static_cast<BzState *>(bz_);
+    const BzApi &api = bz_api();
+    size_t got = 0;
+    while (got < cap && !eof_)
+    {
+        if (b.zs.avail_in == 0)
+        {
+            const ssize_t n = ::read(fd_, b.in.data(), b.in.size());
+            if (n < 0)
+                throw std::runtime_error("read error");
+            if (n == 0)
+            {
+                if (b.open)
+                    throw std::runtime_error("truncated bzip2 stream");
+                eof_ = true;
+                break;
+            }
+            b.zs.next_in = b.in.data();
+            b.zs.avail_in = (unsigned)n;
+        }
+        if (!b.open)
+        {
+            char *keep_in = b.zs.next_in;
+            const unsigned keep_avail = b.zs.avail_in;
+            b.zs = BzStream{};
+            b.zs.next_in = keep_in;
+            b.zs.avail_in = keep_avail;
+            if (api.init(&b.zs, 0, 0) != kBzOk)
+                throw std::runtime_error("bzip2 initialisation failed");
+            b.open = true;
+        }
+        b.zs.next_out = dst + got;
+        b.zs.avail_out = (unsigned)std::min<size_t>(cap - got, 1u << 30);
+        const unsigned before = b.zs.avail_out;
+        const int rc = api.run(&b.zs);
+        got += before - b.zs.avail_out;
+        if (rc == kBzStreamEnd)
+        {
+            api.end(&b.zs);
+            b.open = false; // another stream may follow
+        }
+        else if (rc != kBzOk)
+            throw std::runtime_error("read error (corrupt bzip2 stream?)");
+    }
+    return got;
+}
+
 size_t RecordScanner::fill(char *dst, size_t cap)
 {
     if (bgzf_data_)
         return fill_bgzf(dst, cap);
+    if (bz_)
+        return fill_bz2(dst, cap);
     size_t got = 0;
     while (got < cap && !eof_)
     {
@@ -243,8 +367,13 @@ bool scan_record(const char *data, size_t n, size_t pos, bool at_eof, RecordRef 
     if (!nl && !at_eof)
         return false;
     const char *hdr_end = nl ? nl : end;
-    r.id_off = (uint32_t)(pos + 1);
-    r.id_len = (uint32_t)line_len(p + 1, hdr_end);
+    const char *id = p + 1;
+    if (marker == '>') // SeqAn3's FASTA reader skips the blanks between '>' and the id ("> id" and ">id" are the same record)
+        while (id < hdr_end && (*id == ' ' || *id == '\t'))
+            ++id;
+    r.fasta = marker == '>';
+    r.id_off = (uint32_t)(id - data);
+    r.id_len = (uint32_t)line_len(id, hdr_end);
     p = nl ? nl + 1 : end;
     r.seq_off = (uint32_t)(p - data);
     size_t seq_len = 0, lines = 0;
@@ -383,7 +512,8 @@ MappedFile::MappedFile(const std::string &path)
         {
             data_ = static_cast<const char *>(p);
             madvise(p, size_, MADV_SEQUENTIAL);
-            gzip_ = size_ >= 2 && (unsigned char)data_[0] == 0x1f && (unsigned char)data_[1] == 0x8b;
+            gzip_ = (size_ >= 2 && (unsigned char)data_[0] == 0x1f && (unsigned char)data_[1] == 0x8b) ||
+                    (size_ >= 4 && data_[0] == 'B' && data_[1] == 'Z' && data_[2] == 'h' && data_[3] >= '1' && data_[3] <= '9');
         }
     }
     ::close(fd);
@@ -498,6 +628,20 @@ size_t accept_byte_range(const char *data, size_t size, size_t expected, size_t 
         sg.end = scan_segment(data, size, expected, hi, sg.recs);
     }
     return sg.end;
+}
+
+void clean_record(const char *raw, const RecordRef &r, std::string &out)
+{
+    out.clear();
+    out.reserve(r.seq_len);
+    const char *p = raw + r.seq_off, *end = p + r.seq_span;
+    for (; p < end; ++p)
+    {
+        const unsigned char c = (unsigned char)*p;
+        if (c == ' ' || (c >= '\t' && c <= '\r') || (r.fasta && c >= '0' && c <= '9'))
+            continue;
+        out.push_back((char)c);
+    }
 }
 
 void join_record(const char *raw, const RecordRef &r, std::string &out)

@@ -22,6 +22,7 @@ struct RecordRef // one record inside a raw buffer
     uint32_t seq_off, seq_span; // first sequence byte .. end of the last sequence line (may contain line breaks)
     uint32_t seq_len;          // bases (line breaks excluded)
     uint32_t single_line;      // 1: the seq_len bases are contiguous at seq_off
+    uint32_t fasta;            // 1: '>' record (SeqAn3 drops digits inside FASTA sequence lines, not inside FASTQ ones)
 };
 
 // Streams a sequence file as raw buffers that each start at a record boundary.
@@ -33,6 +34,7 @@ public:
     RecordScanner(const RecordScanner &) = delete;
     RecordScanner &operator=(const RecordScanner &) = delete;
     bool ok() const { return fd_ >= 0 || gz_ != nullptr || bgzf_data_ != nullptr; }
+    const std::string &open_error() const { return open_error_; } // why ok() is false, when there is more to say than "cannot open"
     // Fills `buf` (resized as needed; `target` bytes unless one record needs more) and appends the descriptors of
     // the complete records it holds to `recs` (cleared first).  The incomplete tail is kept for the next call.
     // Returns false when the file is exhausted and nothing was produced; throws std::runtime_error on malformed input.
@@ -53,6 +55,11 @@ private:
     size_t bgzf_size_{0}, bgzf_pos_{0};
     std::vector<char> bgzf_rest_; // tail of a block that did not fit the caller's buffer
     size_t bgzf_rest_pos_{0};
+    // bzip2 (the reference reads it through SeqAn3, taxor_search.cpp:181-182): libbz2.so.1.0 is bound at run time (dlopen) --
+    // the image has the library but not its header, so the three entry points and the stream struct are declared here
+    size_t fill_bz2(char *dst, size_t cap);
+    void *bz_{nullptr};           // BzState
+    std::string open_error_;
 };
 
 // ---- plain (not gzip) files: mapped, cut into byte segments, segments scanned in parallel ----
@@ -64,7 +71,7 @@ public:
     MappedFile(const MappedFile &) = delete;
     MappedFile &operator=(const MappedFile &) = delete;
     bool ok() const { return ok_; }
-    bool gzip() const { return gzip_; } // starts with the gzip magic: use RecordScanner instead
+    bool gzip() const { return gzip_; } // starts with the gzip or bzip2 magic: use RecordScanner instead
     const char *data() const { return data_; }
     size_t size() const { return size_; }
 
@@ -100,4 +107,8 @@ size_t accept_byte_range(const char *data, size_t size, size_t expected, size_t 
 
 // The sequence of `r` with its line breaks removed (multi-line records); single-line records need no copy.
 void join_record(const char *raw, const RecordRef &r, std::string &out);
+// The sequence as SeqAn3's readers deliver it: line breaks dropped, and so are blanks (both formats) and digits (FASTA only)
+// inside sequence lines (format_fasta.hpp / format_fastq.hpp filter them before the alphabet check).  Slow path, taken only
+// for records whose fast pack hit such a character.
+void clean_record(const char *raw, const RecordRef &r, std::string &out);
 } // namespace txr

@@ -340,7 +340,7 @@ __device__ __forceinline__ void scan_bins(const QueryArgs &a, const IxfDev &d, u
 } // namespace
 
 // ---- IXFs with tbins <= 512: one warp per (read, IXF) ----
-template <bool GEN>
+template <bool GEN, int UNROLL>
 __global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(QueryArgs a)
 {
     if (!sm_filter_keep(a.smf))
@@ -372,8 +372,8 @@ __global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(Query
         const uint32_t H = a.hash_count[read];
         const uint64_t *hp = a.hashes + a.hash_off[read];
         const uint64_t thr = a.thr_read ? a.thr_read[read] : (H < a.lut_len ? a.thr_lut[H] : ~0ULL);
-        const uint32_t Hp = probe_chunk<kQueryUnroll, GEN>(d, a.scheme, hp, H, 0u, d.tbins >> 4, cnt, lane,
-                                                           l2_plan_for(d, a.l2_hints != 0), a.early_exit ? thr : 0);
+        const uint32_t Hp = probe_chunk<UNROLL, GEN>(d, a.scheme, hp, H, 0u, d.tbins >> 4, cnt, lane,
+                                                     l2_plan_for(d, a.l2_hints != 0), a.early_exit ? thr : 0);
         __syncwarp();
         scan_bins(a, d, read, thr, cnt, (uint32_t)lane, 32u);
         __syncwarp();
@@ -907,10 +907,17 @@ static int query_ctas(const QueryArgs &a) { return a.ctas_per_sm <= 0 ? 8 : a.ct
 
 cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st)
 {
+    // probe steps in flight per warp (QueryArgs::unroll): 2 fills the memory system when 7-8 CTAs per SM run; with fewer
+    // CTAs (the hash kernel of the next batch beside the probes) 3 or 4 keep as many bytes in flight
+    const int grid = sm_count * query_ctas(a);
     if (a.generic)
-        ixf_query_small_kernel<true><<<sm_count * query_ctas(a), 32 * kQueryWarps, 0, st>>>(a);
+        ixf_query_small_kernel<true, kQueryUnroll><<<grid, 32 * kQueryWarps, 0, st>>>(a);
+    else if (a.unroll == 3)
+        ixf_query_small_kernel<false, 3><<<grid, 32 * kQueryWarps, 0, st>>>(a);
+    else if (a.unroll >= 4)
+        ixf_query_small_kernel<false, 4><<<grid, 32 * kQueryWarps, 0, st>>>(a);
     else
-        ixf_query_small_kernel<false><<<sm_count * query_ctas(a), 32 * kQueryWarps, 0, st>>>(a);
+        ixf_query_small_kernel<false, kQueryUnroll><<<grid, 32 * kQueryWarps, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -44,6 +44,8 @@ struct Config // src/main/taxor_search_configuration.hpp:8-19
     bool threads_given{false};
     std::string gpus;       // extension
     std::string ixf_record; // extension
+    std::string ixf_scheme; // extension: probe arithmetic of the index (hixf_file.hpp IxfSchemeSpec), default the prototype's
+    bool debug{false};
 };
 
 struct ParserError : std::runtime_error
@@ -94,7 +96,8 @@ void print_help()
                  "    --error-rate (double)\n          Expected error rate of reads that will be queried Default: 0.04. Value must be in range [0,1].\n\n"
                  "  B200 options (extensions of this implementation):\n"
                  "    --gpus (std::string)\n          Number of GPUs or comma-separated device list. Default: all visible devices.\n"
-                 "    --ixf-record (std::string)\n          Field order of the interleaved XOR filter records in the index file (see INTEGRATION.md).\n\n"
+                 "    --ixf-record (std::string)\n          Field order of the interleaved XOR filter records in the index file (see INTEGRATION.md).\n"
+                 "    --ixf-scheme (std::string)\n          Probe arithmetic of the interleaved XOR filters: xor3 | fuse3 [:mix=add|xor,fp=fold32|low8|high8,\n          rot=R1/R2,layout=slot|bin]. Default: xor3 (the prototype's arithmetic, see INTEGRATION.md).\n\n"
                  "VERSION\n    taxor-search version: 0.2.0 (taxor_b200)\n";
 }
 
@@ -130,7 +133,10 @@ void parse_args(int argc, char const **argv, Config &c) // taxor_search.cpp:32-8
             exit(0);
         }
         if (a == "--output-verbose-statistics" || a == "--debug") // hidden flags, no effect on search (:69-79)
+        {
+            c.debug = c.debug || a == "--debug"; // here: also prints which record order / filter scheme the index was read with
             continue;
+        }
         if (a.rfind("--", 0) != 0)
             throw ParserError("Too many arguments provided. Please see -h/--help for more information.");
         const size_t eq = a.find('=');
@@ -171,6 +177,14 @@ void parse_args(int argc, char const **argv, Config &c) // taxor_search.cpp:32-8
             c.gpus = v;
         else if (name == "ixf-record")
             c.ixf_record = v;
+        else if (name == "ixf-scheme")
+        {
+            IxfSchemeSpec probe;
+            std::string err;
+            if (!IxfSchemeSpec::parse(v, probe, err))
+                throw ParserError("Validation failed for option --ixf-scheme: " + err);
+            c.ixf_scheme = v;
+        }
         else
             throw ParserError("Unknown option --" + name + ". In case this is meant to be a non-option/argument/parameter, please specify the start of non-options with '--'. See -h/--help for program information.");
     }
@@ -178,12 +192,22 @@ void parse_args(int argc, char const **argv, Config &c) // taxor_search.cpp:32-8
         throw ParserError("Option --index-file is required but not set.");
 }
 
-std::string load_index_file(const std::string &path, const Config &cfg, TaxorIndexFile &idx)
+IxfSchemeSpec scheme_of(const Config &cfg)
 {
+    IxfSchemeSpec sc;
+    std::string err;
+    if (!cfg.ixf_scheme.empty())
+        IxfSchemeSpec::parse(cfg.ixf_scheme, sc, err); // validated by parse_args
+    return sc;
+}
+
+std::string load_index_file(const std::string &path, const Config &cfg, TaxorIndexFile &idx, HixfReadReport *report = nullptr)
+{
+    const IxfSchemeSpec sc = scheme_of(cfg);
     if (cfg.ixf_record.empty())
-        return read_hixf(path, idx, nullptr, nullptr);
+        return read_hixf(path, idx, nullptr, nullptr, &sc, report);
     const IxfRecordSpec spec = IxfRecordSpec::parse(cfg.ixf_record);
-    return read_hixf(path, idx, &spec, nullptr);
+    return read_hixf(path, idx, &spec, nullptr, &sc, report);
 }
 
 // ---- one GPU worker: owns a context with the index in HBM ----
@@ -330,7 +354,8 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
     TaxorIndexFile idx;
     std::string load_error;
-    std::thread loader([&] { load_error = load_index_file(index_path, cfg, idx); }); // the async cereal_worker (:162-180)
+    HixfReadReport read_report;
+    std::thread loader([&] { load_error = load_index_file(index_path, cfg, idx, &read_report); }); // the async cereal_worker (:162-180)
 
     MappedFile mapped(query);
     if (!mapped.ok())
@@ -341,6 +366,14 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     loader.join();
     if (!load_error.empty())
         throw std::runtime_error(load_error);
+    // the record order and the probe arithmetic of the IXFs are defined by a SeqAn3 fork that is not available:
+    // say which ones were used when asked, and say so unasked when the file left the choice open
+    if (!read_report.note.empty())
+        std::cerr << "[TAXOR SEARCH WARNING] " << index_path << ": " << read_report.note << std::endl;
+    if (cfg.debug)
+        std::cerr << "[taxor debug] " << index_path << ": IXF record order [" << read_report.used.str() << "], filter scheme "
+                  << scheme_of(cfg).str() << ", " << read_report.tiling_candidates << " order(s) tile the file, "
+                  << read_report.capacity_consistent << " consistent with max_elems" << std::endl;
 
     Thresholder thresholder(idx.window_size, idx.kmer_size, cfg.threshold, cfg.error_rate, idx.use_syncmer);
     std::cout << thresholder.banner();
@@ -357,12 +390,14 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     std::vector<int64_t> next_flat, ub_flat;
     for (size_t i = 0; i < idx.ixf.size(); ++i)
     {
-        views[i] = txr_ixf_view{idx.ixf[i].seed, idx.ixf[i].bins, idx.ixf[i].tbins, idx.ixf[i].seg_len, idx.ixf[i].fp};
+        views[i] = txr_ixf_view{idx.ixf[i].seed, idx.ixf[i].bins, idx.ixf[i].tbins, idx.ixf[i].seg_len, idx.ixf[i].fp, idx.ixf[i].rows};
         next_flat.insert(next_flat.end(), idx.next_ixf_id[i].begin(), idx.next_ixf_id[i].end());
         ub_flat.insert(ub_flat.end(), idx.ixf_bin_to_filename_position[i].begin(), idx.ixf_bin_to_filename_position[i].end());
         bin_off[i + 1] = next_flat.size();
     }
-    txr_hixf_view hv{idx.ixf.size(), views.data(), bin_off.data(), next_flat.data(), ub_flat.data(), idx.user_bin_filenames.size()};
+    const IxfSchemeSpec sch = scheme_of(cfg);
+    const txr_ixf_scheme scheme{sch.slots, sch.mix, sch.fingerprint, sch.rot1, sch.rot2, sch.layout};
+    txr_hixf_view hv{idx.ixf.size(), views.data(), bin_off.data(), next_flat.data(), ub_flat.data(), idx.user_bin_filenames.size(), &scheme};
     txr_params par{};
     par.kmer_size = idx.kmer_size;
     par.syncmer_size = idx.syncmer_size;
@@ -432,6 +467,7 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     }
     std::string worker_error;
     std::mutex err_m;
+    std::atomic<uint64_t> n_reads_total{0}, n_reads_hit{0};
     std::atomic<bool> failed{false}; // a parse or search error: everything still queued drains without further work
     std::vector<std::thread> workers;
     for (txr_ctx *c : ctxs)
@@ -451,7 +487,14 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
                     failed = true;
                 }
                 else
+                {
                     format_chunk(*ch, res, idx, user_bin_index);
+                    uint64_t hit = 0;
+                    for (size_t r = 0; r < ch->n; ++r)
+                        hit += res.hit_begin[r + 1] > res.hit_begin[r];
+                    n_reads_total += ch->n;
+                    n_reads_hit += hit;
+                }
                 done_q.push(ch);
             }
         });
@@ -509,7 +552,15 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
                     bases = scratch.data();
                 }
                 if (txr_pack_2bit(bases, r.seq_len, ch.words + ch.word_off[idx]) != TXR_OK)
-                    fail("read '" + ch.ids[idx] + "': " + txr_last_error());
+                {
+                    // blanks (and, in FASTA, digits) inside sequence lines are not bases: SeqAn3 filters them before the
+                    // alphabet check.  The record keeps its (larger) word reservation; only its length shrinks.
+                    clean_record(base, r, scratch);
+                    if (scratch.size() == r.seq_len || txr_pack_2bit(scratch.data(), scratch.size(), ch.words + ch.word_off[idx]) != TXR_OK)
+                        fail("read '" + ch.ids[idx] + "': " + txr_last_error());
+                    else
+                        ch.len[idx] = (uint32_t)scratch.size();
+                }
             }
             if (ch.pending.fetch_sub(1) == 1)
                 work_q.push(&ch);
@@ -629,7 +680,7 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
             // gzip (or unmappable) input: one streaming scanner, raw buffers recycled through a pool
             RecordScanner fin(query);
             if (!fin.ok())
-                throw std::runtime_error("cannot open query file " + query);
+                throw std::runtime_error(fin.open_error().empty() ? "cannot open query file " + query : query + ": " + fin.open_error());
             for (auto &rb : raw_pool)
                 raw_free.push(&rb);
             while (!failed)
@@ -666,6 +717,12 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
                   << fp_bytes / 1e9 << " GB), ingest+search+write " << since(t_search) << " s, " << seq << " chunks, " << n_pack
                   << " pack threads\n";
     }
+    // nothing at all matched: with a reference-built index that is what a wrong guess of the (unpinned) record order or
+    // filter arithmetic looks like -- every probe misses silently.  Say it loudly instead.
+    if (n_reads_total.load() >= 1000 && n_reads_hit.load() == 0)
+        std::cerr << "[TAXOR SEARCH WARNING] none of the " << n_reads_total.load() << " reads matched any reference. If this index was "
+                     "written by the reference `taxor build`, its interleaved-XOR-filter record order / probe arithmetic may differ from "
+                     "the ones assumed here (--debug shows them; --ixf-record / --ixf-scheme select others; INTEGRATION.md)." << std::endl;
     for (auto &ch : pool)
         txr_host_free(ch.words);
     for (txr_ctx *c : ctxs)

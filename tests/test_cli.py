@@ -90,6 +90,18 @@ def test_cli_end_to_end_result_file(tmp_path, oracle, built_libs):
     assert "use percentage-model\t0.15" in r.stdout
     body = H.oracle_tsv(oracle, ds.arrays, species, records, k=22, s=12, t=5, use_syncmer=True, percentage=0.15, header=False)
     assert open(out).read() == H.HEADER + body * 4
+    # SeqAn3 reader semantics the reference inherits: blanks after '>' are not part of the id; blanks and digits inside FASTA
+    # sequence lines are dropped before the alphabet check
+    rid, seq = records[5]
+    odd = tmp_path / "odd.fasta"
+    chunks = [seq[i:i + 60] for i in range(0, len(seq), 60)]
+    open(odd, "w").write(">  \t" + rid + "\n" + "\n".join(f"{10 * i + 1:>6} " + " ".join(c[j:j + 10] for j in range(0, len(c), 10))
+                                                          for i, c in enumerate(chunks)) + "\n")
+    r = run_cli("search", "--index-file", str(idx_path), "--query-file", str(odd), "--output-file", str(tmp_path / "odd.tsv"),
+                "--error-rate", "0.1")
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "odd.tsv").read() == H.oracle_tsv(oracle, ds.arrays, species, [records[5]], k=22, s=12, t=5,
+                                                             use_syncmer=True, error_rate=0.1)
     # an illegal character aborts loudly
     bad = "ACGT!ACGTACGTACGTACGTACGTACGT"
     open(tmp_path / "bad.fq", "w").write(f"@r1\n{bad}\n+\n{'I' * len(bad)}\n")

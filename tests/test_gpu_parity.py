@@ -235,7 +235,7 @@ def test_search_wide_rows(monkeypatch, oracle, t_max, n_genomes, early):
         ds = H.make_dataset(oracle, n_genomes=n_genomes, genome_len=2_000, t_max=t_max, size_jitter=True, seed=9000 + t_max)
         assert int(ds.hixf.tbins[0]) == t_max
         rng = np.random.default_rng(t_max)
-        own = H.make_reads(ds, rng.integers(300, 1900, 80), err=0.02)
+        own = H.make_reads(ds, rng.integers(300, 800, 80), err=0.02)
         foreign = [rng.integers(0, 4, int(n), dtype=np.uint8) for n in rng.integers(300, 6000, 60)]
         seqs = foreign + [capi.unpack_codes(own, i) for i in range(own.n)] + [np.zeros(0, np.uint8), np.zeros(21, np.uint8)]
         reads = capi.pack_codes([seqs[i] for i in rng.permutation(len(seqs))])
@@ -439,7 +439,7 @@ def test_ixf_scheme_variants(oracle, scheme, t_max):
         values = np.concatenate([ds.hixf._ub[3][:400], ds.hixf._ub[11][:300], rng.integers(0, 2**63, 1500, dtype=np.uint64)])
         for x in range(min(ds.hixf.n_ixf, 4)):
             assert np.array_equal(c.ixf_bulk_count(x, values, int(ds.hixf.bins[x])), oracle.ixf_bulk_count(oh, x, values)), x
-        reads = H.make_reads(ds, rng.integers(300, 1900 if t_max > 16 else 9000, 150), err=0.03)
+        reads = H.make_reads(ds, rng.integers(300, 800 if t_max > 16 else 9000, 150), err=0.03)
         res, ora = _search_case(c, oracle, ds, reads, error_rate=0.1)
         assert int(res.hit_begin[-1]) > 30
         # the same index handed over bin-major (one plain filter after the other): re-laid-out on upload

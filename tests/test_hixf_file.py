@@ -44,6 +44,54 @@ def test_roundtrip_and_header_bytes(tmp_path, built_libs):
     hx.close()
 
 
+def test_record_order_is_pinned_by_capacity_or_reported_ambiguous(tmp_path, built_libs):
+    """`seed` and `max_elems` are both free u64 scalars: orders that only swap them tile equally well.  The reader prefers the
+    order whose max_elems reproduces the stored geometry (rows == geometry(max_elems)); when the file carries no usable
+    capacity the ambiguity is REPORTED (HixfFile.note / the CLI's warning), not silently resolved."""
+    hx = small_index()
+    path = tmp_path / "t.hixf"
+    tools.write_hixf(path, hx, k=22, s=12, t=5)                          # writer's order, with the capacities the builder used
+    f = tools.HixfFile(path)
+    assert f.record_spec == "bins,tbins,slots,bin_words,max_elems,seed" and np.array_equal(f.seed, hx.seed)
+    assert "equally well" not in f.note
+    f.close()
+    # the swapped order tiles as well, but its "max_elems" (really the seed) does not reproduce the geometry: not picked
+    swapped = "bins,tbins,slots,bin_words,seed,max_elems"
+    g = tools.HixfFile(path, swapped)
+    assert not np.array_equal(g.seed, hx.seed)                            # an explicit wrong order is the caller's business ...
+    g.close()
+    # ... a file WITHOUT capacities leaves the choice open: the reader says so
+    class NoCap:
+        pass
+    nc = NoCap()
+    for k in ("seed", "bins", "tbins", "seg_len", "data", "bin_off", "next_ixf_id", "bin_to_ub", "n_user_bins", "rows"):
+        setattr(nc, k, getattr(hx, k))
+    tools.write_hixf(path, nc, k=22, s=12, t=5)
+    f = tools.HixfFile(path)
+    assert "tiling alone" in f.note or "equally well" in f.note
+    f.close()
+    hx.close()
+
+
+def test_binary_fuse_index_file_roundtrip(tmp_path, built_libs):
+    """a binary-fuse index (second candidate scheme) needs seg_len AND slots in the record; the geometry check follows the scheme"""
+    rng = np.random.default_rng(4)
+    ub = [np.unique(rng.integers(0, 2**63, size=int(n), dtype=np.uint64)) for n in rng.integers(300, 2000, 30)]
+    hx = tools.BuiltHixf(ub, t_max=8, seed=3, scheme=(1, 0, 0, 0, 0))
+    path = tmp_path / "fuse.hixf"
+    spec = "bins,tbins,slots,bin_words,max_elems,seg_len,seed"
+    tools.write_hixf(path, hx, k=22, s=12, t=5, record_spec=spec)
+    f = tools.HixfFile(path, scheme="fuse3")
+    assert f.record_spec == spec and np.array_equal(f.rows, hx.rows) and np.array_equal(f.seg_len, hx.seg_len)
+    assert all(np.array_equal(x, y) for x, y in zip(f.data, hx.data))
+    f.close()
+    with pytest.raises(RuntimeError):
+        tools.HixfFile(path)                                              # read as xor3: slots are not three equal segments
+    with pytest.raises(RuntimeError, match="scheme"):
+        tools.HixfFile(path, scheme="cuckoo")
+    hx.close()
+
+
 def test_malformed_files_are_rejected(tmp_path, built_libs):
     hx = small_index()
     path = tmp_path / "t.hixf"

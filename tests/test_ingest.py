@@ -175,6 +175,34 @@ def test_bgzf_blocks_are_inflated_in_parallel_and_in_order(tmp_path, fmt):
         _dump(bad, 1 << 20, tmp_path)
 
 
+@pytest.mark.parametrize("fmt", ["fasta", "fastq"])
+def test_bzip2_input_through_the_runtime_bound_library(tmp_path, fmt):
+    """bzip2 reads (the reference takes them through SeqAn3, taxor_search.cpp:181-182): libbz2.so.1.0 is bound with dlopen --
+    single stream, concatenated streams (pbzip2 / cat), small buffers, and a damaged file"""
+    import bz2
+    rng = np.random.default_rng(91 if fmt == "fasta" else 92)
+    recs, blob = _make(rng, fmt, 300, b"\n", 0 if fmt == "fastq" else 60)
+    p = tmp_path / f"x.{fmt}.bz2"
+    p.write_bytes(bz2.compress(blob, 1))
+    for target in (1 << 22, 70_000, 1000):
+        assert _dump(p, target, tmp_path) == recs, target
+    cut = blob.index(b"\n", len(blob) // 2) + 1
+    while blob[cut:cut + 1] not in (b">", b"@") or (fmt == "fastq" and blob[cut - 1:cut] != b"\n"):
+        cut = blob.index(b"\n", cut) + 1                   # any line start works: the streams are simply concatenated
+        break
+    p.write_bytes(bz2.compress(blob[:cut], 9) + bz2.compress(blob[cut:], 5))
+    assert _dump(p, 1 << 20, tmp_path) == recs
+    raw = bytearray(p.read_bytes())
+    raw[len(raw) // 3] ^= 0x5A
+    bad = tmp_path / "bad.bz2"
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(RuntimeError, match="corrupt|start|truncated"):
+        _dump(bad, 1 << 20, tmp_path)
+    (tmp_path / "short.bz2").write_bytes(bz2.compress(blob, 9)[:-20])
+    with pytest.raises(RuntimeError, match="corrupt|truncated"):
+        _dump(tmp_path / "short.bz2", 1 << 20, tmp_path)
+
+
 def test_ingest_fuzz_under_sanitizers(tmp_path):
     """tests/fuzz/ingest_fuzz.cpp built with -fsanitize=address,undefined: mutated FASTA/FASTQ through the streaming and the
     mapped byte-range path; no crash, no sanitizer report, and both paths accept/reject and parse alike."""
