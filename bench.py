@@ -355,7 +355,7 @@ def cpu_oracle():
     if "o" not in _ORACLES:
         from oracle.oracle import Oracle
         try:
-            _ORACLES["o"], _ORACLES["build"] = Oracle(native=True), "-O3 -march=native, built on this box"
+            _ORACLES["o"], _ORACLES["build"] = Oracle(native=True), "-O3 -march=native -ffp-contract=off, built on this box"
         except Exception as e:                                     # no compiler on the box: say so in the line
             _ORACLES["o"], _ORACLES["build"] = Oracle(), f"portable -march=x86-64-v2 build (native build failed: {type(e).__name__})"
     return _ORACLES["o"]

@@ -190,6 +190,43 @@ int txr_plan_segments(const txr_params *params, const uint64_t *words, uint64_t 
 int txr_hash_user_bins(txr_ctx *ctx, const uint64_t *words, const uint64_t *word_off, const uint32_t *len,
                        uint64_t n_seqs, const uint32_t *seq_bin, uint64_t n_bins, txr_bin_hashes *out);
 
+/* ---- `taxor profile` head fed from in-memory results (host code, no GPU) ----
+ * Replaces the TSV round trip between `taxor search` and `taxor profile`: parse_search_results
+ * (src/main/taxor_profile.cpp:93-163) becomes txr_profile_add_batch on txr_result batches (or txr_profile_add_file for a
+ * result file written earlier), and the three reference-filter rounds that open tax_profile (:796-825:
+ * remove_matches_to_nonunique_refs :186-234, remove_low_confidence_references(3, 0.01) :269-282, filter_ref_associations
+ * :289-462) run on the table.  The EM loop and the CAMI writers stay with the reference binary. */
+typedef struct txr_profile txr_profile;
+typedef struct
+{
+    uint64_t user_bin, seq_len;                    /* Species::user_bin, Species::seq_len (src/taxonomy/Species.hpp:14-21) */
+    const char *accession_id, *taxid, *taxnames_string, *taxid_string;
+} txr_profile_species;
+typedef struct                                     /* the table in std::map order (by read id), hits in arrival order */
+{
+    uint64_t n_reads;
+    const char *const *read_id;                    /* [n_reads]                                                        */
+    const uint64_t *hit_begin;                     /* [n_reads+1]                                                      */
+    const char *const *accession_id;               /* [n_hits] "-" = unclassified (taxonomy::Search_Result fields)     */
+    const char *const *tax_id;
+    const uint64_t *ref_len, *query_len, *query_hash_count, *query_hash_match;
+    uint64_t n_taxa;                               /* references left after round 3 (filter_ref_associations' result)  */
+} txr_profile_view;
+const char *txr_profile_last_error(void);
+int txr_profile_create(txr_profile **out);
+void txr_profile_destroy(txr_profile *p);
+/* read_ids[r] / read_len[r] describe read r of `result` (the id is cut at its first space, :125-126); only hits with
+ * keep != 0 count (the result file holds no others); reads without hits enter as "-" (:129-133) */
+int txr_profile_add_batch(txr_profile *p, const txr_result *result, const char *const *read_ids, const uint32_t *read_len,
+                          const txr_profile_species *species, uint64_t n_species);
+int txr_profile_add_file(txr_profile *p, const char *search_file);
+/* runs the filter rounds not yet run, up to `rounds` (1..3) */
+int txr_profile_filter(txr_profile *p, int rounds);
+int txr_profile_get(txr_profile *p, txr_profile_view *out);
+/* line format for tests and hand-over: "R <id> <n>", n x "H <accession> <taxid> <ref_len> <query_len> <hashes> <matches>",
+ * then "T <accession> <ref_len>" per remaining reference and "P <accession> <taxid string> <taxname string>" (tab separated) */
+int txr_profile_text(txr_profile *p, const char **text, uint64_t *len);
+
 /* ---- kernel-level entry points for parity tests ---- */
 /* kernel #1 alone: seq_to_syncmers / minimiser_hash for a batch.  hash_off[n_reads+1]; hashes of read r are
  * hashes[hash_off[r] .. hash_off[r+1]) (distinct, unordered, in syncmer mode; position order in k-mer mode).

@@ -295,6 +295,21 @@ class Reference:
         L.ref_kmer_ci.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.ref_adjust_seed.restype = C.c_uint64
         L.ref_adjust_seed.argtypes = [C.c_uint8]
+        if hasattr(L, "ref_profile_prefilter"):
+            L.ref_profile_prefilter.restype = C.c_void_p
+            L.ref_profile_prefilter.argtypes = [C.c_char_p, C.c_int]
+            L.ref_profile_free.argtypes = [C.c_void_p]
+
+    def profile_prefilter(self, search_file, stage: int = 3) -> str:
+        """the reference's own parse_search_results + filter rounds (src/main/taxor_profile.cpp:93-462, compiled in place) on a
+        result file; stage 0..3 = how many rounds; the table in the line format of txr_profile_text"""
+        p = self.lib.ref_profile_prefilter(str(search_file).encode(), stage)
+        if not p:
+            raise RuntimeError("ref_profile_prefilter failed")
+        try:
+            return C.string_at(p).decode()
+        finally:
+            self.lib.ref_profile_free(p)
 
     def syncmer_hashes(self, codes, k, s, t):
         codes = np.ascontiguousarray(codes, dtype=np.uint8)

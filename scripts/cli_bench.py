@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--threads", type=int, default=16)
     ap.add_argument("--gz", action="store_true", help="also time a gzip-compressed copy of the reads")
     ap.add_argument("--bgzf", action="store_true", help="also time a BGZF (bgzip-style blocked gzip) copy of the reads")
+    ap.add_argument("--gpus", default="1", help="--gpus of the CLI; a comma list of counts runs every one (e.g. 1,2,8)")
     args = ap.parse_args()
     from taxor_b200 import capi, tools
     import taxor_b200
@@ -95,22 +96,31 @@ def main():
         if not os.path.exists(bg):
             write_bgzf(fq, bg)
         files.append(("fastq.bgzf", bg))
+    def one(tag, path, th, gpus, extra_env=None):
+        out = os.path.join(args.work, "out.tsv")
+        env = dict(os.environ, TAXOR_TIMING="1", **(extra_env or {}))
+        t0 = time.time()
+        r = subprocess.run([taxor_b200.CLI_PATH, "search", "--index-file", hixf, "--query-file", path, "--output-file", out,
+                            "--error-rate", "0.1", "--threads", str(th), "--gpus", str(gpus)], capture_output=True, text=True, env=env)
+        wall = time.time() - t0
+        if r.returncode != 0:
+            raise SystemExit(r.stderr)
+        m = re.search(r"index load ([\d.e+-]+) s, upload to \d+ GPU\(s\) ([\d.e+-]+) s \(([\d.e+-]+) GB\), ingest\+search\+write ([\d.e+-]+) s", r.stderr)
+        load, upload, gb, search = (float(x) for x in m.groups())
+        return {"wall_s": round(wall, 2), "index_load_s": load, "index_upload_s": upload, "index_GB": gb, "gpus": gpus,
+                "upload_GBps_per_copy": round(gb / max(upload, 1e-9), 1),
+                "ingest_search_write_s": search, "file_GB": round(os.path.getsize(path) / 1e9, 2),
+                "Mbases_per_s_search_phase": round(args.reads * args.read_len / search / 1e6),
+                "hit_lines": sum(1 for line in open(out) if "\t-\t-\t" not in line) - 1}
+    gpu_counts = [int(x) for x in str(args.gpus).split(",")]
     for tag, path in files:
         for th in sorted({1, args.threads}):
-            out = os.path.join(args.work, "out.tsv")
-            env = dict(os.environ, TAXOR_TIMING="1")
-            t0 = time.time()
-            r = subprocess.run([taxor_b200.CLI_PATH, "search", "--index-file", hixf, "--query-file", path, "--output-file", out,
-                                "--error-rate", "0.1", "--threads", str(th), "--gpus", "1"], capture_output=True, text=True, env=env)
-            wall = time.time() - t0
-            if r.returncode != 0:
-                raise SystemExit(r.stderr)
-            m = re.search(r"index load ([\d.e+-]+) s, upload to \d+ GPU\(s\) ([\d.e+-]+) s \(([\d.e+-]+) GB\), ingest\+search\+write ([\d.e+-]+) s", r.stderr)
-            load, upload, gb, search = (float(x) for x in m.groups())
-            runs[f"{tag}_threads{th}"] = {"wall_s": round(wall, 2), "index_load_s": load, "index_upload_s": upload, "index_GB": gb,
-                                          "ingest_search_write_s": search, "file_GB": round(os.path.getsize(path) / 1e9, 2),
-                                          "Mbases_per_s_search_phase": round(args.reads * args.read_len / search / 1e6),
-                                          "hit_lines": sum(1 for line in open(out) if "\t-\t-\t" not in line) - 1}
+            runs[f"{tag}_threads{th}"] = one(tag, path, th, gpu_counts[0])
+    # index start-up (load_index + replication): the staged multi-threaded upload against the plain
+    # pageable copy, and one upload + device-to-device clones against the number of GPUs
+    runs["fastq_serial_upload"] = one("fastq", fq, args.threads, gpu_counts[0], {"TXR_UPLOAD_THREADS": "1"})
+    for g in gpu_counts[1:]:
+        runs[f"fastq_gpus{g}"] = one("fastq", fq, args.threads, g)
     print(json.dumps({"what": "taxor search CLI end to end (file -> file), 1 GPU", "reads": args.reads, "read_len": args.read_len,
                       "hixf_write_s": round(t_write, 1), "host_cores": os.cpu_count(), "runs": runs}))
 

@@ -106,6 +106,15 @@ def lib():
     L.txr_hash_user_bins.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(BinHashes)]
     L.txr_plan_segments.argtypes = [C.POINTER(Params), vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.txr_ixf_bulk_count.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp]
+    L.txr_profile_last_error.restype = C.c_char_p
+    L.txr_profile_create.argtypes = [C.POINTER(vp)]
+    L.txr_profile_destroy.argtypes = [vp]
+    L.txr_profile_destroy.restype = None
+    L.txr_profile_add_batch.argtypes = [vp, C.POINTER(Result), vp, vp, vp, C.c_uint64]
+    L.txr_profile_add_file.argtypes = [vp, C.c_char_p]
+    L.txr_profile_filter.argtypes = [vp, C.c_int]
+    L.txr_profile_get.argtypes = [vp, vp]
+    L.txr_profile_text.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64)]
     _LIB = L
     return L
 
@@ -114,7 +123,9 @@ EXPORTED = ["txr_last_error", "txr_version", "txr_ctx_create", "txr_ctx_destroy"
             "txr_index_upload", "txr_index_clone", "txr_params_set", "txr_threshold_get", "txr_threshold_eval", "txr_packed_words", "txr_pack_2bit",
             "txr_pack_codes", "txr_unpack_codes", "txr_host_alloc", "txr_host_free", "txr_search",
             "txr_reads_upload", "txr_reads_free", "txr_search_resident", "txr_get_timing", "txr_hash_batch",
-            "txr_hash_user_bins", "txr_plan_segments", "txr_ixf_bulk_count"]
+            "txr_hash_user_bins", "txr_plan_segments", "txr_ixf_bulk_count",
+            "txr_profile_last_error", "txr_profile_create", "txr_profile_destroy", "txr_profile_add_batch", "txr_profile_add_file",
+            "txr_profile_filter", "txr_profile_get", "txr_profile_text"]
 
 
 def _check(rc: int) -> None:
@@ -352,3 +363,48 @@ class Context:
         counts = np.zeros(bins, dtype=np.uint32)
         _check(self._L.txr_ixf_bulk_count(self._h, ixf_idx, values.ctypes.data, len(values), counts.ctypes.data))
         return counts
+
+
+class ProfileSpecies(C.Structure):
+    _fields_ = [("user_bin", C.c_uint64), ("seq_len", C.c_uint64), ("accession_id", C.c_char_p), ("taxid", C.c_char_p),
+                ("taxnames_string", C.c_char_p), ("taxid_string", C.c_char_p)]
+
+
+class Profile:
+    """txr_profile: the head of `taxor profile` (parse + the three reference-filter rounds), fed from txr_result batches or from
+    a result file.  Host code only -- usable without a GPU."""
+
+    def __init__(self) -> None:
+        self._L = lib()
+        self._h = C.c_void_p()
+        _check(self._L.txr_profile_create(C.byref(self._h)))
+
+    def _ok(self, rc):
+        if rc != 0:
+            raise TaxorError(f"taxor_b200 error {rc}: {self._L.txr_profile_last_error().decode()}")
+
+    def add_result(self, result: "Result", read_ids, read_len, species) -> None:
+        """result: the ctypes Result of a search call (still valid); species: list of dicts as in tools.default_species"""
+        n = int(result.n_reads)
+        ids = (C.c_char_p * n)(*[s.encode() if isinstance(s, str) else bytes(s) for s in read_ids])
+        ln = np.ascontiguousarray(read_len, dtype=np.uint32)
+        sp = (ProfileSpecies * len(species))(*[ProfileSpecies(int(x["user_bin"]), int(x["seq_len"]), x["accession_id"].encode(),
+                                                              x["taxid"].encode(), x["taxnames_string"].encode(),
+                                                              x["taxid_string"].encode()) for x in species])
+        self._ok(self._L.txr_profile_add_batch(self._h, C.byref(result), ids, ln.ctypes.data, sp, len(species)))
+
+    def add_file(self, path) -> None:
+        self._ok(self._L.txr_profile_add_file(self._h, str(path).encode()))
+
+    def filter(self, rounds: int = 3) -> None:
+        self._ok(self._L.txr_profile_filter(self._h, rounds))
+
+    def text(self) -> str:
+        t, n = C.c_char_p(), C.c_uint64()
+        self._ok(self._L.txr_profile_text(self._h, C.byref(t), C.byref(n)))
+        return C.string_at(t, n.value).decode()
+
+    def close(self) -> None:
+        if self._h:
+            self._L.txr_profile_destroy(self._h)
+            self._h = C.c_void_p()

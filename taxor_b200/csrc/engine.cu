@@ -279,7 +279,11 @@ struct txr_ctx
     bool sort_items{true};     // group level queues by IXF (TXR_SORT_ITEMS=0 disables, for A/B measurements)
     bool early_exit{true};     // exact early exit of kernel #2 (TXR_EARLY_EXIT=0 disables)
     bool l2_hints{true};       // L2 eviction-priority plan for small child IXFs (TXR_L2_HINTS=0 disables)
-    bool fuse_dedup{true};     // distinct set built inside the syncmer kernel (TXR_FUSE_DEDUP=0: separate dedup kernel)
+    // distinct set built inside the syncmer kernel (TXR_FUSE_DEDUP=1).  Off by default: measured slower (hash 13.1 + dedup
+    // 7.4 ms -> 25.0 ms per 1 M reads, profiles/r2_b_*): the hash kernel runs 16 warps per SM at 124 registers and is issue
+    // bound, so the claim rounds cost more there than in the 24-warp dedup kernel; neither side is DRAM bound, the saved
+    // 15 GB round trip buys nothing.
+    bool fuse_dedup{false};
     uint32_t query_unroll{0};  // TXR_QUERY_UNROLL: probe steps in flight per warp (experiments with fewer probe CTAs per SM)
     uint32_t fuse_max_keys{kWarpMaxKeys}; // TXR_FUSE_MAX_KEYS lowers it (tests: forces the hand-over to the CTA-per-read kernel)
     int root_partition{0};     // root level grouped by segment-0 slot: 0 off (default: measured slower), 1 auto, 2 always (TXR_ROOT_PARTITION)

@@ -211,6 +211,15 @@ __device__ __forceinline__ uint32_t probe_chunk(const IxfDev &d, const IxfScheme
     bool flushed = false;
     uint32_t probed = H;
     Probe pr[UNROLL];
+    // the keys of a step are fetched one step ahead: a batch's hash lists are GBs (DRAM, not L2), and a key load in front of
+    // every step's row loads would put two dependent DRAM latencies into each step of a warp
+    uint64_t keys[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+    {
+        const uint32_t idx = u * G + sub;
+        keys[u] = active && idx < H ? hp[idx] : 0;
+    }
     for (uint32_t h0 = 0; h0 < H; h0 += G * UNROLL)
     {
 #pragma unroll
@@ -218,8 +227,13 @@ __device__ __forceinline__ uint32_t probe_chunk(const IxfDev &d, const IxfScheme
         {
             const uint32_t idx = h0 + u * G + sub;
             const bool live = active && idx < H;
-            const uint64_t key = live ? hp[idx] : 0;
-            probe_issue<GEN>(pr[u], d, sch, col_base, key, live, l2);
+            probe_issue<GEN>(pr[u], d, sch, col_base, keys[u], live, l2);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+        {
+            const uint32_t idx = h0 + G * UNROLL + u * G + sub;
+            keys[u] = active && idx < H ? hp[idx] : 0;
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
@@ -340,8 +354,10 @@ __device__ __forceinline__ void scan_bins(const QueryArgs &a, const IxfDev &d, u
 } // namespace
 
 // ---- IXFs with tbins <= 512: one warp per (read, IXF) ----
-template <bool GEN, int UNROLL>
-__global__ void __launch_bounds__(32 * kQueryWarps) ixf_query_small_kernel(QueryArgs a)
+// MINB: CTAs per SM the register allocation must allow (8 = 64 registers, all 32 warps an SM's registers can hold at this
+// CTA size; 1 = whatever the code wants, 72 at UNROLL 2 -> 7 CTAs)
+template <bool GEN, int UNROLL, int MINB>
+__global__ void __launch_bounds__(32 * kQueryWarps, MINB) ixf_query_small_kernel(QueryArgs a)
 {
     if (!sm_filter_keep(a.smf))
         return;
@@ -911,13 +927,15 @@ cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st
     // CTAs (the hash kernel of the next batch beside the probes) 3 or 4 keep as many bytes in flight
     const int grid = sm_count * query_ctas(a);
     if (a.generic)
-        ixf_query_small_kernel<true, kQueryUnroll><<<grid, 32 * kQueryWarps, 0, st>>>(a);
+        ixf_query_small_kernel<true, kQueryUnroll, 1><<<grid, 32 * kQueryWarps, 0, st>>>(a);
     else if (a.unroll == 3)
-        ixf_query_small_kernel<false, 3><<<grid, 32 * kQueryWarps, 0, st>>>(a);
+        ixf_query_small_kernel<false, 3, 1><<<grid, 32 * kQueryWarps, 0, st>>>(a);
     else if (a.unroll >= 4)
-        ixf_query_small_kernel<false, 4><<<grid, 32 * kQueryWarps, 0, st>>>(a);
+        ixf_query_small_kernel<false, 4, 1><<<grid, 32 * kQueryWarps, 0, st>>>(a);
+    else if (query_ctas(a) >= 8)
+        ixf_query_small_kernel<false, kQueryUnroll, 8><<<grid, 32 * kQueryWarps, 0, st>>>(a);
     else
-        ixf_query_small_kernel<false, kQueryUnroll><<<grid, 32 * kQueryWarps, 0, st>>>(a);
+        ixf_query_small_kernel<false, kQueryUnroll, 7><<<grid, 32 * kQueryWarps, 0, st>>>(a);
     return cudaGetLastError();
 }
 

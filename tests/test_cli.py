@@ -144,3 +144,74 @@ def test_cli_minimiser_index(tmp_path, oracle, built_libs):
     got = open(out).read()
     assert got == H.oracle_tsv(oracle, ds.arrays, species, records, k=20, s=0, t=0, use_syncmer=False, window_size=28, error_rate=0.02)
     assert got.count("\t") > 6 * len(records)                   # reads really hit
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus_same_bytes_as_one(tmp_path, oracle, built_libs):
+    """reads sharded over two GPUs (one context per device, index uploaded once and cloned device to device, ordered writer):
+    the result file is byte-identical to the single-GPU file and to the oracle's; `--gpus 0,0` (two contexts on one device)
+    exercises the same multi-context path on a one-GPU box, `--gpus 2` the real thing where two devices exist
+    (taxor_search.cpp:214,308-311: reads are independent, only the output is shared)"""
+    import torch
+    ds = H.make_dataset(oracle, n_genomes=60, genome_len=40_000, t_max=16)
+    species = tools.default_species(ds.hixf.n_user_bins)
+    idx_path = tmp_path / "two.hixf"
+    tools.write_hixf(idx_path, ds.hixf, k=22, s=12, t=5, use_syncmer=True, window_size=20, species=species)
+    rng = np.random.default_rng(12)
+    reads = H.make_reads(ds, rng.integers(200, 9000, 3000), err=0.04)
+    records = [(f"read_{i}", "".join("ACGT"[c] for c in capi.unpack_codes(reads, i))) for i in range(reads.n)]
+    fq = tmp_path / "r.fastq"
+    open(fq, "w").write(fastq_text(records))
+    expect = H.oracle_tsv(oracle, ds.arrays, species, records, k=22, s=12, t=5, use_syncmer=True, error_rate=0.1)
+    outs = {}
+    specs = ["1", "0,0"] + (["2"] if torch.cuda.device_count() >= 2 else [])
+    for spec in specs:
+        out = tmp_path / f"o_{spec.replace(',', '_')}.tsv"
+        r = run_cli("search", "--index-file", str(idx_path), "--query-file", str(fq), "--output-file", str(out), "--error-rate", "0.1",
+                    "--threads", "4", "--gpus", spec)
+        assert r.returncode == 0, r.stderr
+        outs[spec] = open(out).read()
+    assert outs["1"] == expect
+    for spec in specs[1:]:
+        assert outs[spec] == outs["1"], spec
+
+
+@pytest.mark.gpu
+def test_profile_head_from_gpu_results_equals_reference_on_the_result_file(tmp_path, oracle, reference, built_libs):
+    """SURVEY 8(f) rank 3 end to end: the hits of a GPU search, handed to txr_profile_add_batch in memory and filtered, equal
+    what the REFERENCE's own taxor_profile.cpp (compiled in place) makes of the result file the CLI wrote for the same reads"""
+    import ctypes as C
+    if not hasattr(reference.lib, "ref_profile_prefilter"):
+        pytest.skip("oracle/_ref predates the profile shim")
+    ds = H.make_dataset(oracle, n_genomes=48, genome_len=40_000, t_max=8)
+    species = tools.default_species(ds.hixf.n_user_bins)
+    idx_path = tmp_path / "p.hixf"
+    tools.write_hixf(idx_path, ds.hixf, k=22, s=12, t=5, use_syncmer=True, window_size=20, species=species)
+    rng = np.random.default_rng(5)
+    reads = H.make_reads(ds, rng.integers(200, 9000, 2500), err=0.06)
+    ids = [f"read_{i if i % 40 else max(i - 1, 0)} ch={i % 9}" for i in range(reads.n)]          # some ids repeat, all carry a space
+    records = [(ids[i], "".join("ACGT"[c] for c in capi.unpack_codes(reads, i))) for i in range(reads.n)]
+    fq = tmp_path / "r.fastq"
+    open(fq, "w").write(fastq_text(records))
+    out = tmp_path / "o.tsv"
+    r = run_cli("search", "--index-file", str(idx_path), "--query-file", str(fq), "--output-file", str(out), "--error-rate", "0.1")
+    assert r.returncode == 0, r.stderr
+    with capi.Context(0) as ctx:
+        H.upload(ctx, ds)
+        ctx.set_params(k=22, s=12, t=5, use_syncmer=True, window_size=20, error_rate=0.1)
+        res = ctx.search_raw(reads.words.ctypes.data, reads.word_off.ctypes.data, reads.length.ctypes.data, reads.n)
+        prof = capi.Profile()
+        half = reads.n // 2                                       # two batches: a view of the first half, then of the rest
+        first = capi.Result(half, res.hash_count, res.threshold, res.hit_begin, res.user_bin, res.count, res.keep)
+        prof.add_result(first, ids[:half], reads.length[:half], species)
+        u32, u64 = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+        rest = capi.Result(reads.n - half, C.cast(C.addressof(res.hash_count.contents) + 4 * half, u32),
+                           C.cast(C.addressof(res.threshold.contents) + 8 * half, u64),
+                           C.cast(C.addressof(res.hit_begin.contents) + 8 * half, u64), res.user_bin, res.count, res.keep)
+        prof.add_result(rest, ids[half:], reads.length[half:], species)
+        assert prof.text() == reference.profile_prefilter(out, 0)
+        prof.filter(3)
+        got = prof.text()
+        prof.close()
+    assert got == reference.profile_prefilter(out, 3)
+    assert got.count("\nH\tGCF_") > 500

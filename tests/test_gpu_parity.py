@@ -251,7 +251,8 @@ def test_search_wide_rows(monkeypatch, oracle, t_max, n_genomes, early):
         c.close()
 
 
-@pytest.mark.parametrize("env", [{"TXR_FUSE_MAX_KEYS": "64"}, {"TXR_FUSE_MAX_KEYS": "300"}, {"TXR_FUSE_DEDUP": "0"}, {}])
+@pytest.mark.parametrize("env", [{"TXR_FUSE_DEDUP": "1", "TXR_FUSE_MAX_KEYS": "64"}, {"TXR_FUSE_DEDUP": "1", "TXR_FUSE_MAX_KEYS": "300"},
+                                 {"TXR_FUSE_DEDUP": "1"}, {}])
 @pytest.mark.parametrize("scaling", [1, 5])
 def test_fused_distinct_set_variants(monkeypatch, oracle, env, scaling):
     """the distinct set built inside the syncmer kernel: the hand-over of a read to the CTA-per-read kernel (forced early
@@ -508,3 +509,46 @@ def test_errors_are_loud(ctx):
         capi.pack_ascii(["ACGTX"])
     with pytest.raises(capi.TaxorError):
         capi.Context(4096)
+
+
+def test_baseline_config0_exactly_as_defined(ctx, oracle):
+    """BASELINE.json configs[0] as SURVEY 8(d) defines it: 100 genomes x 5,000,000 bp (i.i.d. uniform, genome g from seed
+    1000+g), k=22 s=12 t=5 syncmers; 10,000 reads x 10,000 bp (genome, start, strand uniform; 5 % errors, 1/3 each
+    substitution / insertion / deletion; read seed 42); --error-rate 0.05 (ratio 0.437803).  The genomes are hashed by the
+    GPU build-side entry point (spot-checked against the oracle), the HIXF is peeled on the CPU, every read's hash count,
+    threshold, hits and counts are compared with the oracle."""
+    from taxor_b200 import tools
+    n_g, glen = 100, 5_000_000
+    genomes = [tools.genome(1000 + g, glen) for g in range(n_g)]
+    lens = [glen] * n_g
+    ctx.set_params(k=22, s=12, t=5, use_syncmer=True, window_size=20, error_rate=0.05)
+    nw = np.array([len(w) for w in genomes], dtype=np.uint64)
+    off = np.zeros(n_g, dtype=np.uint64)
+    off[1:] = np.cumsum(nw)[:-1]
+    seqs = capi.PackedReads(np.concatenate(genomes), off, np.full(n_g, glen, np.uint32))
+    boff, hashes, n_seg = ctx.hash_user_bins(seqs, np.arange(n_g, dtype=np.uint32), n_g)
+    ub = [hashes[int(boff[i]):int(boff[i + 1])] for i in range(n_g)]
+    assert n_seg > n_g                                           # long genomes were cut into independently hashed segments
+    for g in (0, 57):                                            # the GPU's sets against the oracle's scan of the whole genome
+        exp = oracle.syncmer_hashes(H.codes_of(genomes[g], glen), 22, 12, 5)
+        assert np.array_equal(np.sort(ub[g]), np.sort(exp))
+    assert 8.5e6 < sum(len(x) for x in ub) < 9.7e6               # "about 9.1 M distinct hashes"
+    hx = tools.BuiltHixf(ub, t_max=64, seed=1)
+    from oracle.oracle import HixfArrays
+    arrays = HixfArrays(hx.seed, hx.bins, hx.tbins, hx.seg_len, hx.data, hx.bin_off, hx.next_ixf_id, hx.bin_to_ub, hx.rows)
+    ds = H.Dataset(22, 12, 5, True, genomes, lens, hx, arrays)
+    words, roff, rlen, _ = tools.simulate_reads(genomes, lens, np.full(10_000, 10_000), 0.05, 42)
+    reads = capi.PackedReads(words, roff, rlen)
+    codes, coff = H.reads_to_codes(reads)
+    oh = oracle.make_hixf(arrays)
+    H.upload(ctx, ds)
+    for er in (0.05, 0.10):                                      # as defined, and the rate at which reads actually classify
+        ctx.set_params(k=22, s=12, t=5, use_syncmer=True, window_size=20, error_rate=er)
+        res = ctx.search(reads)
+        ora = oracle.search_batch(oh, codes, coff, k=22, s=12, t=5, use_syncmer=True, window_size=20, error_rate=er)
+        H.assert_same_search(res, ora, reads.n)
+        if er == 0.05:
+            assert abs(int(res.threshold[0]) / max(int(res.hash_count[0]), 1) - 0.437803) < 2e-3
+        else:
+            assert int(res.hit_begin[-1]) > 3000
+    hx.close()
