@@ -10,6 +10,8 @@ run() { tag=$1; shift; env "$@" $B > gpurun_out/r2c_$tag.json 2> gpurun_out/r2c_
 run q7 TXR_QUERY_CTAS_PER_SM=7
 run q6 TXR_QUERY_CTAS_PER_SM=6
 run fused TXR_FUSE_DEDUP=1
+run s64_all TXR_L2_SECTOR64=1
+run s64_lv TXR_L2_SECTOR64=2
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2c_bench_ref.json 2> gpurun_out/r2c_bench_ref.err; cut -c1-600 gpurun_out/r2c_bench_ref.json
 S="python bench.py --reads 524288 --steps 1 --warmup 1 --no-cpu-baseline"
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"kernel" -c 400 --csv --log-file gpurun_out/r2c_launches.csv $S > gpurun_out/r2c_ncu_bench.json 2> gpurun_out/r2c_ncu.err

@@ -21,6 +21,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <sys/mman.h>
 #include <thread>
 #include <vector>
 
@@ -39,6 +40,7 @@ cudaError_t launch_filter(const DedupArgs &a, cudaStream_t st);
 cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_query_large(const QueryArgs &a, int sm_count, uint32_t max_tbins, cudaStream_t st);
 uint32_t query_large_max_tbins();
+size_t pack_plain_words(const char *ascii, size_t n_words, uint64_t *dst); // pack_simd.cpp
 cudaError_t launch_sort_items(const uint2 *items, const uint32_t *n_ptr, uint32_t cap, uint32_t *hist, uint32_t n_ixf, uint2 *out,
                               int sm_count, cudaStream_t st);
 cudaError_t launch_root_partitioned(const QueryArgs &q, const RootPartArgs &a, int sm_count, cudaStream_t st);
@@ -284,6 +286,10 @@ struct txr_ctx
     // bound, so the claim rounds cost more there than in the 24-warp dedup kernel; neither side is DRAM bound, the saved
     // 15 GB round trip buys nothing.
     bool fuse_dedup{false};
+    // .L2::64B loads for 64-byte rows (TXR_L2_SECTOR64: 0 off, 1 all levels, 2 below the root only).  On: the rows of a T = 64
+    // index then cost two DRAM sectors instead of a 128-byte line; the step gains little (93.5 -> 92.9 ms, the root level is bound by
+    // random accesses per second, not by bytes) but the DRAM traffic per probe byte drops from 1.8x to about 1x.
+    uint32_t l2_sector64{1};
     uint32_t query_unroll{0};  // TXR_QUERY_UNROLL: probe steps in flight per warp (experiments with fewer probe CTAs per SM)
     uint32_t fuse_max_keys{kWarpMaxKeys}; // TXR_FUSE_MAX_KEYS lowers it (tests: forces the hand-over to the CTA-per-read kernel)
     int root_partition{0};     // root level grouped by segment-0 slot: 0 off (default: measured slower), 1 auto, 2 always (TXR_ROOT_PARTITION)
@@ -653,6 +659,7 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
     q.stat_skipped = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 4);
     q.early_exit = c->early_exit;
     q.unroll = c->query_unroll;
+    q.l2_sector64 = c->l2_sector64 == 1;
     q.generic = ix.generic;
     q.scheme = ix.scheme;
     q.smf = c->smf_query;
@@ -724,6 +731,7 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
                 CU(launch_sort_items(raw, lc + 0, s.queue_cap, s.ixf_hist.as<uint32_t>(), (uint32_t)ix.ixf.size(), sorted, c->sm_count, cs));
             q.items = c->sort_items ? sorted : raw;
             q.l2_hints = c->sort_items && c->l2_hints;
+            q.l2_sector64 = c->l2_sector64 != 0;
             q.n_items_ptr = lc + 0;
             q.cursor = lc + 2;
             CU(launch_query_small(q, c->sm_count, cs));
@@ -1117,6 +1125,8 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->early_exit = atoi(e) != 0;
     if (const char *e = getenv("TXR_L2_HINTS"))
         c->l2_hints = atoi(e) != 0;
+    if (const char *e = getenv("TXR_L2_SECTOR64"))
+        c->l2_sector64 = (uint32_t)atoi(e);
     if (const char *e = getenv("TXR_QUERY_UNROLL"))
         c->query_unroll = (uint32_t)atoi(e);
     if (const char *e = getenv("TXR_FUSE_DEDUP"))
@@ -1200,7 +1210,7 @@ static int upload_fingerprints(txr_ctx *c, const txr_hixf_view *v, DeviceIndex &
     {
         uint64_t ixf, row0, rows;
     };
-    constexpr uint64_t kStage = 16ull << 20;
+    constexpr uint64_t kStage = 4ull << 20; // pinned staging is allocated per upload: 2 x 4 MB per worker keeps that under ~30 ms
     const bool bin_major = v->scheme && v->scheme->layout == TXR_IXF_LAYOUT_BIN_MAJOR;
     std::vector<Piece> pieces;
     uint64_t total = 0;
@@ -1262,6 +1272,16 @@ static int upload_fingerprints(txr_ctx *c, const txr_hixf_view *v, DeviceIndex &
                 break;
             }
             const uint8_t *src = x.fp + pc.row0 * x.tbins;
+#ifdef MADV_POPULATE_READ
+            if (!bin_major)
+            {
+                // the source is typically a fresh mmap of the .hixf: map the piece's pages in one go instead of taking a
+                // minor fault every 4 KB inside the memcpy (a hint -- errors, e.g. from older kernels, are ignored)
+                const uintptr_t lo = reinterpret_cast<uintptr_t>(src) & ~uintptr_t(4095);
+                const uintptr_t hi = reinterpret_cast<uintptr_t>(src) + pc.rows * x.tbins;
+                madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_POPULATE_READ);
+            }
+#endif
             if (bin_major)
             {
                 // fp[bin * rows + slot] -> rows of `stride` bytes (HBM is always slot-major: one probe = three rows)
@@ -1627,6 +1647,16 @@ int txr_pack_2bit(const char *ascii, uint64_t len, uint64_t *dst)
     uint64_t i = 0;
     for (uint64_t w = 0; w + 1 < nw; ++w)
     {
+        if (len - i >= 32) // whole words of plain ACGT/acgt take the SIMD lane; it stops at the first word with anything else
+        {
+            const size_t done = txr::pack_plain_words(ascii + i, (size_t)((len - i) / 32), dst + w);
+            if (done)
+            {
+                w += done - 1;
+                i += 32 * (uint64_t)done;
+                continue;
+            }
+        }
         uint64_t x = 0;
         const uint64_t end = std::min<uint64_t>(len, i + 32);
         int sh = 62;

@@ -36,6 +36,17 @@ __device__ __forceinline__ uint4 ldg_row16(const uint8_t *p)
     return r;
 }
 
+// the same load with the 64-byte L2 prefetch-size hint: a miss then brings two sectors from DRAM instead of the whole 128-byte
+// line (ncu: half the dram__bytes for 64-byte rows, profiles/r1_gather_bench2_ncu.txt).  Rows of T = 64 indexes only.
+__device__ __forceinline__ uint4 ldg_row16_s64(const uint8_t *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
 // 0x01 in every byte of x that is zero (exact, no carries across bytes)
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
 {
@@ -81,11 +92,13 @@ struct L2Plan
 {
     bool split;        // segment 0 evict_last, segments 1 and 2 evict_first
     uint64_t keep, stream;
+    bool sector64;     // 64-byte rows: ask L2 for 64 bytes per miss, not for the 128-byte line
 };
 constexpr uint64_t kL2KeepBytes = 28ull << 20;
-__device__ __forceinline__ L2Plan l2_plan_for(const IxfDev &d, bool enabled)
+__device__ __forceinline__ L2Plan l2_plan_for(const IxfDev &d, bool enabled, bool sector64 = false)
 {
     L2Plan p;
+    p.sector64 = sector64 && d.tbins == 64;
     p.split = enabled && (uint64_t)d.seg_len * d.tbins <= kL2KeepBytes && (uint64_t)d.seg_len * d.tbins * 3 > kL2KeepBytes;
     p.keep = l2_policy_evict_last();
     p.stream = l2_policy_evict_first();
@@ -114,7 +127,7 @@ __device__ __forceinline__ uint32_t probe_address(const IxfDev &d, const IxfSche
 
 template <bool GEN>
 __device__ __forceinline__ void probe_issue(Probe &p, const IxfDev &d, const IxfScheme &sch, const uint8_t *col_base, uint64_t key,
-                                            bool live, const L2Plan &l2 = L2Plan{false, 0, 0})
+                                            bool live, const L2Plan &l2 = L2Plan{false, 0, 0, false})
 {
     p.live = live;
     if (live)
@@ -126,6 +139,12 @@ __device__ __forceinline__ void probe_issue(Probe &p, const IxfDev &d, const Ixf
             p.r0 = ldg_row16_hint(col_base + (uint64_t)p0 * d.tbins, l2.keep);
             p.r1 = ldg_row16_hint(col_base + (uint64_t)p1 * d.tbins, l2.stream);
             p.r2 = ldg_row16_hint(col_base + (uint64_t)p2 * d.tbins, l2.stream);
+        }
+        else if (l2.sector64)
+        {
+            p.r0 = ldg_row16_s64(col_base + (uint64_t)p0 * d.tbins);
+            p.r1 = ldg_row16_s64(col_base + (uint64_t)p1 * d.tbins);
+            p.r2 = ldg_row16_s64(col_base + (uint64_t)p2 * d.tbins);
         }
         else
         {
@@ -194,7 +213,7 @@ __device__ __forceinline__ uint32_t max_byte4(const uint32_t (&acc)[4])
 template <int UNROLL, bool GEN>
 __device__ __forceinline__ uint32_t probe_chunk(const IxfDev &d, const IxfScheme &sch, const uint64_t *__restrict__ hp, uint32_t H,
                                                 uint32_t chunk_off, uint32_t lpr, uint32_t *cnt, int lane,
-                                                const L2Plan &l2 = L2Plan{false, 0, 0}, uint64_t exit_thr = 0)
+                                                const L2Plan &l2 = L2Plan{false, 0, 0, false}, uint64_t exit_thr = 0)
 {
     const uint32_t G = 32u / lpr;         // hashes per step
     const uint32_t sub = (uint32_t)lane / lpr;
@@ -389,7 +408,7 @@ __global__ void __launch_bounds__(32 * kQueryWarps, MINB) ixf_query_small_kernel
         const uint64_t *hp = a.hashes + a.hash_off[read];
         const uint64_t thr = a.thr_read ? a.thr_read[read] : (H < a.lut_len ? a.thr_lut[H] : ~0ULL);
         const uint32_t Hp = probe_chunk<UNROLL, GEN>(d, a.scheme, hp, H, 0u, d.tbins >> 4, cnt, lane,
-                                                     l2_plan_for(d, a.l2_hints != 0), a.early_exit ? thr : 0);
+                                                     l2_plan_for(d, a.l2_hints != 0, a.l2_sector64 != 0), a.early_exit ? thr : 0);
         __syncwarp();
         scan_bins(a, d, read, thr, cnt, (uint32_t)lane, 32u);
         __syncwarp();

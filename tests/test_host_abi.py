@@ -134,3 +134,26 @@ def test_segment_cuts_are_history_free(oracle, built_libs, mode):
             parts = set(np.concatenate([oracle.minimiser_hashes(p, k, w) for p in pieces]).tolist())
             assert whole == parts                                   # a piece re-reports its first minimiser: equal as sets
     assert n_cut > 200                                              # the sequences really were cut, ties and all
+
+
+def test_pack_simd_lane_equals_table_lane(built_libs, oracle):
+    """txr_pack_2bit packs whole words of plain ACGT/acgt with AVX2+BMI2 (pack_simd.cpp) and everything else through the dna4
+    table: both lanes, mixed inside one read (an IUPAC code every few hundred bases, lower case, all lengths around the word
+    size), must give the words txr_pack_codes gives for the dna4 ranks; an illegal character is reported at its position"""
+    rng = np.random.default_rng(44)
+    iupac = "NRWMDHVYSBKUnrykm"
+    for n in list(range(0, 70)) + [95, 96, 97, 1000, 4099, 20_001]:
+        codes = rng.integers(0, 4, n, dtype=np.uint8)
+        chars = np.frombuffer(b"ACGT", dtype=np.uint8)[codes].copy()
+        lower = rng.random(n) < 0.3
+        chars[lower] |= 0x20
+        s = bytearray(chars.tobytes())
+        for pos in rng.integers(0, max(n, 1), n // 300 + (1 if n > 40 else 0)):
+            s[int(pos)] = ord(iupac[int(rng.integers(0, len(iupac)))])
+        text = s.decode()
+        want = np.array([oracle.dna4_rank(ch) for ch in text], dtype=np.uint8)
+        assert (want <= 3).all()
+        assert np.array_equal(capi.pack_ascii([text]).words, capi.pack_codes([want]).words), n
+    bad = "ACGT" * 50 + "J" + "ACGT" * 50
+    with pytest.raises(capi.TaxorError, match="0x4a at position 200"):
+        capi.pack_ascii([bad])
