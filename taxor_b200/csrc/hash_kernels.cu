@@ -1036,6 +1036,19 @@ __global__ void __launch_bounds__(32 * kDedupWarps) dedup_warp_kernel(DedupArgs 
             }
         }
         __syncwarp();
+        // Most reads have no repeated k-mer at all: every key was a first occurrence, the list is already the distinct set in
+        // place, and the second pass (another read and a write of the whole list) has nothing to do.
+        {
+            const uint32_t mine_n = n > (uint32_t)lane ? (n - (uint32_t)lane + 31u) / 32u : 0u; // keys this lane looked at
+            const bool clean = (uint32_t)__popcll(firsts) == mine_n;
+            if (a.scaling <= 1 && __all_sync(0xffffffffu, clean))
+            {
+                if (lane == 0)
+                    a.hash_count[r] = n;
+                __syncwarp();
+                continue;
+            }
+        }
         // pass 2: in-place compaction in first-occurrence order (a stage is loaded completely before it is written)
         uint32_t base = 0;
         for (uint32_t s0 = 0; s0 < n; s0 += 32 * kStage)

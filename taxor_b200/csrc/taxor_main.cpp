@@ -413,16 +413,28 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     // one upload over PCIe (staged, multi-threaded), then the other GPUs are filled device to device in a doubling
     // tree (round r: every context that has the index clones it into one that has not -- NVLink between peers), instead
     // of pushing the same 10-100 GB through the host once per GPU
-    std::vector<txr_ctx *> ctxs;
-    for (int d : devices)
-    {
-        txr_ctx *c = nullptr;
-        if (txr_ctx_create(d, &c) != TXR_OK)
-            throw std::runtime_error(std::string("GPU ") + std::to_string(d) + ": " + txr_last_error());
-        ctxs.push_back(c);
-    }
-    if (txr_index_upload(ctxs[0], &hv) != TXR_OK)
-        throw std::runtime_error(std::string("GPU ") + std::to_string(devices[0]) + ": " + txr_last_error());
+    // (creating a CUDA context costs a few hundred ms per device: the contexts of the other GPUs come up on their own
+    // threads while the first one takes the upload)
+    std::vector<txr_ctx *> ctxs(devices.size(), nullptr);
+    std::vector<std::string> ctx_err(devices.size());
+    auto make_ctx = [&](size_t i) {
+        if (txr_ctx_create(devices[i], &ctxs[i]) != TXR_OK)
+            ctx_err[i] = txr_last_error();
+    };
+    make_ctx(0);
+    std::vector<std::thread> ctx_threads;
+    for (size_t i = 1; i < devices.size(); ++i)
+        ctx_threads.emplace_back(make_ctx, i);
+    std::string up_err;
+    if (ctx_err[0].empty() && txr_index_upload(ctxs[0], &hv) != TXR_OK)
+        up_err = txr_last_error();
+    for (auto &t : ctx_threads)
+        t.join();
+    for (size_t i = 0; i < devices.size(); ++i)
+        if (!ctx_err[i].empty())
+            throw std::runtime_error(std::string("GPU ") + std::to_string(devices[i]) + ": " + ctx_err[i]);
+    if (!up_err.empty())
+        throw std::runtime_error(std::string("GPU ") + std::to_string(devices[0]) + ": " + up_err);
     for (size_t have = 1; have < ctxs.size(); have *= 2)
     {
         std::vector<std::thread> th;
