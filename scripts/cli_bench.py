@@ -54,6 +54,8 @@ def main():
     ap.add_argument("--threads", type=int, default=16)
     ap.add_argument("--gz", action="store_true", help="also time a gzip-compressed copy of the reads")
     ap.add_argument("--bgzf", action="store_true", help="also time a BGZF (bgzip-style blocked gzip) copy of the reads")
+    ap.add_argument("--bz2", action="store_true", help="also time a bzip2 copy of the first --bz2-reads reads (libbz2 is one stream, ~100 MB/s)")
+    ap.add_argument("--bz2-reads", type=int, default=20_000)
     ap.add_argument("--gpus", default="1", help="--gpus of the CLI; a comma list of counts runs every one (e.g. 1,2,8)")
     args = ap.parse_args()
     from taxor_b200 import capi, tools
@@ -96,7 +98,21 @@ def main():
         if not os.path.exists(bg):
             write_bgzf(fq, bg)
         files.append(("fastq.bgzf", bg))
-    def one(tag, path, th, gpus, extra_env=None):
+    bz = None
+    if args.bz2:
+        import bz2
+        from concurrent.futures import ThreadPoolExecutor
+        bz = fq + f".first{args.bz2_reads}.bz2"
+        if not os.path.exists(bz):
+            # the first reads of the FASTQ, compressed as concatenated streams of ~64 k lines (what pbzip2 writes)
+            with open(fq, "rb") as f:
+                lines = [f.readline() for _ in range(4 * args.bz2_reads)]
+            chunks = [b"".join(lines[i:i + 65536]) for i in range(0, len(lines), 65536)]
+            with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex, open(bz, "wb") as out:
+                for c in ex.map(lambda x: bz2.compress(x, 1), chunks):
+                    out.write(c)
+
+    def one(tag, path, th, gpus, extra_env=None, n_reads=None):
         out = os.path.join(args.work, "out.tsv")
         env = dict(os.environ, TAXOR_TIMING="1", **(extra_env or {}))
         t0 = time.time()
@@ -110,7 +126,7 @@ def main():
         return {"wall_s": round(wall, 2), "index_load_s": load, "index_upload_s": upload, "index_GB": gb, "gpus": gpus,
                 "upload_GBps_per_copy": round(gb / max(upload, 1e-9), 1),
                 "ingest_search_write_s": search, "file_GB": round(os.path.getsize(path) / 1e9, 2),
-                "Mbases_per_s_search_phase": round(args.reads * args.read_len / search / 1e6),
+                "Mbases_per_s_search_phase": round((n_reads or args.reads) * args.read_len / search / 1e6),
                 "hit_lines": sum(1 for line in open(out) if "\t-\t-\t" not in line) - 1}
     gpu_counts = [int(x) for x in str(args.gpus).split(",")]
     for tag, path in files:
@@ -121,6 +137,8 @@ def main():
     runs["fastq_serial_upload"] = one("fastq", fq, args.threads, gpu_counts[0], {"TXR_UPLOAD_THREADS": "1"})
     for g in gpu_counts[1:]:
         runs[f"fastq_gpus{g}"] = one("fastq", fq, args.threads, g)
+    if bz:
+        runs[f"fastq.bz2_first{args.bz2_reads}_threads{args.threads}"] = one("fastq.bz2", bz, args.threads, gpu_counts[0], n_reads=args.bz2_reads)
     print(json.dumps({"what": "taxor search CLI end to end (file -> file), 1 GPU", "reads": args.reads, "read_len": args.read_len,
                       "hixf_write_s": round(t_write, 1), "host_cores": os.cpu_count(), "runs": runs}))
 

@@ -48,6 +48,7 @@ struct HashArgs
     SmFilter smf;
     int ctas_per_sm;           // host side: CTAs per SM of the persistent grid (0: fill the SM)
     int window;                // minimiser mode: k-mer values per window, window_size - k + 1 (2..kMaxMinimiserValues)
+    int min_blocks;            // host side: register variant of the syncmer kernel (0/4 default, 5 = 102 registers)
     // fused per-read distinct set (syncmer_kernel only; the ankerl::set of syncmer.cpp:145 built while hashing):
     uint32_t fuse_dedup;       // 1: reads whose capacity is <= kFuseMaxCap write DISTINCT hashes + hash_count directly
     uint32_t fuse_max_keys;    // distinct keys the warp table takes before the read is handed over (<= kWarpMaxKeys; tests lower it)

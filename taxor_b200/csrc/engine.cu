@@ -290,6 +290,7 @@ struct txr_ctx
     // index then cost two DRAM sectors instead of a 128-byte line; the step gains little (93.5 -> 92.9 ms, the root level is bound by
     // random accesses per second, not by bytes) but the DRAM traffic per probe byte drops from 1.8x to about 1x.
     uint32_t l2_sector64{1};
+    int hash_regs{0};          // TXR_HASH_REGS=5: the 102-register variant of the syncmer kernel (5 CTAs per SM)
     uint32_t query_unroll{0};  // TXR_QUERY_UNROLL: probe steps in flight per warp (experiments with fewer probe CTAs per SM)
     uint32_t fuse_max_keys{kWarpMaxKeys}; // TXR_FUSE_MAX_KEYS lowers it (tests: forces the hand-over to the CTA-per-read kernel)
     int root_partition{0};     // root level grouped by segment-0 slot: 0 off (default: measured slower), 1 auto, 2 always (TXR_ROOT_PARTITION)
@@ -553,6 +554,7 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     h.window = (int)c->params.window_size - (int)c->params.kmer_size + 1;
     h.smf = c->smf_hash;
     h.ctas_per_sm = c->shape_hash;
+    h.min_blocks = c->hash_regs;
     // the distinct set of a read (syncmer.cpp:145) is built while hashing whenever the templated kernel runs: no raw list
     // round trip through HBM for the reads of the `ids_small` class
     const bool fused = dedup && c->fuse_dedup && c->params.use_syncmer &&
@@ -1127,6 +1129,8 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->l2_hints = atoi(e) != 0;
     if (const char *e = getenv("TXR_L2_SECTOR64"))
         c->l2_sector64 = (uint32_t)atoi(e);
+    if (const char *e = getenv("TXR_HASH_REGS"))
+        c->hash_regs = atoi(e);
     if (const char *e = getenv("TXR_QUERY_UNROLL"))
         c->query_unroll = (uint32_t)atoi(e);
     if (const char *e = getenv("TXR_FUSE_DEDUP"))
@@ -1705,7 +1709,10 @@ int txr_unpack_codes(const uint64_t *words, uint64_t len, uint8_t *codes)
 void *txr_host_alloc(size_t bytes)
 {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+    // TXR_HOST_WC=1: write-combined pinned memory (the CPU only ever streams packed reads INTO these buffers; DMA reads of
+    // write-combined memory skip the cache snoop).  An experiment knob for the many-GPU end-to-end curve; CPU reads are slow.
+    static const bool wc = getenv("TXR_HOST_WC") && atoi(getenv("TXR_HOST_WC")) != 0;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess)
     {
         set_error(TXR_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes);
         return nullptr;

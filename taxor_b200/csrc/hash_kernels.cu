@@ -275,8 +275,10 @@ __device__ bool resolve_tie_local(const uint64_t *w, const uint32_t *sv, uint64_
 }
 } // namespace
 
-template <int K, int S, int T>
-__global__ void __launch_bounds__(32 * kHashWarps, 4) syncmer_kernel(HashArgs a)
+// MINB: CTAs per SM the register allocation has to allow (4: 124 registers, no spills; 5: 102 registers, experiment knob
+// TXR_HASH_REGS=5 -- more warps for an issue-bound kernel against a few spills)
+template <int K, int S, int T, int MINB>
+__global__ void __launch_bounds__(32 * kHashWarps, MINB) syncmer_kernel(HashArgs a)
 {
     if (!sm_filter_keep(a.smf))
         return;
@@ -1269,9 +1271,14 @@ static bool try_launch_syncmer(const HashArgs &a, int k, int s, int t, int grid,
     if (k != K || s != S || t != T)
         return false;
     const size_t smem = a.fuse_dedup ? (size_t)kHashWarps * kWarpSlots * 4 : 0;
+    if (a.min_blocks >= 5 && !smem)
+    {
+        syncmer_kernel<K, S, T, 5><<<grid, 32 * kHashWarps, 0, st>>>(a);
+        return true;
+    }
     if (smem) // static + dynamic shared memory exceed 48 KB; the attribute is per device, so it is set on every launch
-        cudaFuncSetAttribute(syncmer_kernel<K, S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    syncmer_kernel<K, S, T><<<grid, 32 * kHashWarps, smem, st>>>(a);
+        cudaFuncSetAttribute(syncmer_kernel<K, S, T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    syncmer_kernel<K, S, T, 4><<<grid, 32 * kHashWarps, smem, st>>>(a);
     return true;
 }
 

@@ -403,9 +403,13 @@ int txs_reads(const uint64_t *const *genome_words, const uint64_t *genome_len, u
         const uint64_t start = splitmix64(st) % (G - span + 1);
         const bool rev = splitmix64(st) & 1;
         const uint64_t *gw = genome_words[g];
-        uint64_t *dst = words + word_off[r];
+        // built in a thread-local buffer and copied out once: the destination may be write-combined pinned memory
+        // (TXR_HOST_WC=1), where a read-modify-write per base would be an uncached read per base
+        uint64_t *out_words = words + word_off[r];
         const uint64_t nw = packed_words(L);
-        std::memset(dst, 0, nw * 8);
+        thread_local std::vector<uint64_t> local;
+        local.assign(nw, 0);
+        uint64_t *dst = local.data();
         uint64_t src = 0; // offset inside the source window (in read orientation)
         uint32_t produced = 0;
         while (produced < L && src < span)
@@ -433,6 +437,7 @@ int txs_reads(const uint64_t *const *genome_words, const uint64_t *genome_len, u
             dst[produced >> 5] |= (uint64_t)b << (62 - 2 * (produced & 31));
             ++produced;
         }
+        std::memcpy(out_words, dst, nw * 8);
         if (produced < L)
             bad = 1;
         if (out_genome)
