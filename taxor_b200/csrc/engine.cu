@@ -1772,36 +1772,50 @@ static int search_host_impl(txr_ctx *c, const uint64_t *words, const uint64_t *w
     TRY(check_ready(c));
     if (!words || !word_off || !len || !out)
         return set_error(TXR_ERR_ARG, "null argument");
-    TRY(validate_reads(word_off, len, n_reads));
     c->result.clear();
     c->timing = txr_timing{};
     const auto t0 = std::chrono::steady_clock::now();
     TRY(fork_streams(c));
-    std::vector<std::pair<uint64_t, uint32_t>> plan;
-    plan_batches(c, len, n_reads, plan, c->n_slots > 1);
     metas.resize(c->n_slots);
     const size_t S = (size_t)c->n_slots;
-    for (size_t b = 0; b < plan.size() + S - 1; ++b)
+    // Batches are planned and validated one at a time, right before they are submitted: two passes over a million reads in
+    // front of the first copy were 2 ms in which the GPU had nothing to do (the same rule as plan_batches, ramp included).
+    double scale = c->n_slots > 1 ? 1.0 / 16.0 : 1.0;
+    uint64_t next_read = 0;
+    for (size_t b = 0; next_read < n_reads; ++b)
     {
-        if (b >= S - 1 && b - (S - 1) < plan.size())
+        if (b >= S - 1)
         {
             Slot &done = *c->slots[(b - (S - 1)) % S];
             if (done.busy)
                 TRY(collect_batch(c, done, true));
         }
-        if (b < plan.size())
-        {
-            Slot &s = *c->slots[b % S];
-            if (s.busy)
-                TRY(collect_batch(c, s, true));
-            BatchMeta &m = metas[b % S];
-            build_batch_meta(c, word_off, len, plan[b].first, plan[b].second, m);
-            TRY(submit_batch(c, s, m, nullptr, nullptr, words, true));
-        }
+        const uint64_t max_reads = std::max<uint64_t>((uint64_t)((double)c->max_batch_reads * scale), 1);
+        const uint64_t max_bases = std::max<uint64_t>((uint64_t)((double)c->max_batch_bases * scale), 1);
+        uint64_t bases = 0, j = next_read;
+        while (j < n_reads && j - next_read < max_reads && (j == next_read || bases + len[j] <= max_bases))
+            bases += len[j++];
+        scale = std::min(1.0, scale * 1.8);
+        TRY(validate_reads(word_off + next_read, len + next_read, std::min<uint64_t>(j - next_read + 1, n_reads - next_read)));
+        Slot &s = *c->slots[b % S];
+        if (s.busy)
+            TRY(collect_batch(c, s, true));
+        BatchMeta &m = metas[b % S];
+        build_batch_meta(c, word_off, len, next_read, (uint32_t)(j - next_read), m);
+        TRY(submit_batch(c, s, m, nullptr, nullptr, words, true));
+        next_read = j;
     }
-    for (auto &s : c->slots)
-        if (s->busy)
-            TRY(collect_batch(c, *s, true));
+    // the batches still in flight, oldest first (slots are used round robin)
+    for (size_t k = 0; k < S; ++k)
+    {
+        Slot *oldest = nullptr;
+        for (auto &sl : c->slots)
+            if (sl->busy && (!oldest || sl->bm->first_read < oldest->bm->first_read))
+                oldest = sl.get();
+        if (!oldest)
+            break;
+        TRY(collect_batch(c, *oldest, true));
+    }
     TRY(join_streams(c));
     finish_result(c, out);
     c->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
