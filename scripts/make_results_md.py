@@ -27,13 +27,14 @@ def bench_row(tag, d):
 
 def main():
     out = []
-    final = load("r1_final_bench.json")
+    final = load("r2_e_bench.json") or load("r2_c_bench.json")
     if final:
         out.append("| workload (1 × B200) | value Gbases/s | ms/step | hash / dedup / query ms | e2e Gbases/s | e2e ms/step | kernel #2 GB/s | frac of measured HBM | CPU port Gbases/s |")
         out.append("|---|---|---|---|---|---|---|---|---|")
-        out.append(bench_row("configs[1], 10.15 GB index, 1 M × 10 kb (`r1_final_bench.json`)", final))
-        for name, tag in (("r1_bench_kmer.json", "configs[3] k-mer mode, 1 M reads 1–50 kb (`r1_bench_kmer.json`)"),
-                          ("r1_bench_deep.json", "three-level hierarchy, 20,000 genomes (`r1_bench_deep.json`)")):
+        out.append(bench_row("configs[1], 10.15 GB index, 1 M × 10 kb (`r2_e_bench.json`)", final))
+        for name, tag in (("r2_e_bench_kmer.json", "configs[3] k-mer mode, 1 M reads 1–50 kb (`r2_e_bench_kmer.json`)"),
+                          ("r2_e_bench_deep.json", "three-level hierarchy, 20,000 genomes, T = 64 (`r2_e_bench_deep.json`)"),
+                          ("r2_e_bench_gtdb.json", "configs[4] shape: 102,400 user bins, 4096-bin root, 9.7 GB, 250 k reads per step (`r2_e_bench_gtdb.json`)")):
             d = load(name)
             if d:
                 out.append(bench_row(tag, d))
@@ -45,27 +46,31 @@ def main():
                    f"early exit skips {r.get('early_exit_skipped_hashes_per_step', 0) / 1e6:.0f} M of "
                    f"{(r.get('early_exit_skipped_hashes_per_step', 0) + r['algorithmic_bytes_per_step'] / 200) / 1e6:.0f} M probes per step; "
                    f"`traffic` {(r.get('traffic') or 0) / 1e9:.1f} GB per probe launch for {r.get('algorithmic_bytes_per_launch', 0) / 1e9:.1f} GB of probe bytes.")
-    ref = load("r1_final_bench_reference_arm.json")
+    ref = load("r2_e_bench_reference_arm.json") or load("r2_c_bench_reference_arm.json")
     if ref and final:
-        out.append(f"Reference arm (`bench.py --impl reference`, the restated CPU path on {ref['cpu_baseline']['cores']} host cores): "
-                   f"{ref['value'] / 1e3:.2f} Gbases/s ⇒ e2e ≈ {final['e2e']['value'] / ref['value']:.0f}× (reported baseline, not the target).")
-    n2, n1 = load("r1_bench_n2_1GBindex.json"), load("r1_bench_n1_1GBindex.json")
+        v = ref["cpu_baseline"].get("variants", {})
+        out.append(f"Reference arm (`bench.py --impl reference`: the restated CPU path built with `-O3 -march=native -ffp-contract=off` on the "
+                   f"bench box, {ref['cpu_baseline']['cores']} host cores, bulk_count with software prefetch + {ref['cpu_baseline'].get('simd', '?')} compares): "
+                   f"{ref['value'] / 1e3:.2f} Gbases/s (the reference's per-value loop restated as is: {v.get('port', {}).get('value', 0) / 1e3:.2f}) "
+                   f"⇒ e2e ≈ {final['e2e']['value'] / ref['value']:.0f}× the tuned CPU arm (reported baseline, not the target).")
+    n2, n1 = load("r2_d_bench_n2.json"), load("r2_d_bench_n1.json")
     if n2 and n1:
-        out.append(f"2 × B200 under torchrun (weak scaling, plumbing check on a 1 GB index, `r1_bench_n2_1GBindex.json`): value "
+        out.append(f"2 × B200 under torchrun (weak scaling, configs[1] index, `r2_d_bench_n2.json`; parity on both ranks: "
+                   f"{n2['parity_at_scale']['reads']} reads, {n2['parity_at_scale']['mismatches']} mismatches): value "
                    f"{n2['value'] / 1e3:.1f} Gbases/s, e2e {n2['e2e']['value'] / 1e3:.1f} Gbases/s against {n1['value'] / 1e3:.1f} / "
                    f"{n1['e2e']['value'] / 1e3:.1f} on one GPU of the same box ({n2['ms_per_step']:.1f} vs {n1['ms_per_step']:.1f} ms per step).")
-    cli = load("r1_cli_bench.json")
+    cli = load("r2_e_cli_bench.json") or load("r2_d_cli_bench_gpus1_2.json")
     if cli:
         out.append("")
-        out.append("CLI, file → file (`scripts/cli_bench.py`, `r1_cli_bench.json`; 10.15 GB `.hixf` and reads in /dev/shm, 1 GPU):")
+        out.append("CLI, file → file (`scripts/cli_bench.py`, `r2_e_cli_bench.json`; 10.15 GB `.hixf` and reads in /dev/shm, 1 GPU unless stated):")
         out.append("")
         out.append("| input | pack threads | index load (mmap) s | upload s | ingest+search+write s | Gbases/s in that phase | wall s |")
         out.append("|---|---|---|---|---|---|---|")
         for k, v in cli["runs"].items():
-            tag, th = k.rsplit("_threads", 1)
-            out.append(f"| {tag} {v['file_GB']} GB | {th} | {v['index_load_s']:.3f} | {v['index_upload_s']:.2f} | {v['ingest_search_write_s']:.2f} | "
+            tag, th = k.rsplit("_threads", 1) if "_threads" in k else (k, "16")
+            out.append(f"| {tag} {v['file_GB']} GB{' (' + str(v['gpus']) + ' GPUs)' if v.get('gpus', 1) > 1 else ''} | {th} | {v['index_load_s']:.3f} | {v['index_upload_s']:.2f} | {v['ingest_search_write_s']:.2f} | "
                        f"{v['Mbases_per_s_search_phase'] / 1e3:.2f} | {v['wall_s']:.1f} |")
-    cli2 = load("r1_cli_bench_1GBindex_bgzf.json")
+    cli2 = None
     if cli2:
         out.append("")
         out.append("Same script on a 1 GB index with a BGZF copy of the reads (`r1_cli_bench_1GBindex_bgzf.json`):")
