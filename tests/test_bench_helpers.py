@@ -51,3 +51,47 @@ def test_index_depth_from_cached_arrays(oracle, tmp_path):
     ix = bench.LoadedIndex(d)
     assert ix.n_ixf == ds.hixf.n_ixf and ix.n_user_bins == 70 and ix.depth >= 3
     assert all(np.array_equal(a, b) for a, b in zip(ix.data, ds.hixf.data))
+
+
+def test_gtdb_preset_and_cache_tag(monkeypatch):
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "gtdb"])
+    a = bench.parse_args()
+    assert (a.genomes, a.t_max, a.t_max_lower, a.reads, a.genome_len) == (102_400, 4096, 16, 250_000, 100_000)
+    d, _ = bench.index_cache_paths(a)
+    assert d.endswith("_tl16")
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "gtdb", "--reads", "5000", "--t-max", "1024"])
+    a = bench.parse_args()
+    assert (a.reads, a.t_max, a.t_max_lower) == (5000, 1024, 16)
+
+
+def test_at_scale_comparison_flags_every_kind_of_difference(oracle):
+    """bench.compare_with_oracle (the parity_at_scale check of every rank): equal answers pass, and a difference in any of hash
+    count, threshold, hit offsets, user bins or counts is counted -- exercised with the oracle on both sides"""
+    from tests import helpers as H
+    ds = H.make_dataset(oracle, n_genomes=20, genome_len=30_000, t_max=4)
+    reads = H.make_reads(ds, np.random.default_rng(3).integers(300, 6000, 120), err=0.04)
+    codes, off = H.reads_to_codes(reads)
+    ora = oracle.search_batch(oracle.make_hixf(ds.arrays), codes, off, k=22, s=12, t=5, use_syncmer=True, window_size=20, error_rate=0.1)
+
+    class G:                                                   # what capi.SearchResult exposes, built from the oracle's raw output
+        pass
+    g = G()
+    g.hash_count, g.threshold = ora["hash_count"].copy(), ora["threshold"].copy()
+    g.hit_begin, g.user_bin, g.count = ora["raw_off"].copy(), ora["raw_ub"].copy(), ora["raw_cnt"].copy()
+    keep = np.zeros(len(g.count), bool)
+    for r in range(reads.n):
+        a, b = int(g.hit_begin[r]), int(g.hit_begin[r + 1])
+        if b > a:
+            keep[a:b] = ~(g.count[a:b].astype(np.float64) < float(g.count[a:b].max()) * 0.8)
+    g.keep = keep
+    n = reads.n
+    assert bench.compare_with_oracle(g, ora, n)["ok"]
+    assert len(ora["ub"]) > 20
+    for field in ("hash_count", "threshold", "count", "user_bin"):
+        saved = getattr(g, field).copy()
+        getattr(g, field)[int(np.flatnonzero(keep)[0]) if field in ("count", "user_bin") else 5] += 1
+        p = bench.compare_with_oracle(g, ora, n)
+        assert not p["ok"] and p["mismatches"] >= 1, field
+        setattr(g, field, saved)
+    blk = bench.random_access_block({"query_ms": 10.0, "query_bytes": 200 * 1_000_000}, None, type("I", (), {"tbins": np.array([64])})(), None)
+    assert abs(blk["achieved_G_rows_per_s"] - 3 * 1_000_000 / 0.010 / 1e9) < 1e-9

@@ -552,3 +552,44 @@ def test_baseline_config0_exactly_as_defined(ctx, oracle):
         else:
             assert int(res.hit_begin[-1]) > 3000
     hx.close()
+
+
+def test_sharded_search_over_contexts_equals_one_context(oracle):
+    """the Python form of the multi-GPU driver (taxor_b200/shard.py: contiguous blocks, concatenation in read order) on real
+    contexts: shards searched on two devices (two contexts on device 0 where there is only one), merged, equal to one context
+    searching everything and to the oracle"""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from taxor_b200 import shard
+    ds = H.make_dataset(oracle, n_genomes=70, genome_len=40_000, t_max=16)
+    rng = np.random.default_rng(77)
+    reads = H.make_reads(ds, rng.integers(200, 9000, 1001), err=0.05)
+    world = 3
+    devs = [r % max(torch.cuda.device_count(), 1) for r in range(world)]
+    ctxs = [capi.Context(d) for d in devs]
+    try:
+        H.upload(ctxs[0], ds)
+        for c in ctxs[1:]:
+            c.clone_index_from(ctxs[0])
+        for c in ctxs:
+            c.set_params(k=ds.k, s=ds.s, t=ds.t, use_syncmer=True, window_size=20, error_rate=0.1)
+
+        def part(r):
+            lo, hi = shard.shard_range(reads.n, r, world)
+            w0 = int(reads.word_off[lo]) if lo < reads.n else 0
+            sub = capi.PackedReads(reads.words[w0:], reads.word_off[lo:hi] - np.uint64(w0), reads.length[lo:hi])
+            return shard.result_to_dict(ctxs[r].search(sub))
+        with ThreadPoolExecutor(max_workers=world) as ex:                      # one host thread per context, as in the CLI
+            parts = list(ex.map(part, range(world)))
+        merged = shard.concat_results(parts)
+        whole = shard.result_to_dict(ctxs[0].search(reads))
+        for k_ in whole:
+            assert np.array_equal(merged[k_], whole[k_]), k_
+        codes, off = H.reads_to_codes(reads)
+        ora = oracle.search_batch(oracle.make_hixf(ds.arrays), codes, off, k=ds.k, s=ds.s, t=ds.t, use_syncmer=True, window_size=20,
+                                  error_rate=0.1)
+        assert np.array_equal(merged["hit_begin"], ora["raw_off"]) and np.array_equal(merged["user_bin"], ora["raw_ub"])
+        assert np.array_equal(merged["count"], ora["raw_cnt"]) and int(merged["hit_begin"][-1]) > 200
+    finally:
+        for c in ctxs:
+            c.close()
