@@ -577,10 +577,28 @@ def main():
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     resident_ms = float(ms.item())
+
+    # (1b) kernel #2 on its own: the same reads with ONE pipeline slot, which turns the overlap off (the hash stage of the next
+    # batch no longer runs beside the probes) -- the stand-alone duration of the kernel the roofline is about.  Not part of `value`.
+    ctx.configure(n_slots=1, **batch_kw)
+    ctx.search_resident(h, fetch=False)
+    alone = {"hash_ms": 0.0, "dedup_ms": 0.0, "query_ms": 0.0, "query_bytes": 0, "probe_launches": 0, "total_ms": 0.0}
+    alone_steps = max(1, min(args.steps, 2))
+    with torch.cuda.stream(stream):
+        ev2a, ev2b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2a.record()
+        for _ in range(alone_steps):
+            ctx.search_resident(h, fetch=False)
+            tm = ctx.timing()
+            for kname in ("hash_ms", "dedup_ms", "query_ms", "query_bytes", "probe_launches"):
+                alone[kname] += tm[kname]
+        ev2b.record()
+    torch.cuda.synchronize()
+    alone["total_ms"] = ev2a.elapsed_time(ev2b)
     ctx.free_reads(h)
 
     # (2) end to end from pinned host buffers through txr_search (3 pipeline slots)
-    ctx.configure(n_slots=3, **batch_kw)
+    ctx.configure(n_slots=int(os.environ.get("TAXOR_BENCH_E2E_SLOTS", 4)), **batch_kw)
     for _ in range(max(1, min(args.warmup, 2))):
         ctx.search_raw(pin.ptr, off_pin.ptr, len_pin.ptr, n_reads)
     barrier()
@@ -692,7 +710,17 @@ def main():
                 # reads per probed hash, against the microbenchmark's rate for rows of this width
                 "random_access": random_access_block(stage, args, ix, gather),
                 "stage_ms_per_step": {"hash": stage["hash_ms"] / args.steps, "dedup": stage["dedup_ms"] / args.steps,
-                                      "query": stage["query_ms"] / args.steps}}
+                                      "query": stage["query_ms"] / args.steps},
+                "stage_note": "CUDA-event durations per stage, summed over the batches of a step.  With the overlap on (default where it "
+                              "applies) the hash + dedup kernels of batch i+1 run BESIDE the probe kernels of batch i, so the stages "
+                              "overlap in time, do not add up to ms_per_step, and each is slower than alone; `standalone` is the same "
+                              "workload with one pipeline slot (no overlap): the duration kernel #2 has when it owns the GPU",
+                "standalone": {"achieved": alone["query_bytes"] / (alone["query_ms"] / 1e3) / 1e9 if alone["query_ms"] > 0 else None,
+                               "frac": alone["query_bytes"] / (alone["query_ms"] / 1e3) / 1e9 / peak if alone["query_ms"] > 0 else None,
+                               "unit": "GB/s", "steps": alone_steps, "ms_per_step_serial_schedule": alone["total_ms"] / alone_steps,
+                               "stage_ms_per_step": {"hash": alone["hash_ms"] / alone_steps, "dedup": alone["dedup_ms"] / alone_steps,
+                                                     "query": alone["query_ms"] / alone_steps},
+                               "avg_launch_ms": alone["query_ms"] / max(alone["probe_launches"], 1)}}
         cpu, parity = None, multi_parity
         if world == 1 and not args.no_cpu_baseline:
             cpu, ora, n_s = cpu_baseline_block(args, ix, pin, off_pin, len_pin, n_reads, cores, args.cpu_seconds)

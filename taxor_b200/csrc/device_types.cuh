@@ -150,7 +150,8 @@ struct QueryArgs
     int ctas_per_sm;                // host side: CTAs per SM of the persistent probe grid (0: fill the SM)
     uint32_t early_exit;            // 1: stop probing an item once no user bin can reach the threshold any more
     uint32_t l2_hints;              // 1: items are grouped by IXF, use the L2 eviction-priority plan (query_kernels.cu)
-    uint32_t unroll;                // probe steps in flight per warp of the small kernel (0/2 default, 3, 4)
+    uint32_t unroll;                // probe steps in flight per warp of the small kernel (0/2 default, 1, 3, 4)
+    uint32_t regs32;                // unroll == 1: take the 32-register build (16 CTAs per SM fit) whatever the grid
     uint32_t l2_sector64;           // 1: rows of 64-byte IXFs are loaded with the .L2::64B prefetch-size hint; 2: only below the root
     uint32_t generic;               // 1: the index was uploaded with a non-default probe arithmetic (`scheme`)
     IxfScheme scheme;

@@ -237,6 +237,7 @@ struct Slot
     bool busy{false};
     bool split_used{false}, ran_query{true};
     bool fused{false}; // the hash kernel of the batch in flight built the distinct sets itself
+    bool first{true}, last{true}; // position of the batch in its search call (overlap shapes)
 };
 
 struct ResultStore
@@ -290,6 +291,7 @@ struct txr_ctx
     // index then cost two DRAM sectors instead of a 128-byte line; the step gains little (93.5 -> 92.9 ms, the root level is bound by
     // random accesses per second, not by bytes) but the DRAM traffic per probe byte drops from 1.8x to about 1x.
     uint32_t l2_sector64{1};
+    uint32_t query_regs32{0};  // TXR_QUERY_REGS=32: the 32-register build of the one-step probe kernel whatever the CTA count
     int hash_regs{0};          // TXR_HASH_REGS=5: the 102-register variant of the syncmer kernel (5 CTAs per SM)
     uint32_t query_unroll{0};  // TXR_QUERY_UNROLL: probe steps in flight per warp (experiments with fewer probe CTAs per SM)
     uint32_t fuse_max_keys{kWarpMaxKeys}; // TXR_FUSE_MAX_KEYS lowers it (tests: forces the hand-over to the CTA-per-read kernel)
@@ -308,7 +310,8 @@ struct txr_ctx
     cudaStream_t primary{nullptr};     // caller's stream: every search forks from it and joins back into it
     cudaStream_t compute{nullptr};     // the query kernels of all batches run here, in batch order; slot streams only carry copies
     cudaStream_t compute_hash{nullptr}; // overlap mode: hash + dedup (ALU bound) of batch i+1 beside the query (DRAM bound) of batch i
-    bool overlap{false};               // TXR_OVERLAP=1: measured slower end to end, kept for experiments
+    int overlap_mode{2};               // TXR_OVERLAP: 0 off, 1 always, 2 auto (overlap_applies): hash stage of batch i+1 beside the probes of batch i
+    int shape_unroll{0};               // probe steps in flight per warp for the batch being enqueued
     int query_ctas{0}, hash_ctas{0}, dedup_ctas{0}; // CTAs per SM (0: defaults for the mode)
     int level_ctas{0};                              // probe kernels of the levels below the root (0: same as query_ctas)
     // overlap by SM partition: of every `sm_mod` consecutive SM ids the first `sm_hash` run hash + dedup, the rest the
@@ -660,7 +663,8 @@ static int launch_query_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Bat
     q.stat_items = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 2);
     q.stat_skipped = reinterpret_cast<unsigned long long *>(cnt + C_STATS + 4);
     q.early_exit = c->early_exit;
-    q.unroll = c->query_unroll;
+    q.unroll = (uint32_t)c->shape_unroll;
+    q.regs32 = c->query_regs32;
     q.l2_sector64 = c->l2_sector64 == 1;
     q.generic = ix.generic;
     q.scheme = ix.scheme;
@@ -782,14 +786,38 @@ static int per_read_thresholds(txr_ctx *c, Slot &s, const BatchMeta &m, cudaStre
 // compete with each other.  Overlap mode (TXR_OVERLAP=1, several slots): hash + dedup of batch i+1 run on a second
 // stream beside the probe kernels of batch i, either on the same SMs with small grids or, with TXR_SM_SPLIT=mod:n,
 // on disjoint SMs (SmFilter).
-static int enqueue_kernels(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev &bd, const uint64_t *d_words, bool run_query)
+// Is the hash stage of the next batch allowed beside the probe kernels of this one?  TXR_OVERLAP: 0 never, 1 always (manual
+// shapes), 2 = auto: only where it was measured to win -- syncmer indexes hashed by a templated kernel, rows of at most 512
+// bytes (the wide-row kernel needs the whole register file), the default probe arithmetic, thresholds from the LUT.
+static bool overlap_applies(const txr_ctx *c)
 {
-    const bool overlap = c->overlap && c->n_slots > 1;
+    if (c->n_slots <= 1 || c->overlap_mode == 0)
+        return false;
+    if (c->overlap_mode == 1)
+        return true;
+    return c->params.use_syncmer && !c->per_read_thr && !c->index.generic && !c->index.any_large &&
+           syncmer_has_fast_kernel(c->params.kmer_size, c->params.syncmer_size, c->params.t_syncmer);
+}
+
+// `first` / `last`: position of the batch inside its search call.  With the overlap on, the hash + dedup kernels of a batch
+// run with small grids beside the probes of the batch before it -- except for the first batch, which has nothing beside it
+// and takes the whole GPU; the probes of the last batch have no hash kernel beside them and run in their stand-alone shape.
+static int enqueue_kernels(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev &bd, const uint64_t *d_words, bool run_query,
+                           bool first = true, bool last = true)
+{
+    const bool overlap = overlap_applies(c);
     const bool split = overlap && c->sm_mod > 1 && c->sm_hash > 0 && c->sm_hash < c->sm_mod;
-    c->shape_query = c->query_ctas ? c->query_ctas : overlap && !split ? 5 : 8;
+    const bool beside_hash = overlap && !split && !last;  // probes of this batch share the SMs with the next batch's hash stage
+    const bool beside_probe = overlap && !split && !first; // hash stage of this batch shares the SMs with the previous batch's probes
+    // probe kernel beside a hash kernel: one step in flight per warp (40 registers) at 6 CTAs per SM leaves room for two
+    // 124-register hash CTAs (profiles/r2_f_u1_sweep.txt); alone: two steps in flight, 8 CTAs of 64 registers
+    c->shape_query = beside_hash ? (c->query_ctas ? c->query_ctas : 6) : (!overlap && c->query_ctas ? c->query_ctas : 8);
+    c->shape_unroll = beside_hash ? (c->query_unroll ? c->query_unroll : 1) : (!overlap ? c->query_unroll : 0);
     c->shape_level = c->level_ctas ? c->level_ctas : c->shape_query;
-    c->shape_hash = c->hash_ctas ? c->hash_ctas : overlap && !split ? 1 : 8;
-    c->shape_dedup = c->dedup_ctas ? c->dedup_ctas : overlap && !split ? 2 : 6;
+    c->shape_hash = beside_probe ? (c->hash_ctas ? c->hash_ctas : 2) : (!overlap && c->hash_ctas ? c->hash_ctas : 8);
+    c->shape_dedup = beside_probe ? (c->dedup_ctas ? c->dedup_ctas : 3) : (!overlap && c->dedup_ctas ? c->dedup_ctas : 6);
+    s.first = first;
+    s.last = last;
     c->smf_hash = split ? SmFilter{c->sm_mod, 0, c->sm_hash} : SmFilter{0, 0, 0};
     c->smf_query = split ? SmFilter{c->sm_mod, c->sm_hash, c->sm_mod} : SmFilter{0, 0, 0};
     cudaStream_t cs = c->compute, hs = overlap ? c->compute_hash : c->compute;
@@ -840,7 +868,7 @@ static bool split_left_work_undone(const txr_ctx *c, const Slot &s, const BatchM
 
 // enqueue everything for one batch; `h_words` != nullptr: copy the packed reads from the host first
 static int submit_batch(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev *resident_meta,
-                        const uint64_t *d_words_resident, const uint64_t *h_words, bool run_query)
+                        const uint64_t *d_words_resident, const uint64_t *h_words, bool run_query, bool first = true, bool last = true)
 {
     TRY(slot_reserve(c, s, m));
     TRY(ensure_lut(c, m.max_cap + 1));
@@ -857,7 +885,7 @@ static int submit_batch(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchDev 
         d_words = s.words.as<uint64_t>();
     }
     CU(cudaEventRecord(s.ev[1], s.stream));
-    TRY(enqueue_kernels(c, s, m, *bd, d_words, run_query));
+    TRY(enqueue_kernels(c, s, m, *bd, d_words, run_query, first, last));
     s.bm = &m;
     s.bd = bd;
     s.d_words = d_words;
@@ -880,7 +908,7 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
             c->sm_mod = 0;
             CU(cudaDeviceSynchronize());
             CU(cudaEventRecord(s.ev[1], s.stream));
-            TRY(enqueue_kernels(c, s, m, *s.bd, s.d_words, s.ran_query));
+            TRY(enqueue_kernels(c, s, m, *s.bd, s.d_words, s.ran_query, s.first, s.last));
             continue;
         }
         const uint32_t *hc = s.h_counters.as<uint32_t>();
@@ -1105,7 +1133,7 @@ int txr_ctx_create(int device, txr_ctx **out)
     if (const char *e = getenv("TXR_SORT_ITEMS"))
         c->sort_items = atoi(e) != 0;
     if (const char *e = getenv("TXR_OVERLAP"))
-        c->overlap = atoi(e) != 0;
+        c->overlap_mode = atoi(e);
     if (const char *e = getenv("TXR_SM_SPLIT")) // "mod:n": of every mod SM ids, n run hash + dedup
     {
         unsigned mod = 0, n = 0;
@@ -1129,6 +1157,8 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->l2_hints = atoi(e) != 0;
     if (const char *e = getenv("TXR_L2_SECTOR64"))
         c->l2_sector64 = (uint32_t)atoi(e);
+    if (const char *e = getenv("TXR_QUERY_REGS"))
+        c->query_regs32 = atoi(e) == 32;
     if (const char *e = getenv("TXR_HASH_REGS"))
         c->hash_regs = atoi(e);
     if (const char *e = getenv("TXR_QUERY_UNROLL"))
@@ -1802,7 +1832,7 @@ static int search_host_impl(txr_ctx *c, const uint64_t *words, const uint64_t *w
             TRY(collect_batch(c, s, true));
         BatchMeta &m = metas[b % S];
         build_batch_meta(c, word_off, len, next_read, (uint32_t)(j - next_read), m);
-        TRY(submit_batch(c, s, m, nullptr, nullptr, words, true));
+        TRY(submit_batch(c, s, m, nullptr, nullptr, words, true, b == 0, j >= n_reads));
         next_read = j;
     }
     // the batches still in flight, oldest first (slots are used round robin)
@@ -1886,7 +1916,7 @@ static int search_resident_impl(txr_ctx *c, txr_reads *r, int fetch, txr_result 
         if (s.busy)
             TRY(collect_batch(c, s, fetch != 0));
         const BatchMeta &m = r->batches[b];
-        TRY(submit_batch(c, s, m, r->dev[b].get(), r->words.as<uint64_t>() + m.first_word, nullptr, true));
+        TRY(submit_batch(c, s, m, r->dev[b].get(), r->words.as<uint64_t>() + m.first_word, nullptr, true, b == 0, b + 1 == r->batches.size()));
     }
     // collect in submission order
     for (size_t b = (r->batches.size() > S ? r->batches.size() - S : 0); b < r->batches.size(); ++b)

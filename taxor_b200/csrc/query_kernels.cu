@@ -947,7 +947,7 @@ cudaError_t launch_query_small(const QueryArgs &a, int sm_count, cudaStream_t st
     const int grid = sm_count * query_ctas(a);
     if (a.generic)
         ixf_query_small_kernel<true, kQueryUnroll, 1><<<grid, 32 * kQueryWarps, 0, st>>>(a);
-    else if (a.unroll == 1 && query_ctas(a) >= 16) // 32 registers: all 64 warps an SM can hold
+    else if (a.unroll == 1 && (query_ctas(a) >= 16 || a.regs32)) // 32 registers: all 64 warps an SM can hold
         ixf_query_small_kernel<false, 1, 16><<<grid, 32 * kQueryWarps, 0, st>>>(a);
     else if (a.unroll == 1) // one step in flight per warp, 40 registers: up to 12 CTAs (48 warps) per SM
         ixf_query_small_kernel<false, 1, 12><<<grid, 32 * kQueryWarps, 0, st>>>(a);
