@@ -132,7 +132,7 @@ void txr_ctx_destroy(txr_ctx *ctx);
 /* The caller's CUDA stream (a cudaStream_t; NULL = legacy default stream).  Every search call forks its internal
  * streams from it and joins them back, so CUDA events recorded on it bracket the whole call. */
 int txr_ctx_set_stream(txr_ctx *ctx, void *stream);
-/* max reads / bases per internal batch and number of pipeline slots (defaults 262144 / 3e9 / 3). */
+/* max reads / bases per internal batch and number of pipeline slots (defaults 262144 / 3e9 / 4). */
 int txr_ctx_configure(txr_ctx *ctx, uint64_t max_batch_reads, uint64_t max_batch_bases, int n_slots);
 
 /* one-time re-layout of the index into HBM; replaces load_index() + index.ixf() (load_index.hpp:27-38) */

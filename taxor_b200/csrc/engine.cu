@@ -272,7 +272,7 @@ struct txr_ctx
     int sm_count{148};
     uint64_t max_batch_reads{262144};
     uint64_t max_batch_bases{3000000000ull};
-    int n_slots{3};
+    int n_slots{4}; // pipeline slots: copy of batch i+2, hash stage of batch i+1 and probes of batch i in flight together
     std::vector<std::unique_ptr<Slot>> slots;
     DeviceIndex index;
     bool have_params{false};
@@ -292,6 +292,7 @@ struct txr_ctx
     // random accesses per second, not by bytes) but the DRAM traffic per probe byte drops from 1.8x to about 1x.
     uint32_t l2_sector64{1};
     uint32_t query_regs32{0};  // TXR_QUERY_REGS=32: the 32-register build of the one-step probe kernel whatever the CTA count
+    double ramp{1.8};          // growth of the batch sizes of a host-fed search (TXR_RAMP)
     int hash_regs{0};          // TXR_HASH_REGS=5: the 102-register variant of the syncmer kernel (5 CTAs per SM)
     uint32_t query_unroll{0};  // TXR_QUERY_UNROLL: probe steps in flight per warp (experiments with fewer probe CTAs per SM)
     uint32_t fuse_max_keys{kWarpMaxKeys}; // TXR_FUSE_MAX_KEYS lowers it (tests: forces the hand-over to the CTA-per-read kernel)
@@ -1159,6 +1160,8 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->l2_sector64 = (uint32_t)atoi(e);
     if (const char *e = getenv("TXR_QUERY_REGS"))
         c->query_regs32 = atoi(e) == 32;
+    if (const char *e = getenv("TXR_RAMP"))
+        c->ramp = std::max(1.05, atof(e));
     if (const char *e = getenv("TXR_HASH_REGS"))
         c->hash_regs = atoi(e);
     if (const char *e = getenv("TXR_QUERY_UNROLL"))
@@ -1825,7 +1828,7 @@ static int search_host_impl(txr_ctx *c, const uint64_t *words, const uint64_t *w
         uint64_t bases = 0, j = next_read;
         while (j < n_reads && j - next_read < max_reads && (j == next_read || bases + len[j] <= max_bases))
             bases += len[j++];
-        scale = std::min(1.0, scale * 1.8);
+        scale = std::min(1.0, scale * c->ramp);
         TRY(validate_reads(word_off + next_read, len + next_read, std::min<uint64_t>(j - next_read + 1, n_reads - next_read)));
         Slot &s = *c->slots[b % S];
         if (s.busy)
