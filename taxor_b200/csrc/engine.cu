@@ -810,13 +810,18 @@ static int enqueue_kernels(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchD
     const bool split = overlap && c->sm_mod > 1 && c->sm_hash > 0 && c->sm_hash < c->sm_mod;
     const bool beside_hash = overlap && !split && !last;  // probes of this batch share the SMs with the next batch's hash stage
     const bool beside_probe = overlap && !split && !first; // hash stage of this batch shares the SMs with the previous batch's probes
-    // probe kernel beside a hash kernel: one step in flight per warp (40 registers) at 6 CTAs per SM leaves room for two
-    // 124-register hash CTAs (profiles/r2_f_u1_sweep.txt); alone: two steps in flight, 8 CTAs of 64 registers
-    c->shape_query = beside_hash ? (c->query_ctas ? c->query_ctas : 6) : (!overlap && c->query_ctas ? c->query_ctas : 8);
+    // probe kernel beside a hash kernel: one step in flight per warp (40 registers), 7 CTAs per SM launched (6 fit beside two
+    // 124-register hash CTAs, the seventh whenever a hash CTA has left; profiles/r2_f_u1_sweep.txt); alone: two steps in
+    // flight, 8 CTAs of 64 registers
+    c->shape_query = beside_hash ? (c->query_ctas ? c->query_ctas : 7) : (!overlap && c->query_ctas ? c->query_ctas : 8);
     c->shape_unroll = beside_hash ? (c->query_unroll ? c->query_unroll : 1) : (!overlap ? c->query_unroll : 0);
     c->shape_level = c->level_ctas ? c->level_ctas : c->shape_query;
     c->shape_hash = beside_probe ? (c->hash_ctas ? c->hash_ctas : 2) : (!overlap && c->hash_ctas ? c->hash_ctas : 8);
-    c->shape_dedup = beside_probe ? (c->dedup_ctas ? c->dedup_ctas : 3) : (!overlap && c->dedup_ctas ? c->dedup_ctas : 6);
+    // dedup beside the probes: 3 CTAs per SM for full-size batches (fewest probe registers taken: best device-resident step),
+    // 6 for the smaller batches of a host-fed call's ramp, whose dedup must finish within the shorter probes of the batch before
+    // (profiles/r2_f_u1_sweep.txt, run F4: d3 84.2 / 94.8 ms resident / end to end, d6 87.0 / 93.4)
+    const int dedup_beside = m.n_reads >= c->max_batch_reads ? 3 : 6;
+    c->shape_dedup = beside_probe ? (c->dedup_ctas ? c->dedup_ctas : dedup_beside) : (!overlap && c->dedup_ctas ? c->dedup_ctas : 6);
     s.first = first;
     s.last = last;
     c->smf_hash = split ? SmFilter{c->sm_mod, 0, c->sm_hash} : SmFilter{0, 0, 0};
