@@ -46,6 +46,14 @@ def main():
                    f"early exit skips {r.get('early_exit_skipped_hashes_per_step', 0) / 1e6:.0f} M of "
                    f"{(r.get('early_exit_skipped_hashes_per_step', 0) + r['algorithmic_bytes_per_step'] / 200) / 1e6:.0f} M probes per step; "
                    f"`traffic` {(r.get('traffic') or 0) / 1e9:.1f} GB per probe launch for {r.get('algorithmic_bytes_per_launch', 0) / 1e9:.1f} GB of probe bytes.")
+        sa, ra = r.get("standalone") or {}, r.get("random_access") or {}
+        if sa:
+            st = sa["stage_ms_per_step"]
+            out.append(f"configs[1], kernel #2 on its own (`roofline.standalone`: one pipeline slot, no hash stage beside the probes): "
+                       f"{st['query']:.1f} ms of query time per step = {sa['achieved']:.0f} GB/s = **{sa['frac']:.3f}** of the measured HBM peak; "
+                       f"hash {st['hash']:.1f} / dedup {st['dedup']:.1f} ms; the serial schedule takes {sa['ms_per_step_serial_schedule']:.1f} ms per step "
+                       f"against {final['ms_per_step']:.1f} with the overlap.  As random row reads: {ra.get('achieved_G_rows_per_s', 0):.1f} G rows/s in the "
+                       f"(overlapped) timed region, {ra.get('vs_microbench', 0):.2f}× the one-row gather microbenchmark ({ra.get('microbench_G_rows_per_s', 0):.1f} G rows/s).")
     ref = load("r2_e_bench_reference_arm.json") or load("r2_c_bench_reference_arm.json")
     if ref and final:
         v = ref["cpu_baseline"].get("variants", {})
