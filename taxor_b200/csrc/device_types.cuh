@@ -20,6 +20,12 @@ struct SmFilter
     uint32_t mod, lo, hi;
 };
 #if defined(__CUDACC__)
+// adaptive grid of the hash-stage kernels: true = this CTA should leave (the probes own the GPU and this CTA is beyond the share
+// the hash stage gets beside them)
+__device__ __forceinline__ bool yield_to_probes(const uint32_t *probe_flag, uint32_t small_grid)
+{
+    return probe_flag != nullptr && blockIdx.x >= small_grid && *reinterpret_cast<const volatile uint32_t *>(probe_flag) != 0u;
+}
 __device__ __forceinline__ bool sm_filter_keep(const SmFilter &f)
 {
     if (f.mod == 0)
@@ -49,6 +55,10 @@ struct HashArgs
     int ctas_per_sm;           // host side: CTAs per SM of the persistent grid (0: fill the SM)
     int window;                // minimiser mode: k-mer values per window, window_size - k + 1 (2..kMaxMinimiserValues)
     int min_blocks;            // host side: register variant of the syncmer kernel (0/4 default, 5 = 102 registers)
+    // adaptive grid (overlap): the kernel is launched with a grid for the whole GPU; CTAs beyond `small_grid` leave at once when the
+    // probe kernels of the batch before are running (`*probe_flag` != 0, set and cleared in stream order around every query stage)
+    const uint32_t *probe_flag;
+    uint32_t small_grid;
     // fused per-read distinct set (syncmer_kernel only; the ankerl::set of syncmer.cpp:145 built while hashing):
     uint32_t fuse_dedup;       // 1: reads whose capacity is <= kFuseMaxCap write DISTINCT hashes + hash_count directly
     uint32_t fuse_max_keys;    // distinct keys the warp table takes before the read is handed over (<= kWarpMaxKeys; tests lower it)
@@ -76,6 +86,8 @@ struct DedupArgs
     double scaling_limit;      // double(UINT64_MAX) / double(scaling)
     SmFilter smf;
     int ctas_per_sm;           // host side: CTAs per SM of the warp-per-read grid (0: default)
+    const uint32_t *probe_flag; // adaptive grid, as in HashArgs
+    uint32_t small_grid;
 };
 
 // ---- build side: distinct hash set of a user bin from the raw hash lists of its sequence segments ----

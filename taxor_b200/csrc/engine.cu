@@ -292,6 +292,7 @@ struct txr_ctx
     // random accesses per second, not by bytes) but the DRAM traffic per probe byte drops from 1.8x to about 1x.
     uint32_t l2_sector64{1};
     uint32_t query_regs32{0};  // TXR_QUERY_REGS=32: the 32-register build of the one-step probe kernel whatever the CTA count
+    bool adaptive{true};       // TXR_ADAPTIVE=0: fixed small grids for the hash stage beside the probes
     double ramp{1.8};          // growth of the batch sizes of a host-fed search (TXR_RAMP)
     int hash_regs{0};          // TXR_HASH_REGS=5: the 102-register variant of the syncmer kernel (5 CTAs per SM)
     uint32_t query_unroll{0};  // TXR_QUERY_UNROLL: probe steps in flight per warp (experiments with fewer probe CTAs per SM)
@@ -307,12 +308,14 @@ struct txr_ctx
     std::vector<uint64_t> hb_off, hb_hashes;
     std::vector<uint64_t> ub_off, ub_hashes; // txr_hash_user_bins result
     DevBuf scratch_a, scratch_b;
+    DevBuf probe_flag;         // != 0 while the probe kernels of some batch run (adaptive grids of the hash stage, overlap)
     DevBuf binset[8]; // txr_hash_user_bins: segment bins, tables, table offsets, flags, output, output offsets, counts, cursor
     cudaStream_t primary{nullptr};     // caller's stream: every search forks from it and joins back into it
     cudaStream_t compute{nullptr};     // the query kernels of all batches run here, in batch order; slot streams only carry copies
     cudaStream_t compute_hash{nullptr}; // overlap mode: hash + dedup (ALU bound) of batch i+1 beside the query (DRAM bound) of batch i
     int overlap_mode{2};               // TXR_OVERLAP: 0 off, 1 always, 2 auto (overlap_applies): hash stage of batch i+1 beside the probes of batch i
     int shape_unroll{0};               // probe steps in flight per warp for the batch being enqueued
+    int adaptive_small_hash{0}, adaptive_small_dedup{0}; // != 0: CTAs per SM the hash / dedup kernel keeps while probes run (adaptive grid)
     int query_ctas{0}, hash_ctas{0}, dedup_ctas{0}; // CTAs per SM (0: defaults for the mode)
     int level_ctas{0};                              // probe kernels of the levels below the root (0: same as query_ctas)
     // overlap by SM partition: of every `sm_mod` consecutive SM ids the first `sm_hash` run hash + dedup, the rest the
@@ -356,6 +359,11 @@ static int ensure_slots(txr_ctx *c)
     {
         CU(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c->compute_hash, cudaStreamNonBlocking));
+    }
+    if (!c->probe_flag.p)
+    {
+        TRY(c->probe_flag.ensure(4));
+        CU(cudaMemset(c->probe_flag.p, 0, 4));
     }
     while ((int)c->slots.size() < c->n_slots)
     {
@@ -559,6 +567,8 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     h.smf = c->smf_hash;
     h.ctas_per_sm = c->shape_hash;
     h.min_blocks = c->hash_regs;
+    h.probe_flag = c->adaptive_small_hash ? c->probe_flag.as<uint32_t>() : nullptr;
+    h.small_grid = (uint32_t)(c->adaptive_small_hash * c->sm_count);
     // the distinct set of a read (syncmer.cpp:145) is built while hashing whenever the templated kernel runs: no raw list
     // round trip through HBM for the reads of the `ids_small` class
     const bool fused = dedup && c->fuse_dedup && c->params.use_syncmer &&
@@ -594,6 +604,8 @@ static int launch_hash_stage(txr_ctx *c, Slot &s, const BatchMeta &m, const Batc
     dd.scaling_limit = double(UINT64_MAX) / double(c->params.scaling ? c->params.scaling : 1);
     dd.smf = c->smf_hash;
     dd.ctas_per_sm = c->shape_dedup;
+    dd.probe_flag = c->adaptive_small_dedup ? c->probe_flag.as<uint32_t>() : nullptr;
+    dd.small_grid = (uint32_t)(c->adaptive_small_dedup * c->sm_count);
     if (c->params.use_syncmer)
     {
         if (!m.ids_small.empty())
@@ -816,12 +828,19 @@ static int enqueue_kernels(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchD
     c->shape_query = beside_hash ? (c->query_ctas ? c->query_ctas : 7) : (!overlap && c->query_ctas ? c->query_ctas : 8);
     c->shape_unroll = beside_hash ? (c->query_unroll ? c->query_unroll : 1) : (!overlap ? c->query_unroll : 0);
     c->shape_level = c->level_ctas ? c->level_ctas : c->shape_query;
-    c->shape_hash = beside_probe ? (c->hash_ctas ? c->hash_ctas : 2) : (!overlap && c->hash_ctas ? c->hash_ctas : 8);
+    // Adaptive grids (TXR_ADAPTIVE, default on): the hash-stage kernels of a batch that may run beside probes are launched for the
+    // whole GPU, and their CTAs beyond the small share leave at once if the probes are running at that moment.  When the probes of
+    // the batch before are long done -- a host-fed search bound by its H2D copies, as on a box where eight GPUs pull reads out of
+    // one host -- the hash stage then takes the idle GPU instead of crawling through it with a quarter of the warps.
+    const bool adaptive = beside_probe && c->adaptive && !c->hash_ctas && !c->dedup_ctas;
+    c->adaptive_small_hash = adaptive ? 2 : 0;
+    c->shape_hash = adaptive ? 8 : beside_probe ? (c->hash_ctas ? c->hash_ctas : 2) : (!overlap && c->hash_ctas ? c->hash_ctas : 8);
     // dedup beside the probes: 3 CTAs per SM for full-size batches (fewest probe registers taken: best device-resident step),
     // 6 for the smaller batches of a host-fed call's ramp, whose dedup must finish within the shorter probes of the batch before
     // (profiles/r2_f_u1_sweep.txt, run F4: d3 84.2 / 94.8 ms resident / end to end, d6 87.0 / 93.4)
     const int dedup_beside = m.n_reads >= c->max_batch_reads ? 3 : 6;
-    c->shape_dedup = beside_probe ? (c->dedup_ctas ? c->dedup_ctas : dedup_beside) : (!overlap && c->dedup_ctas ? c->dedup_ctas : 6);
+    c->adaptive_small_dedup = adaptive ? dedup_beside : 0;
+    c->shape_dedup = adaptive ? 6 : beside_probe ? (c->dedup_ctas ? c->dedup_ctas : dedup_beside) : (!overlap && c->dedup_ctas ? c->dedup_ctas : 6);
     s.first = first;
     s.last = last;
     c->smf_hash = split ? SmFilter{c->sm_mod, 0, c->sm_hash} : SmFilter{0, 0, 0};
@@ -837,7 +856,13 @@ static int enqueue_kernels(txr_ctx *c, Slot &s, const BatchMeta &m, const BatchD
     CU(cudaStreamWaitEvent(cs, s.ev[9], 0));
     CU(cudaEventRecord(s.ev[8], cs));
     if (run_query)
+    {
+        if (overlap)
+            CU(cudaMemsetAsync(c->probe_flag.p, 1, 4, cs)); // "probes running": read by the adaptive grids of the next batch's hash stage
         TRY(launch_query_stage(c, s, m, bd, cs));
+        if (overlap)
+            CU(cudaMemsetAsync(c->probe_flag.p, 0, 4, cs));
+    }
     else
         CU(cudaEventRecord(s.ev[4], cs));
     CU(cudaEventRecord(s.ev[7], cs));
@@ -1165,6 +1190,8 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->l2_sector64 = (uint32_t)atoi(e);
     if (const char *e = getenv("TXR_QUERY_REGS"))
         c->query_regs32 = atoi(e) == 32;
+    if (const char *e = getenv("TXR_ADAPTIVE"))
+        c->adaptive = atoi(e) != 0;
     if (const char *e = getenv("TXR_RAMP"))
         c->ramp = std::max(1.05, atof(e));
     if (const char *e = getenv("TXR_HASH_REGS"))
@@ -1214,6 +1241,7 @@ void txr_ctx_destroy(txr_ctx *c)
     c->d_lut.release();
     c->scratch_a.release();
     c->scratch_b.release();
+    c->probe_flag.release();
     for (auto &b : c->binset)
         b.release();
     delete c;
@@ -1962,6 +1990,7 @@ int txr_hash_batch(txr_ctx *c, const uint64_t *words, const uint64_t *word_off, 
     c->hb_off.assign(1, 0);
     c->hb_hashes.clear();
     c->shape_hash = c->shape_dedup = 0; // this entry point runs the hash stage alone: full grids, every SM
+    c->adaptive_small_hash = c->adaptive_small_dedup = 0;
     c->smf_hash = SmFilter{0, 0, 0};
     std::vector<std::pair<uint64_t, uint32_t>> plan;
     plan_batches(c, len, n_reads, plan);
@@ -2144,6 +2173,7 @@ int txr_hash_user_bins(txr_ctx *c, const uint64_t *words, const uint64_t *word_o
     c->ub_off.assign(n_bins + 1, 0);
     c->ub_hashes.clear();
     c->shape_hash = c->shape_dedup = 0;
+    c->adaptive_small_hash = c->adaptive_small_dedup = 0;
     c->smf_hash = SmFilter{0, 0, 0};
     Slot &s = *c->slots[0];
     cudaStream_t st = s.stream;

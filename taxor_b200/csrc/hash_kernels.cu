@@ -280,7 +280,7 @@ __device__ bool resolve_tie_local(const uint64_t *w, const uint32_t *sv, uint64_
 template <int K, int S, int T, int MINB>
 __global__ void __launch_bounds__(32 * kHashWarps, MINB) syncmer_kernel(HashArgs a)
 {
-    if (!sm_filter_keep(a.smf))
+    if (!sm_filter_keep(a.smf) || yield_to_probes(a.probe_flag, a.small_grid))
         return;
     constexpr int WN = K - S + 1;    // s-mers per k-mer window
     constexpr int QN = 32 + WN - 1;  // s-mers a lane needs for its 32 windows
@@ -962,7 +962,7 @@ constexpr int kDedupWarps = 4; // 32 KB of static shared memory per CTA
 __global__ void __launch_bounds__(32 * kDedupWarps) dedup_warp_kernel(DedupArgs a, uint32_t *work_counter, uint32_t *deferred,
                                                                       uint32_t *n_deferred)
 {
-    if (!sm_filter_keep(a.smf))
+    if (!sm_filter_keep(a.smf) || yield_to_probes(a.probe_flag, a.small_grid))
         return;
     __shared__ uint32_t s_tab[kDedupWarps][kWarpSlots];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
