@@ -135,6 +135,10 @@ int txr_ctx_set_stream(txr_ctx *ctx, void *stream);
 /* max reads / bases per internal batch and number of pipeline slots (defaults 262144 / 3e9 / 4). */
 int txr_ctx_configure(txr_ctx *ctx, uint64_t max_batch_reads, uint64_t max_batch_bases, int n_slots);
 
+/* optional: allocate now what the first search call of up to n_reads reads / n_bases bases would allocate (needs
+ * txr_params_set; a multi-GPU driver calls it from each GPU's thread while the reads are still being parsed) */
+int txr_ctx_reserve(txr_ctx *ctx, uint64_t n_reads, uint64_t n_bases);
+
 /* one-time re-layout of the index into HBM; replaces load_index() + index.ixf() (load_index.hpp:27-38) */
 int txr_index_upload(txr_ctx *ctx, const txr_hixf_view *index);
 /* replicate the index already resident in `src` (same or another GPU) into `dst`, device to device (NVLink between

@@ -82,6 +82,7 @@ def lib():
     L.txr_ctx_destroy.restype = None
     L.txr_ctx_set_stream.argtypes = [vp, vp]
     L.txr_ctx_configure.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int]
+    L.txr_ctx_reserve.argtypes = [vp, C.c_uint64, C.c_uint64]
     L.txr_index_upload.argtypes = [vp, C.POINTER(HixfView)]
     L.txr_index_clone.argtypes = [vp, vp]
     L.txr_params_set.argtypes = [vp, C.POINTER(Params)]
@@ -120,7 +121,7 @@ def lib():
 
 
 EXPORTED = ["txr_last_error", "txr_version", "txr_ctx_create", "txr_ctx_destroy", "txr_ctx_set_stream", "txr_ctx_configure",
-            "txr_index_upload", "txr_index_clone", "txr_params_set", "txr_threshold_get", "txr_threshold_eval", "txr_packed_words", "txr_pack_2bit",
+            "txr_ctx_reserve", "txr_index_upload", "txr_index_clone", "txr_params_set", "txr_threshold_get", "txr_threshold_eval", "txr_packed_words", "txr_pack_2bit",
             "txr_pack_codes", "txr_unpack_codes", "txr_host_alloc", "txr_host_free", "txr_search",
             "txr_reads_upload", "txr_reads_free", "txr_search_resident", "txr_get_timing", "txr_hash_batch",
             "txr_hash_user_bins", "txr_plan_segments", "txr_ixf_bulk_count",
@@ -292,6 +293,10 @@ class Context:
             sch = C.pointer(IxfScheme(*[int(x) for x in sc], int(layout)))
         v = HixfView(n, ixfs, bin_off.ctypes.data, nx.ctypes.data, ub.ctypes.data, int(n_user_bins), sch)
         _check(self._L.txr_index_upload(self._h, C.byref(v)))
+
+    def reserve(self, n_reads: int, n_bases: int) -> None:
+        """txr_ctx_reserve: allocate the per-slot buffers of a search of this size now instead of inside the first call"""
+        _check(self._L.txr_ctx_reserve(self._h, int(n_reads), int(n_bases)))
 
     def clone_index_from(self, other: "Context") -> None:
         """txr_index_clone: device-to-device replica of the index resident in `other` (NVLink between peer GPUs)."""

@@ -1427,6 +1427,40 @@ static int upload_fingerprints(txr_ctx *c, const txr_hixf_view *v, DeviceIndex &
     return TXR_OK;
 }
 
+// Allocates the per-slot device and pinned buffers a search of up to n_reads reads / n_bases bases per call would allocate
+// on its first call, so that the first call does not pay for it (a driver with several GPUs calls this from each GPU's own
+// thread while the reads are still being parsed: the allocations of eight contexts otherwise land in the timed search phase).
+int txr_ctx_reserve(txr_ctx *c, uint64_t n_reads, uint64_t n_bases)
+{
+    if (!c || !c->have_params || n_reads == 0)
+        return set_error(TXR_ERR_STATE, "txr_params_set not called");
+    CU(cudaSetDevice(c->device));
+    TRY(ensure_slots(c));
+    const uint64_t n = std::min<uint64_t>(n_reads, c->max_batch_reads);
+    const uint64_t bases = std::min<uint64_t>(std::max<uint64_t>(n_bases, n), c->max_batch_bases);
+    BatchMeta m;
+    m.n_reads = (uint32_t)n;
+    m.n_bases = bases;
+    const uint64_t mean_len = (bases + n - 1) / n;
+    const uint64_t cap = hash_capacity(c->params, mean_len + 64);
+    m.total_cap = cap * n;
+    m.max_cap = cap;
+    m.n_words = bases / 32 + 2 * n + 64;
+    m.gtable_off.assign(1, 0);
+    TRY(ensure_lut(c, cap + 1));
+    for (auto &sp : c->slots)
+    {
+        Slot &s = *sp;
+        TRY(slot_reserve(c, s, m));
+        TRY(s.words.ensure(m.n_words * 8));
+        TRY(s.h_meta.ensure((size_t)n * 32 + 4096));
+        TRY(s.meta.word_off.ensure((size_t)n * 8));
+        TRY(s.meta.len.ensure((size_t)n * 4));
+        TRY(s.meta.out_off.ensure((size_t)(n + 1) * 8));
+    }
+    return TXR_OK;
+}
+
 int txr_index_upload(txr_ctx *c, const txr_hixf_view *v)
 {
     if (!c || !v || v->n_ixf == 0)

@@ -304,8 +304,10 @@ __global__ void __launch_bounds__(32 * kHashWarps, MINB) syncmer_kernel(HashArgs
     static_assert(kWarpMaxKeys < kPendingBase && kPendingBase + 127 < 2048, "slot payload ranges overlap");
     while (true)
     {
-        uint32_t r = 0;
-        if (lane == 0)
+        // a CTA beyond the small share re-checks before every read: it leaves as soon as a probe kernel starts, so that the probe
+        // CTAs find registers (a persistent full grid that only looked once would hold the SMs until the whole batch is hashed)
+        uint32_t r = 0xffffffffu;
+        if (lane == 0 && !yield_to_probes(a.probe_flag, a.small_grid))
             r = atomicAdd(a.work_counter, 1u);
         r = __shfl_sync(0xffffffffu, r, 0);
         if (r >= a.n_reads)
@@ -969,8 +971,8 @@ __global__ void __launch_bounds__(32 * kDedupWarps) dedup_warp_kernel(DedupArgs 
     volatile uint32_t *tab = s_tab[wib];
     while (true)
     {
-        uint32_t id = 0;
-        if (lane == 0)
+        uint32_t id = 0xffffffffu;
+        if (lane == 0 && !yield_to_probes(a.probe_flag, a.small_grid)) // re-checked per read, as in the syncmer kernel
             id = atomicAdd(work_counter, 1u);
         id = __shfl_sync(0xffffffffu, id, 0);
         if (id >= a.n_ids)

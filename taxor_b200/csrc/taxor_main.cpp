@@ -484,6 +484,8 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     std::vector<std::thread> workers;
     for (txr_ctx *c : ctxs)
         workers.emplace_back([&, c] {
+            // the buffers a chunk-sized search needs, allocated while the first chunk is still being parsed and packed
+            txr_ctx_reserve(c, kChunkReads, kChunkBases);
             Chunk *ch;
             while (work_q.pop(ch))
             {
