@@ -27,11 +27,11 @@ def bench_row(tag, d):
 
 def main():
     out = []
-    final = load("r2_e_bench.json") or load("r2_c_bench.json")
+    final = load("r2_i_bench.json") or load("r2_e_bench.json")
     if final:
         out.append("| workload (1 × B200) | value Gbases/s | ms/step | hash / dedup / query ms | e2e Gbases/s | e2e ms/step | kernel #2 GB/s | frac of measured HBM | CPU port Gbases/s |")
         out.append("|---|---|---|---|---|---|---|---|---|")
-        out.append(bench_row("configs[1], 10.15 GB index, 1 M × 10 kb (`r2_e_bench.json`)", final))
+        out.append(bench_row("configs[1], 10.15 GB index, 1 M × 10 kb (`r2_i_bench.json`)", final))
         for name, tag in (("r2_e_bench_kmer.json", "configs[3] k-mer mode, 1 M reads 1–50 kb (`r2_e_bench_kmer.json`)"),
                           ("r2_e_bench_deep.json", "three-level hierarchy, 20,000 genomes, T = 64 (`r2_e_bench_deep.json`)"),
                           ("r2_e_bench_gtdb.json", "configs[4] shape: 102,400 user bins, 4096-bin root, 9.7 GB, 250 k reads per step (`r2_e_bench_gtdb.json`)")):
