@@ -66,7 +66,7 @@ def main():
         out.append(f"2 × B200 under torchrun (weak scaling, configs[1] index, `r2_d_bench_n2.json`; parity on both ranks: "
                    f"{n2['parity_at_scale']['reads']} reads, {n2['parity_at_scale']['mismatches']} mismatches): value "
                    f"{n2['value'] / 1e3:.1f} Gbases/s, e2e {n2['e2e']['value'] / 1e3:.1f} Gbases/s against {n1['value'] / 1e3:.1f} / "
-                   f"{n1['e2e']['value'] / 1e3:.1f} on one GPU of the same box ({n2['ms_per_step']:.1f} vs {n1['ms_per_step']:.1f} ms per step).")
+                   f"{n1['e2e']['value'] / 1e3:.1f} on one GPU of the same box ({n2['ms_per_step']:.1f} vs {n1['ms_per_step']:.1f} ms per step; run D, before the overlap was enabled).")
     cli = load("r2_e_cli_bench.json") or load("r2_d_cli_bench_gpus1_2.json")
     if cli:
         out.append("")
