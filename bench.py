@@ -537,6 +537,14 @@ def main():
         return 0
 
     # ---------------------------------------------------------------- our arm
+    # torchrun exports OMP_NUM_THREADS=1; the library's host pass (ordering the hits of a batch, OpenMP over reads) would then run
+    # on one thread per rank.  Give every rank its share of the host cores, as a user launching N processes would.
+    omp_threads = int(os.environ.get("TAXOR_BENCH_OMP", 0)) or max(1, cores // max(world, 1))
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1", mode=ctypes.RTLD_GLOBAL).omp_set_num_threads(omp_threads)
+    except OSError:
+        omp_threads = None
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -741,7 +749,7 @@ def main():
                                              "is the time the copies need even when perfectly overlapped)"}},
                 "gpu_launches": int(stage["launches"]),
                 "roofline": roof, "cpu_baseline": cpu, "parity_at_scale": parity, "clocks": clocks,
-                "index_build": ix.info, "host_cores": cores}
+                "index_build": ix.info, "host_cores": cores, "host_threads_per_rank": omp_threads}
         print(json.dumps(line))
         if parity is not None and not parity["ok"]:
             print("PARITY FAILURE at full size: " + json.dumps(parity), file=sys.stderr)
