@@ -349,13 +349,14 @@ class ClockSampler:
 _ORACLES = {}
 
 
-def cpu_oracle():
+def cpu_oracle(rebuild=True):
     """The CPU arm's library: the oracle restatement compiled ON THIS BOX with -O3 -march=native (oracle/Makefile `native`;
-    BASELINE.md section 2).  Falls back to the portable test build if the box has no compiler."""
+    BASELINE.md section 2).  Falls back to the portable test build if the box has no compiler.  Under torchrun rank 0 builds it
+    (rebuild=True) before a barrier and the other ranks load the file (rebuild=False)."""
     if "o" not in _ORACLES:
         from oracle.oracle import Oracle
         try:
-            _ORACLES["o"], _ORACLES["build"] = Oracle(native=True), "-O3 -march=native -ffp-contract=off, built on this box"
+            _ORACLES["o"], _ORACLES["build"] = Oracle(native=True, rebuild=rebuild), "-O3 -march=native -ffp-contract=off, built on this box"
         except Exception as e:                                     # no compiler on the box: say so in the line
             _ORACLES["o"], _ORACLES["build"] = Oracle(), f"portable -march=x86-64-v2 build (native build failed: {type(e).__name__})"
     return _ORACLES["o"]
@@ -481,10 +482,14 @@ def main():
         hx, info = build_index_arrays(args, genomes, lens, ctx)
         save_index(hx, d, info)
         hx.close()
+    if rank == 0 and not reference and not args.no_cpu_baseline:
+        cpu_oracle(rebuild=True)             # the native CPU-arm library: built once per box, by rank 0, before the barrier
     while not os.path.exists(done):          # the other ranks sleep (no spinning collective) while rank 0 builds
         time.sleep(1.0)
     if dist is not None:
         dist.barrier()
+    if rank != 0 and not args.no_cpu_baseline:
+        cpu_oracle(rebuild=False)
     ix = LoadedIndex(d)
     if not reference:
         upload_index(ctx, ix)

@@ -78,9 +78,11 @@ def build_native() -> str:
 
 
 class Oracle:
-    def __init__(self, native: bool = False) -> None:
+    def __init__(self, native: bool = False, rebuild: bool = True) -> None:
+        """native: the -march=native build made on THIS machine (bench.py's CPU arm); rebuild=False loads the file another
+        process of the same machine has just built (the ranks of a torchrun job must not all run make on one file)."""
         build()
-        L = self.lib = C.CDLL(build_native() if native else ORACLE_SO)
+        L = self.lib = C.CDLL((build_native() if rebuild or not os.path.exists(NATIVE_SO) else NATIVE_SO) if native else ORACLE_SO)
         L.orc_set_tuned.restype = None
         L.orc_set_tuned.argtypes = [C.c_int]
         L.orc_build_flags.restype = C.c_int
