@@ -3,8 +3,10 @@
 // Replaces the chunk loop + worker of search_single (src/main/taxor_search.cpp:196-326) for batches of reads:
 //   H2D packed reads -> kernel #1 (hash) -> dedup -> kernel #2 once per HIXF level -> D2H hits -> host: order the
 //   hits of every read in the reference's DFS pre-order (hixf.hpp:313-338), thresholds, 0.8*max filter flags.
-// The index is re-laid-out once into HBM (txr_index_upload); reads stream through `n_slots` pipeline slots,
-// each with its own stream, so the copy of batch i+1 overlaps the kernels of batch i.
+// The index is re-laid-out once into HBM (txr_index_upload: staged, multi-threaded; txr_index_clone: device to device);
+// reads stream through `n_slots` pipeline slots: each slot's own stream carries its copies, the probe kernels of all
+// batches run in batch order on one compute stream, and the hash + dedup kernels of batch i+1 run on a second stream beside
+// the probes of batch i where that was measured to win (enqueue_kernels: overlap, adaptive grids).
 #include "../../include/taxor_b200.h"
 #include "device_types.cuh"
 #include "ixf_arith.cuh"

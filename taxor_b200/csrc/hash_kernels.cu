@@ -5,9 +5,13 @@
 //   syncmer_generic_kernel  same for any (k,s,t): one thread per read, sequential restatement
 //   kmer_kernel             canonical k-mers XOR seed (replaces seq | minimiser_hash with window == k,
 //                           src/main/taxor_search.cpp:210-212,240-256)
-//   dedup_smem_kernel /     per-read distinct set (the ankerl::unordered_dense::set of syncmer.cpp:145) and the
-//   dedup_global_kernel /   FracMin scaling filter (taxor_search.cpp:223-233, 244-251)
+//   dedup_warp_kernel /     per-read distinct set (the ankerl::unordered_dense::set of syncmer.cpp:145) and the
+//   dedup_smem_kernel /     FracMin scaling filter (taxor_search.cpp:223-233, 244-251); syncmer_kernel can also build the
+//   dedup_global_kernel /   set itself while hashing (HashArgs::fuse_dedup, measured slower, off by default)
 //   filter_kernel
+//   binset_*_kernel         build side: per-user-bin distinct sets (compute_hashes.cpp:76-142)
+// The hash-stage kernels have adaptive grids (yield_to_probes): launched for the whole GPU, their CTAs beyond a small share
+// leave while probe kernels of the previous batch are running (engine.cu: overlap).
 //
 // Design (not a translation): reads are 2-bit packed MSB-first, so the forward code of any s-mer / k-mer is a
 // bit field of the packed stream and its reverse complement is a bit field of the bit-reversed, complemented

@@ -8,12 +8,19 @@
 // split-bin runs that reach it append (read, user bin, count) to the hit list.  Hits of one read are put into
 // the reference's DFS pre-order on the host (engine.cu).
 //
-// HBM-bound random gather: per hash three rows of `tbins` bytes.  A lane owns 16 consecutive bins (one 16-byte
-// load per row); tbins/16 lanes cover a row, so a warp probes 32/(tbins/16) hashes per step.  Hits are detected
-// with a branch-free zero-byte test on r0^r1^r2^splat(f) and accumulated in byte-packed registers, spilled to
-// 32-bit shared-memory counters at most every 255 steps.  Loads of the next step are issued before the current
-// step is reduced (register double buffering); the index has no reuse, so rows are fetched with
-// ld.global.nc.L1::no_allocate.
+// HBM-bound random gather: per hash three rows of `tbins` bytes.
+//   rows <= 512 bytes (ixf_query_small_kernel): one warp per item; a lane owns 16 consecutive bins (one 16-byte load per
+//     row); tbins/16 lanes cover a row, so a warp probes 32/(tbins/16) hashes per step.  UNROLL steps are in flight per warp;
+//     the keys of a step are loaded one step ahead (the hash lists of a batch are GBs, i.e. DRAM).  Builds: two steps in
+//     flight at 64 / 70 registers (8 / 7 CTAs per SM) for a kernel that owns the GPU, one step at 40 / 32 registers for
+//     the probes that share the SMs with the hash stage of the next batch (engine.cu: overlap).
+//   rows > 512 bytes (ixf_query_large_kernel): one CTA per item, the hash list dealt to the 8 warps, every warp covers whole
+//     rows in 2 KB passes (the wide roots of GTDB-scale indexes).
+// Hits are detected with a branch-free zero-byte test on r0^r1^r2^splat(f) and accumulated in byte-packed registers,
+// spilled to 32-bit shared-memory counters at most every 255 steps.  The index has no reuse at the root, so rows are fetched
+// with ld.global.nc.L1::no_allocate (64-byte rows: with the .L2::64B prefetch-size hint, two DRAM sectors instead of a
+// line).  The probe arithmetic is either the prototype's with folded constants or driven by the descriptor the index was
+// uploaded with (probe_address<GEN>, ixf_arith.cuh).
 #include "device_types.cuh"
 #include "ixf_arith.cuh"
 
