@@ -27,11 +27,11 @@ def bench_row(tag, d):
 
 def main():
     out = []
-    final = load("r2_i_bench.json") or load("r2_e_bench.json")
+    final = load("r2_final_bench.json") or load("r2_i_bench.json")
     if final:
         out.append("| workload (1 × B200) | value Gbases/s | ms/step | hash / dedup / query ms | e2e Gbases/s | e2e ms/step | kernel #2 GB/s | frac of measured HBM | CPU port Gbases/s |")
         out.append("|---|---|---|---|---|---|---|---|---|")
-        out.append(bench_row("configs[1], 10.15 GB index, 1 M × 10 kb (`r2_i_bench.json`)", final))
+        out.append(bench_row("configs[1], 10.15 GB index, 1 M × 10 kb (`r2_final_bench.json`)", final))
         for name, tag in (("r2_e_bench_kmer.json", "configs[3] k-mer mode, 1 M reads 1–50 kb (`r2_e_bench_kmer.json`)"),
                           ("r2_e_bench_deep.json", "three-level hierarchy, 20,000 genomes, T = 64 (`r2_e_bench_deep.json`)"),
                           ("r2_e_bench_gtdb.json", "configs[4] shape: 102,400 user bins, 4096-bin root, 9.7 GB, 250 k reads per step (`r2_e_bench_gtdb.json`)")):
@@ -54,7 +54,7 @@ def main():
                        f"hash {st['hash']:.1f} / dedup {st['dedup']:.1f} ms; the serial schedule takes {sa['ms_per_step_serial_schedule']:.1f} ms per step "
                        f"against {final['ms_per_step']:.1f} with the overlap.  As random row reads: {ra.get('achieved_G_rows_per_s', 0):.1f} G rows/s in the "
                        f"(overlapped) timed region, {ra.get('vs_microbench', 0):.2f}× the one-row gather microbenchmark ({ra.get('microbench_G_rows_per_s', 0):.1f} G rows/s).")
-    ref = load("r2_e_bench_reference_arm.json") or load("r2_c_bench_reference_arm.json")
+    ref = load("r2_final_bench_reference_arm.json") or load("r2_e_bench_reference_arm.json")
     if ref and final:
         v = ref["cpu_baseline"].get("variants", {})
         out.append(f"Reference arm (`bench.py --impl reference`: the restated CPU path built with `-O3 -march=native -ffp-contract=off` on the "
