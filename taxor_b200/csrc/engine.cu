@@ -326,6 +326,9 @@ struct txr_ctx
     SmFilter smf_hash{0, 0, 0}, smf_query{0, 0, 0}; // filters of the batch being enqueued ...
     int shape_query{0}, shape_level{0}, shape_hash{0}, shape_dedup{0}; // ... and its CTAs per SM (0: fill the SM)
     cudaEvent_t fork_ev{nullptr}, join_ev{nullptr};
+    bool trace{false};                 // TXR_TRACE=1
+    cudaEvent_t trace_ev{nullptr};
+    std::chrono::steady_clock::time_point trace_t0{};
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -984,6 +987,17 @@ static int collect_batch(txr_ctx *c, Slot &s, bool fetch)
     c->timing.dedup_ms += ms;
     cudaEventElapsedTime(&ms, s.ev[8], s.ev[4]);
     c->timing.query_ms += ms;
+    if (c->trace && c->trace_ev)
+    {
+        // TXR_TRACE=1: when each stage of the batch started and ended, in ms since the call's fork (stderr; experiments only)
+        float t[8] = {0};
+        const int idx[8] = {0, 1, 6, 2, 3, 8, 4, 7};
+        for (int i = 0; i < 8; ++i)
+            cudaEventElapsedTime(&t[i], c->trace_ev, s.ev[idx[i]]);
+        const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c->trace_t0).count();
+        fprintf(stderr, "[txr trace] reads %u..+%u  h2d %.2f-%.2f  hash %.2f-%.2f  dedup -%.2f  query %.2f-%.2f  done %.2f  (collected at host %.2f)\n",
+                (unsigned)m.first_read, m.n_reads, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], host_ms);
+    }
 
     if (fetch)
     {
@@ -1109,6 +1123,13 @@ static int fork_streams(txr_ctx *c)
         CU(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
     }
     CU(cudaEventRecord(c->fork_ev, c->primary));
+    if (c->trace)
+    {
+        if (!c->trace_ev)
+            CU(cudaEventCreate(&c->trace_ev));
+        CU(cudaEventRecord(c->trace_ev, c->primary));
+        c->trace_t0 = std::chrono::steady_clock::now();
+    }
     CU(cudaStreamWaitEvent(c->compute, c->fork_ev, 0));
     CU(cudaStreamWaitEvent(c->compute_hash, c->fork_ev, 0));
     for (auto &s : c->slots)
@@ -1192,6 +1213,8 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->l2_sector64 = (uint32_t)atoi(e);
     if (const char *e = getenv("TXR_QUERY_REGS"))
         c->query_regs32 = atoi(e) == 32;
+    if (const char *e = getenv("TXR_TRACE"))
+        c->trace = atoi(e) != 0;
     if (const char *e = getenv("TXR_ADAPTIVE"))
         c->adaptive = atoi(e) != 0;
     if (const char *e = getenv("TXR_RAMP"))
