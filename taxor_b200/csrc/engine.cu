@@ -296,6 +296,7 @@ struct txr_ctx
     uint32_t query_regs32{0};  // TXR_QUERY_REGS=32: the 32-register build of the one-step probe kernel whatever the CTA count
     bool adaptive{true};       // TXR_ADAPTIVE=0: fixed small grids for the hash stage beside the probes
     double ramp{1.8};          // growth of the batch sizes of a host-fed search (TXR_RAMP)
+    double ramp_cum{0.0};      // TXR_RAMP_CUM: cap of a batch as a fraction of the reads submitted before it (0: off)
     int hash_regs{0};          // TXR_HASH_REGS=5: the 102-register variant of the syncmer kernel (5 CTAs per SM)
     uint32_t query_unroll{0};  // TXR_QUERY_UNROLL: probe steps in flight per warp (experiments with fewer probe CTAs per SM)
     uint32_t fuse_max_keys{kWarpMaxKeys}; // TXR_FUSE_MAX_KEYS lowers it (tests: forces the hand-over to the CTA-per-read kernel)
@@ -1217,6 +1218,8 @@ int txr_ctx_create(int device, txr_ctx **out)
         c->trace = atoi(e) != 0;
     if (const char *e = getenv("TXR_ADAPTIVE"))
         c->adaptive = atoi(e) != 0;
+    if (const char *e = getenv("TXR_RAMP_CUM"))
+        c->ramp_cum = atof(e);
     if (const char *e = getenv("TXR_RAMP"))
         c->ramp = std::max(1.05, atof(e));
     if (const char *e = getenv("TXR_HASH_REGS"))
@@ -1915,8 +1918,13 @@ static int search_host_impl(txr_ctx *c, const uint64_t *words, const uint64_t *w
             if (done.busy)
                 TRY(collect_batch(c, done, true));
         }
-        const uint64_t max_reads = std::max<uint64_t>((uint64_t)((double)c->max_batch_reads * scale), 1);
+        uint64_t max_reads = std::max<uint64_t>((uint64_t)((double)c->max_batch_reads * scale), 1);
         const uint64_t max_bases = std::max<uint64_t>((uint64_t)((double)c->max_batch_bases * scale), 1);
+        // With the hash stage of batch b+1 running beside the probes of batch b, a batch must not be much larger than what was
+        // submitted before it: its copy ends late and its (slowed) hash stage would outlast the probes it hides behind
+        // (profiles/r2_trace_e2e_timeline.txt).  Cap: a fraction of all reads submitted so far, never below 1/4 of a full batch.
+        if (c->ramp_cum > 0 && overlap_applies(c))
+            max_reads = std::min<uint64_t>(max_reads, std::max<uint64_t>((uint64_t)(c->ramp_cum * (double)next_read), c->max_batch_reads / 4));
         uint64_t bases = 0, j = next_read;
         while (j < n_reads && j - next_read < max_reads && (j == next_read || bases + len[j] <= max_bases))
             bases += len[j++];
