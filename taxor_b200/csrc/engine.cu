@@ -296,7 +296,7 @@ struct txr_ctx
     uint32_t query_regs32{0};  // TXR_QUERY_REGS=32: the 32-register build of the one-step probe kernel whatever the CTA count
     bool adaptive{true};       // TXR_ADAPTIVE=0: fixed small grids for the hash stage beside the probes
     double ramp{1.8};          // growth of the batch sizes of a host-fed search (TXR_RAMP)
-    double ramp_cum{0.0};      // TXR_RAMP_CUM: cap of a batch as a fraction of the reads submitted before it (0: off)
+    double ramp_cum{0.35};     // TXR_RAMP_CUM: cap of a batch as a fraction of the reads submitted before it (0: off; 93.5 -> 91.7 ms e2e, profiles/r2_m_ramp_cum.txt)
     int hash_regs{0};          // TXR_HASH_REGS=5: the 102-register variant of the syncmer kernel (5 CTAs per SM)
     uint32_t query_unroll{0};  // TXR_QUERY_UNROLL: probe steps in flight per warp (experiments with fewer probe CTAs per SM)
     uint32_t fuse_max_keys{kWarpMaxKeys}; // TXR_FUSE_MAX_KEYS lowers it (tests: forces the hand-over to the CTA-per-read kernel)
@@ -1924,7 +1924,7 @@ static int search_host_impl(txr_ctx *c, const uint64_t *words, const uint64_t *w
         // submitted before it: its copy ends late and its (slowed) hash stage would outlast the probes it hides behind
         // (profiles/r2_trace_e2e_timeline.txt).  Cap: a fraction of all reads submitted so far, never below 1/4 of a full batch.
         if (c->ramp_cum > 0 && overlap_applies(c))
-            max_reads = std::min<uint64_t>(max_reads, std::max<uint64_t>((uint64_t)(c->ramp_cum * (double)next_read), c->max_batch_reads / 4));
+            max_reads = std::min<uint64_t>(max_reads, std::max<uint64_t>({(uint64_t)(c->ramp_cum * (double)next_read), c->max_batch_reads / 4, (uint64_t)1}));
         uint64_t bases = 0, j = next_read;
         while (j < n_reads && j - next_read < max_reads && (j == next_read || bases + len[j] <= max_bases))
             bases += len[j++];
