@@ -1,6 +1,7 @@
 """not gpu: SURVEY 8(f) rank 3 -- the head of `taxor profile` (parse_search_results + the three reference-filter rounds) in the
 product (txr_profile_*, host code) against the REFERENCE'S OWN src/main/taxor_profile.cpp compiled in place (oracle/_ref)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -129,3 +130,21 @@ def test_profile_in_memory_feed_equals_the_file_round_trip(tmp_path, reference):
     with pytest.raises(capi.TaxorError, match="columns"):
         bad.add_file(tmp_path / "short.tsv")
     bad.close()
+
+
+def test_profile_fuzz_under_sanitizers(tmp_path):
+    """tests/fuzz/profile_fuzz.cpp built with -fsanitize=address,undefined: damaged result files through add_file, the three
+    filter rounds and both read-out calls; rejected with a message or accepted and consistent, never a crash."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    exe = str(tmp_path / "profile_fuzz")
+    build = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", exe,
+                            os.path.join(root, "tests/fuzz/profile_fuzz.cpp"), os.path.join(root, "taxor_b200/csrc/profile_ingest.cpp")],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr.lower():
+        pytest.skip("compiler without sanitizer runtimes")
+    assert build.returncode == 0, build.stderr[-2000:]
+    run = subprocess.run([exe, str(tmp_path / "r.tsv"), "1500", "5"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "fuzz ok" in run.stdout, run.stdout[-500:] + run.stderr[-3000:]
