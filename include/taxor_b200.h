@@ -158,6 +158,7 @@ int txr_pack_2bit(const char *ascii, uint64_t len, uint64_t *dst_words);     /* 
 int txr_pack_codes(const uint8_t *codes, uint64_t len, uint64_t *dst_words); /* codes 0..3 */
 int txr_unpack_codes(const uint64_t *words, uint64_t len, uint8_t *codes);
 void *txr_host_alloc(size_t bytes);                                          /* pinned host memory */
+void *txr_ctx_host_alloc(txr_ctx *ctx, size_t bytes);   /* the same from any thread: makes ctx's device current first */
 void txr_host_free(void *p);
 
 /* ---- search: replaces the per-read body of `worker` (taxor_search.cpp:196-313) for n_reads reads ---- */

@@ -95,6 +95,8 @@ def lib():
     L.txr_unpack_codes.argtypes = [vp, C.c_uint64, vp]
     L.txr_host_alloc.argtypes = [C.c_size_t]
     L.txr_host_alloc.restype = vp
+    L.txr_ctx_host_alloc.argtypes = [vp, C.c_size_t]
+    L.txr_ctx_host_alloc.restype = vp
     L.txr_host_free.argtypes = [vp]
     L.txr_host_free.restype = None
     L.txr_search.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(Result)]
@@ -122,7 +124,7 @@ def lib():
 
 EXPORTED = ["txr_last_error", "txr_version", "txr_ctx_create", "txr_ctx_destroy", "txr_ctx_set_stream", "txr_ctx_configure",
             "txr_ctx_reserve", "txr_index_upload", "txr_index_clone", "txr_params_set", "txr_threshold_get", "txr_threshold_eval", "txr_packed_words", "txr_pack_2bit",
-            "txr_pack_codes", "txr_unpack_codes", "txr_host_alloc", "txr_host_free", "txr_search",
+            "txr_pack_codes", "txr_unpack_codes", "txr_host_alloc", "txr_ctx_host_alloc", "txr_host_free", "txr_search",
             "txr_reads_upload", "txr_reads_free", "txr_search_resident", "txr_get_timing", "txr_hash_batch",
             "txr_hash_user_bins", "txr_plan_segments", "txr_ixf_bulk_count",
             "txr_profile_last_error", "txr_profile_create", "txr_profile_destroy", "txr_profile_add_batch", "txr_profile_add_file",

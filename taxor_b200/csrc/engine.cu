@@ -1847,6 +1847,20 @@ void *txr_host_alloc(size_t bytes)
     }
     return p;
 }
+void *txr_ctx_host_alloc(txr_ctx *c, size_t bytes)
+{
+    if (!c)
+    {
+        set_error(TXR_ERR_ARG, "null context");
+        return nullptr;
+    }
+    if (cudaSetDevice(c->device) != cudaSuccess)
+    {
+        set_error(TXR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+        return nullptr;
+    }
+    return txr_host_alloc(bytes);
+}
 void txr_host_free(void *p)
 {
     if (p)

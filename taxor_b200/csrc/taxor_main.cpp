@@ -422,6 +422,44 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
             ctx_err[i] = txr_last_error();
     };
     make_ctx(0);
+    // The pinned chunk pool (scan -> pack jobs -> GPU workers -> ordered writer) is allocated on its own thread from here on:
+    // pinning ~100 MB per chunk costs tens of ms each, which used to sit between the upload and the first parsed byte; now the
+    // buffers come up while the index is uploaded, and parsing starts as soon as ONE exists.
+    const size_t n_chunks = 2 * devices.size() + 2;
+    std::vector<Chunk> pool(n_chunks);
+    Channel<Chunk *> free_q, work_q, done_q;
+    std::string pool_error;
+    double t_pool = 0;
+    std::thread pool_thread;
+    struct JoinOnExit // the allocation thread never outlives `pool`, whatever is thrown below
+    {
+        std::thread &t;
+        ~JoinOnExit()
+        {
+            if (t.joinable())
+                t.join();
+        }
+    } pool_join{pool_thread};
+    if (ctx_err[0].empty())
+        pool_thread = std::thread([&] {
+            const auto t0 = std::chrono::steady_clock::now();
+            for (auto &ch : pool)
+            {
+                ch.words_cap = kChunkBases / 32 + 2 * kChunkReads + 64;
+                ch.words = static_cast<uint64_t *>(txr_ctx_host_alloc(ctxs[0], ch.words_cap * 8));
+                if (!ch.words)
+                {
+                    pool_error = txr_last_error();
+                    free_q.close(); // the assembler finds the pool dry instead of waiting for ever
+                    return;
+                }
+                ch.ids.resize(kChunkReads);
+                ch.len.resize(kChunkReads);
+                ch.word_off.resize(kChunkReads);
+                free_q.push(&ch);
+            }
+            t_pool = since(t0);
+        });
     std::vector<std::thread> ctx_threads;
     for (size_t i = 1; i < devices.size(); ++i)
         ctx_threads.emplace_back(make_ctx, i);
@@ -462,21 +500,11 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
 #ifdef _OPENMP
     omp_set_num_threads((int)n_pack); // block-parallel BGZF inflation inside the scanner obeys --threads as well
 #endif
-    const size_t n_chunks = 2 * ctxs.size() + 2;
-    std::vector<Chunk> pool(n_chunks);
-    Channel<Chunk *> free_q, work_q, done_q;
     Channel<std::function<void()>> jobs;
-    for (auto &ch : pool)
-    {
-        ch.words_cap = kChunkBases / 32 + 2 * kChunkReads + 64;
-        ch.words = static_cast<uint64_t *>(txr_host_alloc(ch.words_cap * 8));
-        if (!ch.words)
-            throw std::runtime_error(txr_last_error());
-        ch.ids.resize(kChunkReads);
-        ch.len.resize(kChunkReads);
-        ch.word_off.resize(kChunkReads);
-        free_q.push(&ch);
-    }
+    // where the phase goes (TAXOR_TIMING=1): seconds the assembler waited for a scanned segment / for a free chunk, seconds the
+    // GPU workers spent in txr_search / formatting, seconds the writer spent writing
+    double w_seg = 0, w_chunk = 0, w_write = 0;
+    std::atomic<uint64_t> us_search{0}, us_format{0}, us_scan{0}, us_pack{0};
     std::string worker_error;
     std::mutex err_m;
     std::atomic<uint64_t> n_reads_total{0}, n_reads_hit{0};
@@ -492,7 +520,12 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
                 txr_result res{};
                 if (failed.load()) // after the first failure no context is searched again; the chunks only circulate
                     ch->text.clear();
-                else if (txr_search(c, ch->words, ch->word_off.data(), ch->len.data(), ch->n, &res) != TXR_OK)
+                else if ([&] {
+                             const auto t0 = std::chrono::steady_clock::now();
+                             const int rc = txr_search(c, ch->words, ch->word_off.data(), ch->len.data(), ch->n, &res);
+                             us_search += (uint64_t)(since(t0) * 1e6);
+                             return rc;
+                         }() != TXR_OK)
                 {
                     std::lock_guard<std::mutex> l(err_m);
                     if (worker_error.empty())
@@ -502,7 +535,9 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
                 }
                 else
                 {
+                    const auto t0 = std::chrono::steady_clock::now();
                     format_chunk(*ch, res, idx, user_bin_index);
+                    us_format += (uint64_t)(since(t0) * 1e6);
                     uint64_t hit = 0;
                     for (size_t r = 0; r < ch->n; ++r)
                         hit += res.hit_begin[r + 1] > res.hit_begin[r];
@@ -523,7 +558,9 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
             {
                 Chunk *w = pending.begin()->second;
                 pending.erase(pending.begin());
+                const auto t0 = std::chrono::steady_clock::now();
                 out << w->text; // sync_out::write (:311): here in read order
+                w_write += since(t0);
                 ++next;
                 free_q.push(w);
             }
@@ -554,6 +591,7 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
         jobs.push([&, hold, base, recs, count, chp, first_read] {
             Chunk &ch = *chp;
             thread_local std::string scratch;
+            const auto t0 = std::chrono::steady_clock::now();
             for (uint32_t k = 0; k < count && !failed.load(std::memory_order_relaxed); ++k)
             {
                 const RecordRef &r = recs[k];
@@ -576,6 +614,7 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
                         ch.len[idx] = (uint32_t)scratch.size();
                 }
             }
+            us_pack += (uint64_t)(since(t0) * 1e6);
             if (ch.pending.fetch_sub(1) == 1)
                 work_q.push(&ch);
         });
@@ -600,7 +639,13 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
         {
             if (!cur)
             {
-                free_q.pop(cur);
+                const auto t0 = std::chrono::steady_clock::now();
+                if (!free_q.pop(cur)) // only a failed pool allocation closes this queue
+                {
+                    cur = nullptr;
+                    throw std::runtime_error(pool_error.empty() ? "chunk pool exhausted" : pool_error);
+                }
+                w_chunk += since(t0);
                 cur->n = 0;
                 cur->words_used = 0;
                 cur->pending = 1;
@@ -664,8 +709,10 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
                     auto sg = std::make_shared<Segment>();
                     segs[dispatched] = sg;
                     const size_t lo = dispatched * kRawTarget, hi = std::min(size, lo + kRawTarget);
-                    jobs.push([&seg_m, &seg_cv, sg, lo, hi, data, size, first, marker] {
+                    jobs.push([&seg_m, &seg_cv, &us_scan, sg, lo, hi, data, size, first, marker] {
+                        const auto t0 = std::chrono::steady_clock::now();
                         scan_byte_range(data, size, first, marker, lo, hi, *sg);
+                        us_scan += (uint64_t)(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e6);
                         {
                             std::lock_guard<std::mutex> l(seg_m);
                             sg->done = true;
@@ -680,8 +727,10 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
                 dispatch(k + 2 * n_pack + 2);
                 std::shared_ptr<Segment> sg = segs[k];
                 {
+                    const auto t0 = std::chrono::steady_clock::now();
                     std::unique_lock<std::mutex> l(seg_m);
                     seg_cv.wait(l, [&] { return sg->done; });
+                    w_seg += since(t0);
                 }
                 segs[k].reset();
                 const size_t hi = std::min(size, (k + 1) * kRawTarget);
@@ -714,6 +763,8 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
         fail(e.what());
         seal();
     }
+    if (pool_thread.joinable())
+        pool_thread.join();
     jobs.close();
     for (auto &t : job_threads)
         t.join();
@@ -729,7 +780,10 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
             fp_bytes += 3 * x.seg_len * x.tbins;
         std::cerr << "[taxor timing] index load " << t_load << " s, upload to " << ctxs.size() << " GPU(s) " << t_upload << " s ("
                   << fp_bytes / 1e9 << " GB), ingest+search+write " << since(t_search) << " s, " << seq << " chunks, " << n_pack
-                  << " pack threads\n";
+                  << " pack threads\n"
+                  << "[taxor timing]   chunk pool " << t_pool << " s (on its own thread, from the start of the upload); assembler waited " << w_seg << " s for scans, " << w_chunk
+                  << " s for a free chunk; job threads: scan " << us_scan / 1e6 << " s, pack " << us_pack / 1e6 << " s (summed over threads); GPU workers: search "
+                  << us_search / 1e6 << " s, format " << us_format / 1e6 << " s; writer " << w_write << " s\n";
     }
     // nothing at all matched: with a reference-built index that is what a wrong guess of the (unpinned) record order or
     // filter arithmetic looks like -- every probe misses silently.  Say it loudly instead.
