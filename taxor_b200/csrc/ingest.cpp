@@ -1,4 +1,5 @@
 #include "ingest.hpp"
+#include "inflate_fast.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -129,7 +130,23 @@ RecordScanner::RecordScanner(const std::string &path)
                 munmap(m, (size_t)st.st_size);
         }
     }
-    if (n >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) // gzip: inflate through zlib, everything else is read() directly
+    if (n >= 2 && magic[0] == 0x1f && magic[1] == 0x8b && fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0 &&
+        !(getenv("TAXOR_GZIP") && !strcmp(getenv("TAXOR_GZIP"), "zlib")))
+    {
+        // gzip in a regular file: map it and decode with the word-at-a-time inflater
+        void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd_, 0);
+        if (m != MAP_FAILED)
+        {
+            gzmap_ = static_cast<const unsigned char *>(m);
+            gzmap_size_ = (size_t)st.st_size;
+            madvise(m, gzmap_size_, MADV_SEQUENTIAL);
+            gzs_ = new GzipStream(gzmap_, gzmap_size_);
+            ::close(fd_);
+            fd_ = -1;
+            return;
+        }
+    }
+    if (n >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) // gzip that cannot be mapped: inflate through zlib; everything else is read() directly
     {
         gz_ = gzdopen(fd_, "rb");
         if (!gz_)
@@ -158,6 +175,9 @@ RecordScanner::~RecordScanner()
     }
     if (bgzf_data_)
         munmap(const_cast<unsigned char *>(bgzf_data_), bgzf_size_);
+    delete static_cast<GzipStream *>(gzs_);
+    if (gzmap_)
+        munmap(const_cast<unsigned char *>(gzmap_), gzmap_size_);
     if (gz_)
         gzclose(gz_);
     if (fd_ >= 0)
@@ -240,21 +260,8 @@ size_t RecordScanner::fill_bgzf(char *dst, size_t cap)
         for (long i = 0; i < (long)blocks.size(); ++i)
         {
             const Block &b = blocks[(size_t)i];
-            z_stream zs{};
-            if (inflateInit2(&zs, -15) != Z_OK)
-            {
-#pragma omp atomic write
-                bad = 1;
-                continue;
-            }
-            zs.next_in = const_cast<unsigned char *>(bgzf_data_ + b.in);
-            zs.avail_in = (unsigned)b.in_len;
-            zs.next_out = reinterpret_cast<unsigned char *>(dst + b.out);
-            zs.avail_out = (unsigned)b.out_len;
-            const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END || zs.total_out != b.out_len ||
-                crc32(0, reinterpret_cast<const unsigned char *>(dst + b.out), (unsigned)b.out_len) != b.crc)
+            uint8_t *const o = reinterpret_cast<uint8_t *>(dst + b.out);
+            if (!inflate_raw_exact(bgzf_data_ + b.in, b.in_len, o, b.out_len) || crc32_fast(0, o, b.out_len) != b.crc)
             {
 #pragma omp atomic write
                 bad = 1;
@@ -326,6 +333,13 @@ size_t RecordScanner::fill(char *dst, size_t cap)
         return fill_bgzf(dst, cap);
     if (bz_)
         return fill_bz2(dst, cap);
+    if (gzs_)
+    {
+        const size_t n = static_cast<GzipStream *>(gzs_)->read(reinterpret_cast<uint8_t *>(dst), cap);
+        if (n < cap)
+            eof_ = true;
+        return n;
+    }
     size_t got = 0;
     while (got < cap && !eof_)
     {

@@ -33,7 +33,7 @@ public:
     ~RecordScanner();
     RecordScanner(const RecordScanner &) = delete;
     RecordScanner &operator=(const RecordScanner &) = delete;
-    bool ok() const { return fd_ >= 0 || gz_ != nullptr || bgzf_data_ != nullptr; }
+    bool ok() const { return fd_ >= 0 || gz_ != nullptr || bgzf_data_ != nullptr || gzs_ != nullptr; }
     const std::string &open_error() const { return open_error_; } // why ok() is false, when there is more to say than "cannot open"
     // Fills `buf` (resized as needed; `target` bytes unless one record needs more) and appends the descriptors of
     // the complete records it holds to `recs` (cleared first).  The incomplete tail is kept for the next call.
@@ -60,6 +60,11 @@ private:
     size_t fill_bz2(char *dst, size_t cap);
     void *bz_{nullptr};           // BzState
     std::string open_error_;
+    // single-stream gzip in a regular file: mapped and decoded by GzipStream (inflate_fast.hpp); zlib's gzread (gz_) is kept for
+    // input that cannot be mapped and behind TAXOR_GZIP=zlib
+    const unsigned char *gzmap_{nullptr};
+    size_t gzmap_size_{0};
+    void *gzs_{nullptr}; // GzipStream
 };
 
 // ---- plain (not gzip) files: mapped, cut into byte segments, segments scanned in parallel ----

@@ -212,10 +212,54 @@ def test_ingest_fuzz_under_sanitizers(tmp_path):
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
     exe = str(tmp_path / "ingest_fuzz")
     build = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fopenmp", "-o", exe,
-                            os.path.join(root, "tests/fuzz/ingest_fuzz.cpp"), os.path.join(root, "taxor_b200/csrc/ingest.cpp"), "-lz"],
+                            os.path.join(root, "tests/fuzz/ingest_fuzz.cpp"), os.path.join(root, "taxor_b200/csrc/ingest.cpp"),
+                            os.path.join(root, "taxor_b200/csrc/inflate_fast.cpp"), "-lz", "-ldl"],
                            capture_output=True, text=True)
     if build.returncode != 0 and "sanitize" in build.stderr.lower():
         pytest.skip("compiler without sanitizer runtimes")
     assert build.returncode == 0, build.stderr[-2000:]
     run = subprocess.run([exe, str(tmp_path / "f.txt"), "3000", "11"], capture_output=True, text=True, timeout=300)
     assert run.returncode == 0 and "fuzz ok" in run.stdout, run.stdout[-500:] + run.stderr[-3000:]
+
+
+def test_fast_inflater_against_zlib_under_sanitizers(tmp_path):
+    """tests/fuzz/inflate_fuzz.cpp built with -fsanitize=address,undefined: the ingest's own DEFLATE / gzip decoder against zlib --
+    every block type, level and strategy, flush points, several members, reads of random size; the whole-buffer (BGZF) form;
+    damaged and truncated streams; the carry-less-multiply CRC.  Both builds of the symbol loop (BMI2 and baseline)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    exe = str(tmp_path / "inflate_fuzz")
+    build = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", exe,
+                            os.path.join(root, "tests/fuzz/inflate_fuzz.cpp"), os.path.join(root, "taxor_b200/csrc/inflate_fast.cpp"), "-lz"],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr.lower():
+        pytest.skip("compiler without sanitizer runtimes")
+    assert build.returncode == 0, build.stderr[-2000:]
+    for isa, seed in (("", "21"), ("generic", "22")):
+        run = subprocess.run([exe, "120", seed], capture_output=True, text=True, timeout=600, env=dict(os.environ, TAXOR_INFLATE_ISA=isa))
+        assert run.returncode == 0 and "fuzz ok" in run.stdout and "runtime error" not in run.stderr, run.stdout[-500:] + run.stderr[-3000:]
+
+
+def test_gzip_paths_agree(tmp_path):
+    """single-member, multi-member and BGZF-less gzip through the mapped fast decoder and through zlib (TAXOR_GZIP=zlib, in a
+    fresh process because the choice is read when the scanner opens the file): the same records"""
+    import subprocess
+    import sys
+    rng = np.random.default_rng(11)
+    recs = [(b"r%d some text" % i, _rand_seq(rng, int(rng.integers(0, 5000)))) for i in range(300)]
+    blob = b"".join(b"@" + i + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n" for i, s in recs)
+    one = tmp_path / "one.fq.gz"
+    one.write_bytes(gzip.compress(blob, 6))
+    cut = len(blob) // 2
+    two = tmp_path / "two.fq.gz"
+    two.write_bytes(gzip.compress(blob[:cut], 9) + gzip.compress(blob[cut:], 1) + b"\0" * 7)
+    for path in (one, two):
+        assert _dump(path, 1 << 16, tmp_path) == recs
+        code = ("import sys; sys.path.insert(0, %r); from tests import test_ingest as T; import pathlib; "
+                "r = T._dump(pathlib.Path(%r), 1 << 16, pathlib.Path(%r)); print(len(r), hash(tuple(r)))" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(path), str(tmp_path)))
+        a = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, TAXOR_GZIP="zlib", PYTHONHASHSEED="0"))
+        b = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONHASHSEED="0"))
+        assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+        assert a.stdout == b.stdout and a.stdout.split()[0] == str(len(recs))
