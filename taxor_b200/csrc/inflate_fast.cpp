@@ -163,6 +163,9 @@ void pair_literals(uint32_t *tab, unsigned tb)
 
 void Inflater::reset(const uint8_t *in, size_t n)
 {
+    base_ = in;
+    stop_bit_ = ~uint64_t(0);
+    stopped_ = false;
     p_ = in;
     end_ = in + n;
     buf_ = 0;
@@ -345,7 +348,7 @@ void Inflater::read_block_header()
 // Fast: the caller guarantees >= 32 input bytes and >= kMargin bytes of room at entry; the loop re-checks both before every
 // refill and leaves when one no longer holds.  No per-symbol bounds checks inside.  The literal/length entry of the NEXT
 // symbol is loaded before a match is copied, so that its latency hides behind the copy.
-__attribute__((always_inline)) inline uint8_t *Inflater::fast_body(const uint8_t *hist, uint8_t *out, uint8_t *out_end, bool &block_ended)
+template <class T> __attribute__((always_inline)) inline T *Inflater::fast_body(const T *hist, T *out, T *out_end, bool &block_ended)
 {
     constexpr uint32_t lmask = (1u << kLitBits) - 1, dmask = (1u << kDistBits) - 1;
     const uint32_t *const lit = lit_, *const dist = dist_;
@@ -360,12 +363,18 @@ __attribute__((always_inline)) inline uint8_t *Inflater::fast_body(const uint8_t
         p += (63 - cnt) >> 3;       \
         cnt |= 56;                  \
     } while (0)
-#define TXR_LITERAL(e)                  \
-    do                                  \
-    {                                   \
-        TXR_CONSUME((e)&0xff);          \
-        store16(out, (e) >> 16);        \
-        out += 1 + (((e) >> 8) & 1);    \
+#define TXR_LITERAL(e)                            \
+    do                                            \
+    {                                             \
+        TXR_CONSUME((e)&0xff);                    \
+        if (sizeof(T) == 1)                       \
+            store16((uint8_t *)out, (e) >> 16);   \
+        else                                      \
+        {                                         \
+            out[0] = (T)(((e) >> 16) & 0xff);     \
+            out[1] = (T)((e) >> 24);              \
+        }                                         \
+        out += 1 + (((e) >> 8) & 1);              \
     } while (0)
 #define TXR_ROOM() (end - p >= 32 && out_end - out >= (ptrdiff_t)kMargin)
     TXR_REFILL();
@@ -434,47 +443,53 @@ __attribute__((always_inline)) inline uint8_t *Inflater::fast_body(const uint8_t
         const size_t distance = TXR_VALUE(e, saved);
         if (distance > (size_t)(out - hist))
             bad("match distance reaches before the start of the data");
-        const uint8_t *src = out - distance;
-        uint8_t *const stop = out + length;
+        T *const stop = out + length;
         const bool more = end - p >= 32 && out_end - stop >= (ptrdiff_t)kMargin;
         if (more)
         {
             TXR_REFILL();
             e = lit[buf & lmask];
         }
-        if (distance >= 16)
+        // the copy, in bytes: chunks of 16 or 8 where source and destination are that far apart, else element by element
         {
-            do
+            uint8_t *o = reinterpret_cast<uint8_t *>(out), *const o_stop = reinterpret_cast<uint8_t *>(stop);
+            const size_t gap = distance * sizeof(T);
+            const uint8_t *src = o - gap;
+            if (gap >= 16)
             {
-                store64(out, load64(src));
-                store64(out + 8, load64(src + 8));
-                out += 16;
-                src += 16;
-            } while (out < stop);
-        }
-        else if (distance >= 8)
-        {
-            do
+                do
+                {
+                    store64(o, load64(src));
+                    store64(o + 8, load64(src + 8));
+                    o += 16;
+                    src += 16;
+                } while (o < o_stop);
+            }
+            else if (gap >= 8)
             {
-                store64(out, load64(src));
-                out += 8;
-                src += 8;
-            } while (out < stop);
-        }
-        else if (distance == 1)
-        {
-            const uint64_t v = 0x0101010101010101ull * *src;
-            do
+                do
+                {
+                    store64(o, load64(src));
+                    o += 8;
+                    src += 8;
+                } while (o < o_stop);
+            }
+            else if (sizeof(T) == 1 && distance == 1)
             {
-                store64(out, v);
-                out += 8;
-            } while (out < stop);
-        }
-        else
-        {
-            do
-                *out++ = *src++;
-            while (out < stop);
+                const uint64_t v = 0x0101010101010101ull * *src;
+                do
+                {
+                    store64(o, v);
+                    o += 8;
+                } while (o < o_stop);
+            }
+            else
+            {
+                const T *s = out - distance;
+                do
+                    *out++ = *s++;
+                while (out < stop);
+            }
         }
         out = stop;
         if (!more)
@@ -489,21 +504,21 @@ __attribute__((always_inline)) inline uint8_t *Inflater::fast_body(const uint8_t
     return out;
 }
 
-uint8_t *Inflater::fast_generic(const uint8_t *hist, uint8_t *out, uint8_t *out_end, bool &block_ended)
+template <class T> T *Inflater::fast_generic(const T *hist, T *out, T *out_end, bool &block_ended)
 {
-    return fast_body(hist, out, out_end, block_ended);
+    return fast_body<T>(hist, out, out_end, block_ended);
 }
 #if defined(__x86_64__)
 // the same loop compiled for BMI2: shrx / shlx / bzhi instead of shifts through %cl and mask arithmetic
-__attribute__((target("bmi2"))) uint8_t *Inflater::fast_bmi2(const uint8_t *hist, uint8_t *out, uint8_t *out_end, bool &block_ended)
+template <class T> __attribute__((target("bmi2"))) T *Inflater::fast_bmi2(const T *hist, T *out, T *out_end, bool &block_ended)
 {
-    return fast_body(hist, out, out_end, block_ended);
+    return fast_body<T>(hist, out, out_end, block_ended);
 }
 #endif
 
 // Careful: any amount of input and room; every symbol is checked against the room that is left and undone if it does not fit;
 // bits of the imaginary bytes behind the input may be looked at but not consumed.
-uint8_t *Inflater::careful_loop(const uint8_t *hist, uint8_t *out, uint8_t *out_end, bool &block_ended)
+template <class T> T *Inflater::careful_loop(const T *hist, T *out, T *out_end, bool &block_ended)
 {
     constexpr uint32_t lmask = (1u << kLitBits) - 1, dmask = (1u << kDistBits) - 1;
     const uint32_t *const lit = lit_, *const dist = dist_;
@@ -541,9 +556,9 @@ uint8_t *Inflater::careful_loop(const uint8_t *hist, uint8_t *out, uint8_t *out_
             }
             TXR_CONSUME(e & 0xff);
             check_not_past_end();
-            *out++ = (uint8_t)(e >> 16);
+            *out++ = (T)((e >> 16) & 0xff);
             if (n_lit == 2)
-                *out++ = (uint8_t)(e >> 24);
+                *out++ = (T)(e >> 24);
             continue;
         }
         if (e & kEnd)
@@ -578,7 +593,7 @@ uint8_t *Inflater::careful_loop(const uint8_t *hist, uint8_t *out, uint8_t *out_
             undo();
             return out;
         }
-        const uint8_t *src = out - distance;
+        const T *src = out - distance;
         for (size_t i = 0; i < length; ++i)
             out[i] = src[i];
         out += length;
@@ -587,19 +602,42 @@ uint8_t *Inflater::careful_loop(const uint8_t *hist, uint8_t *out, uint8_t *out_
 #undef TXR_CONSUME
 #undef TXR_VALUE
 
-uint8_t *Inflater::run(const uint8_t *hist, uint8_t *out, uint8_t *out_end)
+uint8_t *Inflater::run(const uint8_t *hist, uint8_t *out, uint8_t *out_end) { return run_t<uint8_t>(hist, out, out_end); }
+uint16_t *Inflater::run16(const uint16_t *hist, uint16_t *out, uint16_t *out_end) { return run_t<uint16_t>(hist, out, out_end); }
+
+uint64_t Inflater::bit_pos() const { return (uint64_t)(p_ - base_) * 8 + 8 * overrun_ - cnt_; }
+
+void Inflater::reset_at_bit(const uint8_t *in, size_t n, uint64_t bit)
 {
+    reset(in, n);
+    p_ = in + (bit >> 3);
+    if (bit & 7)
+        (void)take((unsigned)(bit & 7));
+}
+
+template <class T> T *Inflater::run_t(const T *hist, T *out, T *out_end)
+{
+    stopped_ = false;
     for (;;)
     {
         switch (state_)
         {
         case State::header:
+            if (bit_pos() >= stop_bit_) // a block boundary at or behind the position the caller asked to stop at
+            {
+                stopped_ = true;
+                return out;
+            }
             read_block_header();
             break;
         case State::stored:
         {
             const size_t n = std::min({stored_left_, (size_t)(out_end - out), (size_t)(end_ - p_)});
-            memcpy(out, p_, n);
+            if (sizeof(T) == 1)
+                memcpy(out, p_, n);
+            else
+                for (size_t i = 0; i < n; ++i)
+                    out[i] = (T)p_[i];
             out += n;
             p_ += n;
             stored_left_ -= n;
@@ -620,14 +658,14 @@ uint8_t *Inflater::run(const uint8_t *hist, uint8_t *out, uint8_t *out_end)
 #if defined(__x86_64__)
                 // TAXOR_INFLATE_ISA=generic keeps the baseline build of the loop (tests run both)
                 static const bool bmi2 = __builtin_cpu_supports("bmi2") && !(getenv("TAXOR_INFLATE_ISA") && !strcmp(getenv("TAXOR_INFLATE_ISA"), "generic"));
-                out = bmi2 ? fast_bmi2(hist, out, out_end, ended) : fast_generic(hist, out, out_end, ended);
+                out = bmi2 ? fast_bmi2<T>(hist, out, out_end, ended) : fast_generic<T>(hist, out, out_end, ended);
 #else
-                out = fast_generic(hist, out, out_end, ended);
+                out = fast_generic<T>(hist, out, out_end, ended);
 #endif
             }
             if (!ended)
             {
-                out = careful_loop(hist, out, out_end, ended);
+                out = careful_loop<T>(hist, out, out_end, ended);
                 if (!ended)
                     return out; // the next symbol does not fit
             }

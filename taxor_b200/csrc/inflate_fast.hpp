@@ -28,6 +28,15 @@ public:
     bool done() const { return state_ == State::done; }
     const uint8_t *input_pos() const; // after done(): the first byte behind the stream
 
+    // ---- for decoding a stream in pieces, from several threads (gzip_parallel.cpp) ----
+    // The same with 16-bit output elements: a piece that starts in the middle of a stream does not know the 32 KiB before it;
+    // the caller presets them with marker values >= 256, matches copy the markers along, and they are replaced later.
+    uint16_t *run16(const uint16_t *hist, uint16_t *out, uint16_t *out_end);
+    void reset_at_bit(const uint8_t *in, size_t n, uint64_t bit); // a block header starts at this bit of `in`
+    uint64_t bit_pos() const;                                     // bits of `in` consumed so far
+    void stop_at_block_from(uint64_t bit) { stop_bit_ = bit; }    // run() returns at the first block boundary at or behind `bit`
+    bool stopped() const { return stopped_; }                     // ... and says so here; bit_pos() is that boundary
+
 private:
     enum class State
     {
@@ -45,11 +54,15 @@ private:
     void read_block_header();
     void read_dynamic_tables();
     void use_fixed_tables();
-    uint8_t *fast_body(const uint8_t *hist, uint8_t *out, uint8_t *out_end, bool &block_ended);
-    uint8_t *fast_generic(const uint8_t *hist, uint8_t *out, uint8_t *out_end, bool &block_ended);
-    uint8_t *fast_bmi2(const uint8_t *hist, uint8_t *out, uint8_t *out_end, bool &block_ended);
-    uint8_t *careful_loop(const uint8_t *hist, uint8_t *out, uint8_t *out_end, bool &block_ended);
+    template <class T> T *run_t(const T *hist, T *out, T *out_end);
+    template <class T> T *fast_body(const T *hist, T *out, T *out_end, bool &block_ended);
+    template <class T> T *fast_generic(const T *hist, T *out, T *out_end, bool &block_ended);
+    template <class T> T *fast_bmi2(const T *hist, T *out, T *out_end, bool &block_ended);
+    template <class T> T *careful_loop(const T *hist, T *out, T *out_end, bool &block_ended);
 
+    const uint8_t *base_{nullptr};
+    uint64_t stop_bit_{~uint64_t(0)};
+    bool stopped_{false};
     const uint8_t *p_{nullptr}, *end_{nullptr};
     uint64_t buf_{0};
     unsigned cnt_{0};

@@ -1,7 +1,11 @@
 #include "ingest.hpp"
+#include "gzip_parallel.hpp"
 #include "inflate_fast.hpp"
 
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cstring>
 #include <dlfcn.h>
 #include <fcntl.h>
@@ -140,7 +144,18 @@ RecordScanner::RecordScanner(const std::string &path)
             gzmap_ = static_cast<const unsigned char *>(m);
             gzmap_size_ = (size_t)st.st_size;
             madvise(m, gzmap_size_, MADV_SEQUENTIAL);
-            gzs_ = new GzipStream(gzmap_, gzmap_size_);
+            // one stream, several threads: pieces of the file are inflated speculatively and chained (gzip_parallel.hpp);
+            // TAXOR_GZIP=serial keeps the one-thread decoder
+            unsigned threads = 1;
+#ifdef _OPENMP
+            threads = (unsigned)std::max(1, omp_get_max_threads());
+#endif
+            const char *mode = getenv("TAXOR_GZIP");
+            gz_parallel_ = threads > 1 && gzmap_size_ >= (size_t(4) << 20) && !(mode && !strcmp(mode, "serial"));
+            if (gz_parallel_)
+                gzs_ = new ParallelGzip(gzmap_, gzmap_size_, threads);
+            else
+                gzs_ = new GzipStream(gzmap_, gzmap_size_);
             ::close(fd_);
             fd_ = -1;
             return;
@@ -175,7 +190,10 @@ RecordScanner::~RecordScanner()
     }
     if (bgzf_data_)
         munmap(const_cast<unsigned char *>(bgzf_data_), bgzf_size_);
-    delete static_cast<GzipStream *>(gzs_);
+    if (gz_parallel_)
+        delete static_cast<ParallelGzip *>(gzs_);
+    else
+        delete static_cast<GzipStream *>(gzs_);
     if (gzmap_)
         munmap(const_cast<unsigned char *>(gzmap_), gzmap_size_);
     if (gz_)
@@ -335,7 +353,8 @@ size_t RecordScanner::fill(char *dst, size_t cap)
         return fill_bz2(dst, cap);
     if (gzs_)
     {
-        const size_t n = static_cast<GzipStream *>(gzs_)->read(reinterpret_cast<uint8_t *>(dst), cap);
+        const size_t n = gz_parallel_ ? static_cast<ParallelGzip *>(gzs_)->read(reinterpret_cast<uint8_t *>(dst), cap)
+                                      : static_cast<GzipStream *>(gzs_)->read(reinterpret_cast<uint8_t *>(dst), cap);
         if (n < cap)
             eof_ = true;
         return n;

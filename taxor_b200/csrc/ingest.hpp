@@ -64,7 +64,8 @@ private:
     // input that cannot be mapped and behind TAXOR_GZIP=zlib
     const unsigned char *gzmap_{nullptr};
     size_t gzmap_size_{0};
-    void *gzs_{nullptr}; // GzipStream
+    void *gzs_{nullptr}; // GzipStream, or (several threads, file of some size) ParallelGzip when gz_parallel_ is set
+    bool gz_parallel_{false};
 };
 
 // ---- plain (not gzip) files: mapped, cut into byte segments, segments scanned in parallel ----

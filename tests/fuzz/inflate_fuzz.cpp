@@ -8,6 +8,7 @@
 //      original bytes, never a crash or a read outside the buffers;
 //   4. the carry-less-multiply CRC-32 against zlib's on random lengths and alignments.
 // usage: inflate_fuzz <iterations> <seed>
+#include "../../taxor_b200/csrc/gzip_parallel.hpp"
 #include "../../taxor_b200/csrc/inflate_fast.hpp"
 
 #include <cstdio>
@@ -163,13 +164,42 @@ static bool read_all(const Bytes &gz, std::mt19937_64 &rng, Bytes &out, std::str
     }
 }
 
+// the same through the multi-threaded reader, with pieces small enough that even these inputs are cut many times
+static bool read_all_parallel(const Bytes &gz, std::mt19937_64 &rng, Bytes &out, std::string &err, ParallelGzip::Stats *stats = nullptr)
+{
+    out.clear();
+    try
+    {
+        static const size_t piece_sizes[] = {1024, 3000, 10000, 65536, 300000};
+        ParallelGzip pg(gz.data(), gz.size(), 1 + (unsigned)(rng() % 4), piece_sizes[rng() % 5]);
+        Bytes piece;
+        for (;;)
+        {
+            static const size_t caps[] = {1, 100, 4096, 65536, 1 << 20, 3 << 20};
+            piece.resize(caps[rng() % 6]);
+            const size_t n = pg.read(piece.data(), piece.size());
+            out.insert(out.end(), piece.begin(), piece.begin() + (long)n);
+            if (n < piece.size())
+                break;
+        }
+        if (stats)
+            *stats = pg.stats();
+        return true;
+    }
+    catch (std::runtime_error const &e)
+    {
+        err = e.what();
+        return false;
+    }
+}
+
 int main(int argc, char **argv)
 {
     if (argc < 3)
         return 2;
     const long iters = atol(argv[1]);
     std::mt19937_64 rng((uint64_t)atoll(argv[2]));
-    long n_round = 0, n_damaged = 0, n_rejected = 0, n_raw = 0;
+    long n_round = 0, n_damaged = 0, n_rejected = 0, n_raw = 0, par_bytes = 0, seq_bytes = 0;
     static const int strategies[] = {Z_DEFAULT_STRATEGY, Z_FILTERED, Z_HUFFMAN_ONLY, Z_RLE, Z_FIXED};
     for (long it = 0; it < iters; ++it)
     {
@@ -198,6 +228,21 @@ int main(int argc, char **argv)
             return 1;
         }
         ++n_round;
+        {
+            ParallelGzip::Stats st;
+            if (!read_all_parallel(gz, rng, back, err, &st))
+            {
+                printf("iteration %ld: the parallel reader rejected a valid stream: %s\n", it, err.c_str());
+                return 1;
+            }
+            if (back != whole)
+            {
+                printf("iteration %ld: parallel reader: %zu bytes in, %zu bytes out, contents differ\n", it, whole.size(), back.size());
+                return 1;
+            }
+            par_bytes += (long)st.parallel_bytes;
+            seq_bytes += (long)st.sequential_bytes;
+        }
 
         // 2. the whole-buffer form on a raw stream
         {
@@ -263,6 +308,24 @@ int main(int argc, char **argv)
                 for (size_t j = rng() % bad.size(), e = std::min(bad.size(), j + 1 + rng() % 64); j < e; ++j)
                     bad[j] = (uint8_t)rng();
             }
+            {
+                // the parallel reader on the same damaged bytes: it may differ from the serial one only in WHERE it notices
+                Bytes got2;
+                std::string err2;
+                if (read_all_parallel(bad, rng, got2, err2))
+                {
+                    if (got2.size() > whole.size() || !same(got2.data(), whole.data(), got2.size()))
+                    {
+                        printf("iteration %ld: parallel reader accepted damaged input with different contents\n", it);
+                        return 1;
+                    }
+                }
+                else if (err2.find("corrupt or truncated") == std::string::npos)
+                {
+                    printf("iteration %ld: parallel reader, unexpected error text: %s\n", it, err2.c_str());
+                    return 1;
+                }
+            }
             Bytes got;
             ++n_damaged;
             if (!read_all(bad, rng, got, err))
@@ -298,6 +361,7 @@ int main(int argc, char **argv)
             }
         }
     }
-    printf("fuzz ok: %ld round trips, %ld raw streams, %ld damaged inputs (%ld rejected)\n", n_round, n_raw, n_damaged, n_rejected);
+    printf("fuzz ok: %ld round trips (parallel reader: %ld bytes from pieces, %ld decoded sequentially), %ld raw streams, %ld damaged inputs (%ld rejected)\n",
+           n_round, par_bytes, seq_bytes, n_raw, n_damaged, n_rejected);
     return 0;
 }
