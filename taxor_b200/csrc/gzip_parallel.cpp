@@ -385,7 +385,9 @@ void ParallelGzip::decode_piece(size_t k, Piece &pc)
         }
         pc.found = true;
         pc.start_bit = start;
-        constexpr size_t kMaxOut = size_t(96) << 20; // elements: a piece that inflates beyond this is left to the sequential path
+        // elements: a piece that inflates beyond this (more than 16x at the default piece size) is left to the sequential path,
+        // which needs no memory to speak of -- sequence files compress 2-8x
+        constexpr size_t kMaxOut = size_t(16) << 20;
         {
             const Buffer b = get_buffer(kWindow + std::max<size_t>(4 * (c1 - c0), 1 << 16));
             pc.sym = b.p;
