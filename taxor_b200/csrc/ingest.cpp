@@ -274,12 +274,31 @@ size_t RecordScanner::fill_bgzf(char *dst, size_t cap)
             continue;
         }
         int bad = 0;
+        static const bool use_zlib = getenv("TAXOR_GZIP") && !strcmp(getenv("TAXOR_GZIP"), "zlib");
 #pragma omp parallel for schedule(dynamic, 4) if (blocks.size() > 8)
         for (long i = 0; i < (long)blocks.size(); ++i)
         {
             const Block &b = blocks[(size_t)i];
             uint8_t *const o = reinterpret_cast<uint8_t *>(dst + b.out);
-            if (!inflate_raw_exact(bgzf_data_ + b.in, b.in_len, o, b.out_len) || crc32_fast(0, o, b.out_len) != b.crc)
+            bool good;
+            if (use_zlib) // TAXOR_GZIP=zlib: the round-1 path, kept for A/B runs
+            {
+                z_stream zs{};
+                good = inflateInit2(&zs, -15) == Z_OK;
+                if (good)
+                {
+                    zs.next_in = const_cast<unsigned char *>(bgzf_data_ + b.in);
+                    zs.avail_in = (unsigned)b.in_len;
+                    zs.next_out = o;
+                    zs.avail_out = (unsigned)b.out_len;
+                    const int rc = inflate(&zs, Z_FINISH);
+                    inflateEnd(&zs);
+                    good = rc == Z_STREAM_END && zs.total_out == b.out_len && crc32(0, o, (unsigned)b.out_len) == b.crc;
+                }
+            }
+            else
+                good = inflate_raw_exact(bgzf_data_ + b.in, b.in_len, o, b.out_len) && crc32_fast(0, o, b.out_len) == b.crc;
+            if (!good)
             {
 #pragma omp atomic write
                 bad = 1;
