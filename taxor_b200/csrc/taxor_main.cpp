@@ -503,7 +503,7 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
     Channel<std::function<void()>> jobs;
     // where the phase goes (TAXOR_TIMING=1): seconds the assembler waited for a scanned segment / for a free chunk, seconds the
     // GPU workers spent in txr_search / formatting, seconds the writer spent writing
-    double w_seg = 0, w_chunk = 0, w_write = 0;
+    double w_seg = 0, w_chunk = 0, w_write = 0, w_stream = 0;
     std::atomic<uint64_t> us_search{0}, us_format{0}, us_scan{0}, us_pack{0};
     std::string worker_error;
     std::mutex err_m;
@@ -750,7 +750,10 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
             {
                 RawBuf *rb = nullptr;
                 raw_free.pop(rb);
-                if (!fin.next(rb->data, rb->recs, kRawTarget))
+                const auto t0 = std::chrono::steady_clock::now();
+                const bool more = fin.next(rb->data, rb->recs, kRawTarget);
+                w_stream += since(t0);
+                if (!more)
                     break;
                 std::shared_ptr<RawBuf> hold(rb, [&raw_free](RawBuf *p) { raw_free.push(p); });
                 assemble(hold, rb->data.data(), rb->recs);
@@ -782,7 +785,7 @@ void search_single(const Config &cfg, const std::string &query, const std::strin
                   << fp_bytes / 1e9 << " GB), ingest+search+write " << since(t_search) << " s, " << seq << " chunks, " << n_pack
                   << " pack threads\n"
                   << "[taxor timing]   chunk pool " << t_pool << " s (on its own thread, from the start of the upload); assembler waited " << w_seg << " s for scans, " << w_chunk
-                  << " s for a free chunk; job threads: scan " << us_scan / 1e6 << " s, pack " << us_pack / 1e6 << " s (summed over threads); GPU workers: search "
+                  << " s for a free chunk, spent " << w_stream << " s in the streaming reader (compressed input); job threads: scan " << us_scan / 1e6 << " s, pack " << us_pack / 1e6 << " s (summed over threads); GPU workers: search "
                   << us_search / 1e6 << " s, format " << us_format / 1e6 << " s; writer " << w_write << " s\n";
     }
     // nothing at all matched: with a reference-built index that is what a wrong guess of the (unpinned) record order or
